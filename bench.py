@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — samples/sec of the render hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # our CUDA path
+    python bench.py --impl reference --gpus N ...          # the CPU oracle (restated reference)
+
+A "step" is one full render of the workload: every pixel x sample of
+cornell_box.yml at 1920x1080, 1024 spp, max_depth 20 (BASELINE configs[3], the
+configuration the metric is quoted on; it fits one GPU).  With N > 1 (one
+process per GPU under torchrun) the image is split into interleaved 16x8 tiles
+(tile k -> rank k mod N), every rank renders all samples of its tiles and rank
+0 receives the disjoint tiles with one NCCL reduce of the accumulation buffer
+(SUM over disjoint supports = gather); total work is fixed => "strong" scaling.
+
+`value` is timed with CUDA events on the launching stream with the scene and
+camera already resident on the device; `e2e` runs the same step through the
+public host call (scene + camera upload, render, download of the gamma'd f64
+image into host memory).  The roofline is the FP32 issue roofline of SURVEY
+§8(d): algorithmic flops per sample (cost table x oracle counters) x samples/s
+over the FFMA micro-benchmark measured in this run.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene, width, height, spp, max_depth, split)
+    "cornell_box_1080p_1024spp": ("cornell_box", 1920, 1080, 1024, 20, "tiles"),
+    "clown_4k_4096spp": ("clown", 3840, 2160, 4096, 20, "samples"),
+    "three_balls_600_200spp": ("three_balls", 600, 600, 200, 20, "tiles"),
+    "emissive_600_200spp": ("emissive", 600, 600, 200, 20, "tiles"),
+    "noise_and_textures_600_200spp": ("noise_and_textures", 600, 600, 200, 20, "tiles"),
+}
+
+# Algorithmic FP32 flop cost table, SURVEY.md §8(d) (FMA = 2, SFU = 1)
+COST = {
+    "raygen_accumulate": 40, "node_test": 27, "sphere_test": 23, "sphere_hit_extra": 30,
+    "rect_test": 12, "rect_hit_extra": 20, "lambertian": 50, "metal": 60, "dielectric": 60,
+    "emit_terminate": 6, "tex_checker": 9, "tex_image": 8, "tex_noise": 1650, "sky": 21,
+}
+
+
+def flops_per_sample(cnt: dict, bg_is_sky: bool, linear_prims=None) -> float:
+    """A = 40 + sum over segments [nodes*27 + prims tested + hit extra + scatter + texture] + terminal.
+    linear_prims = (n_spheres, n_rects): brute force over all primitives, N_node = 0."""
+    s = cnt["samples"]
+    f = COST["raygen_accumulate"] * s
+    if linear_prims is None:
+        f += COST["node_test"] * cnt["node_tests"]
+        f += COST["sphere_test"] * cnt["prim_tests"][0] + COST["rect_test"] * sum(cnt["prim_tests"][1:])
+    else:
+        f += cnt["segments"] * (COST["sphere_test"] * linear_prims[0] + COST["rect_test"] * linear_prims[1])
+    f += COST["sphere_hit_extra"] * cnt["prim_hits"][0] + COST["rect_hit_extra"] * sum(cnt["prim_hits"][1:])
+    f += COST["lambertian"] * cnt["scatters"][0] + COST["metal"] * cnt["scatters"][1]
+    f += COST["dielectric"] * cnt["scatters"][2] + COST["emit_terminate"] * cnt["scatters"][3]
+    f += COST["tex_checker"] * cnt["tex_evals"][1] + COST["tex_image"] * cnt["tex_evals"][2]
+    f += COST["tex_noise"] * cnt["tex_evals"][3]
+    if bg_is_sky:
+        f += COST["sky"] * cnt["background"]
+    return f / s
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def oracle_slice(job, params, spp, threads=0):
+    """Time the oracle (restated reference, f64, all host threads) on an spp-slice."""
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    _, cnt = O.render(job, params, rng=O.RNG_SEQUENTIAL, threads=threads, sample_begin=0, sample_count=spp,
+                      linear_sum=True, want_counters=True)
+    dt = time.perf_counter() - t0
+    return params.width * params.height * spp / dt, dt, cnt.as_dict()
+
+
+def run_reference(args, wl_name):
+    """--impl reference: the reference's CPU algorithm (oracle restatement; the Rust
+    reference cannot be built: no cargo/rustc in the image) on all host cores."""
+    from racer_tracer_b200 import capi, harness
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scene, w, h, spp, depth, split = WORKLOADS[wl_name]
+    cfg = harness.load_config(os.path.join(ROOT, "tests", "golden", "config.yml"))
+    job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".yml"), cfg, w, h)
+    params = harness.make_params(w, h, spp, depth, seed=0, sampler=capi.RC_SAMPLER_REJECTION)
+    cores = os.cpu_count() or 1
+    # bounded sample per step: ~4 s of CPU work
+    probe, _, _ = oracle_slice(job, harness.make_params(w // 8, h // 8, spp, depth, sampler=capi.RC_SAMPLER_REJECTION), 4)
+    slice_spp = max(1, min(spp, int(probe * 4.0 / (w * h))))
+    for _ in range(args.warmup):
+        oracle_slice(job, params, 1)
+    t = []
+    for _ in range(args.steps):
+        sps, dt, _ = oracle_slice(job, params, slice_spp)
+        t.append(dt)
+    total = sum(t)
+    value = w * h * slice_spp * args.steps / total
+    line = {
+        "impl": "reference", "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "scene": scene + ".yml", "width": w, "height": h, "spp": spp,
+                   "max_depth": depth},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{slice_spp}-spp slice of the {w}x{h} frame per step, sequential RNG, "
+                                   "rejection samplers, 10x10 tile grid (restated reference, f64)"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cornell_box_1080p_1024spp", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default=os.environ.get("RC_VARIANT", "megakernel"), choices=["megakernel", "wavefront"])
+    ap.add_argument("--sampler", default="direct", choices=["direct", "rejection"])
+    ap.add_argument("--rng-rounds", type=int, default=10)
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling runs only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args, args.workload)
+
+    import torch
+    import torch.distributed as dist
+    from racer_tracer_b200 import capi, harness
+
+    if args.warmup < 3:
+        print(f"note: warmup {args.warmup} < 3; numbers from this run are not valid bench values", file=sys.stderr)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene, w, h, spp, depth, split_name = WORKLOADS[args.workload]
+    if args.spp > 0:
+        spp = args.spp
+    split = capi.RC_SPLIT_TILES if split_name == "tiles" else capi.RC_SPLIT_SAMPLES
+    cfg = harness.load_config(os.path.join(ROOT, "tests", "golden", "config.yml"))
+    job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".yml"), cfg, w, h)
+    variant = capi.RC_VARIANT_MEGAKERNEL if args.variant == "megakernel" else capi.RC_VARIANT_WAVEFRONT
+    sampler = capi.RC_SAMPLER_DIRECT if args.sampler == "direct" else capi.RC_SAMPLER_REJECTION
+    params = harness.make_params(w, h, spp, depth, seed=0, variant=variant, sampler=sampler, split=split,
+                                 rank=rank, world=world, rng_rounds=args.rng_rounds)
+
+    r = harness.CudaRenderer([local_rank])
+    stream = torch.cuda.current_stream()
+    r.set_stream(stream.cuda_stream)
+    r.upload(job)
+    n = w * h * 3
+    accum = torch.zeros(n, dtype=torch.float32, device="cuda")
+    rgb = torch.empty(n, dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 256 MiB > 126 MB L2
+
+    launches = [0]
+
+    def step():
+        accum.zero_()
+        r.render_accumulate(params, accum.data_ptr())
+        launches[0] += int(r.stats().kernel_launches) + 1
+        if world > 1:
+            # exchange step: disjoint tiles (or partial sample sums) summed onto rank 0 over NVLink
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            r.finalize(accum.data_ptr(), w, h, spp, rgb.data_ptr())
+            launches[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler_thread = ClockSampler(local_rank) if rank == 0 else None
+    if sampler_thread:
+        sampler_thread.start()
+    launches[0] = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(float(i))          # L2 flush between timed iterations (outside the events)
+        ev[i][0].record(stream)
+        step()
+        ev[i][1].record(stream)
+        kernel_ms.append(r.stats().gpu_ms)
+    barrier()
+    wall = time.perf_counter() - wall0
+    if sampler_thread:
+        sampler_thread.stop_flag.set()
+        sampler_thread.join()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    total_samples = w * h * spp
+    value = total_samples / (ms_per_step * 1e-3)
+    segs = torch.tensor([float(r.stats().segments)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(segs, op=dist.ReduceOp.SUM)
+
+    # ---- end to end through the public host call (rank-local share; N GPUs run concurrently) ----
+    e2e_steps = max(1, min(args.steps, 3))
+    host_out = np.empty((h, w, 3), dtype=np.float64)
+    scene_bytes = (job.scene.c.n_prims * (4 + 40 + 4 + 4 + 4 + 48) + job.scene.c.n_materials * 16 +
+                   job.scene.c.n_textures * 48 + job.scene.c.n_nodes * 56 + job.scene.c.n_perlin * C.sizeof(capi.rc_perlin) +
+                   sum(im[0] * im[1] * 4 for im in job.scene.images) + C.sizeof(capi.rc_camera) + C.sizeof(capi.rc_params))
+    e2e_params = harness.make_params(w, h, spp, depth, seed=0, variant=variant, sampler=sampler, split=split,
+                                     rank=rank, world=world, rng_rounds=args.rng_rounds)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r.upload(job)                       # host -> device: scene tables + camera
+        if world == 1:
+            host_out[...] = 0
+            out = r.render(e2e_params)      # render + device -> host of the gamma'd f64 image
+        else:
+            accum.zero_()
+            r.render_accumulate(e2e_params, accum.data_ptr())
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                r.finalize(accum.data_ptr(), w, h, spp, rgb.data_ptr())
+                out = rgb.cpu().numpy()
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_samples / float(te.item())
+    d2h = n * (8 if world == 1 else 4)
+
+    if rank == 0:
+        peaks, peaks_kind = measured_peaks()
+        fp32_tflops, lane_ginstr = r.fp32_peak()
+        st = r.stats()
+        line = {
+            "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "scene": scene + ".yml", "width": w, "height": h, "spp": spp,
+                       "max_depth": depth, "variant": args.variant, "sampler": args.sampler,
+                       "rng": f"philox4x32-{args.rng_rounds}", "split": split_name,
+                       "l2": "256 MiB buffer written between timed iterations (flush)",
+                       "parallelism": f"tiles{world}" if split_name == "tiles" else f"samples{world}"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(scene_bytes),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+            "gpu_launches": launches[0],
+            "clocks": sampler_thread.summary() if sampler_thread else None,
+            "wall_s": wall,
+            "segments_per_sample": float(segs.item()) / total_samples,
+            "kernel_ms_rank0": sum(kernel_ms) / len(kernel_ms),
+        }
+        # ---- roofline: FP32 issue + cpu baseline (oracle counters give A) ----
+        cpu = None
+        A = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle as O  # noqa: F401  (checker / baseline only)
+            pr = harness.make_params(w, h, spp, depth, seed=0, sampler=capi.RC_SAMPLER_REJECTION)
+            probe, _, _ = oracle_slice(job, harness.make_params(max(2, w // 8), max(2, h // 8), spp, depth,
+                                                                sampler=capi.RC_SAMPLER_REJECTION), 4)
+            slice_spp = max(1, min(spp, int(probe * 15.0 / (w * h))))
+            sps, dt, cnt = oracle_slice(job, pr, slice_spp)
+            types = job.scene.np["prim_type"]
+            n_sph = int((types == capi.RC_PRIM_SPHERE).sum())
+            A = flops_per_sample(cnt, job.scene.c.bg_type == capi.RC_BG_SKY)
+            A_lin = flops_per_sample(cnt, job.scene.c.bg_type == capi.RC_BG_SKY, (n_sph, len(types) - n_sph))
+            cpu = {"value": sps, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{slice_spp}-spp slice of the full {w}x{h} frame ({dt:.1f} s), restated reference "
+                             "(f64, rejection samplers, sequential RNG, 10x10 tiles, all host threads)",
+                   "segments_per_sample": cnt["segments"] / cnt["samples"],
+                   "flops_per_sample_bvh": A, "flops_per_sample_linear": A_lin}
+        if A is not None:
+            # brute force (N_node = 0) when the scene has <= 8 primitives, else the
+            # oracle's BVH counters
+            A_used = A_lin if job.scene.c.n_prims <= 8 else A
+            achieved = value / world * A_used / 1e12
+            line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": fp32_tflops, "unit": "TFLOP/s",
+                                "frac": achieved / fp32_tflops, "traffic": None,
+                                "peak_source": "FFMA micro-benchmark in this run (rc_fp32_peak), per GPU",
+                                "flops_per_sample": A_used, "lane_ginstr_per_s_peak": lane_ginstr,
+                                "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_kind,
+                                "sm_count": st.sm_count}
+        line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    barrier()
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -297,6 +297,11 @@ int rc_primary_aov(rc_ctx* ctx, const rc_params* params, int32_t precision,
 
 int rc_get_stats(rc_ctx* ctx, rc_stats* out);
 
+/* FP32 (non-tensor) FMA micro-benchmark on device 0: the roofline denominator
+ * of SURVEY §8(d).  Returns achieved TFLOP/s (FMA = 2 flop) of a register-only
+ * FFMA loop filling every SM, and the SM clock implied by it. */
+int rc_fp32_peak(rc_ctx* ctx, double* tflops, double* lane_ginstr_per_s);
+
 /* Text of the last error raised on the calling thread ("" if none). */
 const char* rc_last_error(void);
 

@@ -108,25 +108,86 @@ struct Xoshiro {
     double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }  // gen::<f64>()
 };
 
-const uint32_t TAG_SAMPLE = 0u, TAG_PIXEL = 1u;
+// Stream tags (counter word 3, bits 24..31) — DESIGN.md "RNG streams"; the
+// GPU (racer_tracer_b200/csrc/rt_math.cuh) uses the same table.
+const uint32_t TAG_PIXEL = 1u;   // (pixel, 0, 0, tag): x -> per-pixel u jitter
+const uint32_t TAG_VJIT = 3u;    // (pixel, sample>>2, 0, tag): word sample&3 -> v jitter
+const uint32_t TAG_LENS = 4u;    // (pixel, sample, 0, tag|j): x,y -> lens disk; z -> time
+const uint32_t TAG_BOUNCE = 5u;  // (pixel, sample, (b+1)>>1, tag): b odd -> (x,y), even -> (z,w)
+const uint32_t TAG_REJECT = 6u;  // (pixel, sample, b, tag|j): x,y,z of rejection iteration j
 
-// One sample's random source.  `block(bounce, j)` returns the j-th group of
-// four uniforms in [0,1) of the given bounce (bounce 0 = camera ray).
+inline double u21_from_bits(uint32_t x) { return (double)x * (1.0 / 2097152.0); }  // x < 2^21
+
+// One sample's random source.  With ORACLE_RNG_PHILOX every request maps to a
+// fixed counter, so the values do not depend on call order; with
+// ORACLE_RNG_SEQUENTIAL each request pulls the next uniforms of the stream.
 struct Draws {
     int backend;
     uint32_t key[2];
     int rounds;
     uint32_t pixel, sample;
     Xoshiro* seq;
-    void block(uint32_t tag, uint32_t bounce, uint32_t j, int n_needed, double u[4]) const {
-        if (backend == ORACLE_RNG_PHILOX) {
-            uint32_t ctr[4] = {pixel, tag == TAG_PIXEL ? 0u : sample, bounce, (tag << 24) | j};
-            uint32_t out[4];
-            philox4x32(ctr, key, rounds, out);
-            for (int i = 0; i < 4; ++i) u[i] = u01_from_bits(out[i]);
-        } else {
-            for (int i = 0; i < n_needed; ++i) u[i] = seq->uniform();
-        }
+
+    void words(uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
+        uint32_t ctr[4] = {pixel, c1, c2, c3};
+        philox4x32(ctr, key, rounds, out);
+    }
+    double pixel_jitter() const {  // cpu.rs:35-36
+        if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
+        uint32_t w[4];
+        words(0u, 0u, TAG_PIXEL << 24, w);
+        return u01_from_bits(w[0]);
+    }
+    double v_jitter() const {  // cpu.rs:39-40
+        if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
+        uint32_t w[4];
+        words(sample >> 2, 0u, TAG_VJIT << 24, w);
+        return u01_from_bits(w[sample & 3u]);
+    }
+    // j = 0: the direct lens sample (u1, u2) and the time draw; j >= 1: the
+    // j-th iteration of random_in_unit_disk
+    void lens(uint32_t j, double u[3]) const {
+        if (backend != ORACLE_RNG_PHILOX) { u[0] = seq->uniform(); u[1] = seq->uniform(); u[2] = 0.0; return; }
+        uint32_t w[4];
+        words(sample, 0u, (TAG_LENS << 24) | j, w);
+        for (int i = 0; i < 3; ++i) u[i] = u01_from_bits(w[i]);
+    }
+    double time_u() const {
+        if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
+        double u[3];
+        lens(0, u);
+        return u[2];
+    }
+    // the 64 random bits of bounce b (1-based)
+    void bounce_bits(uint32_t b, uint32_t& lo, uint32_t& hi) const {
+        uint32_t w[4];
+        words(sample, (b + 1u) >> 1, TAG_BOUNCE << 24, w);
+        if (b & 1u) { lo = w[0]; hi = w[1]; } else { lo = w[2]; hi = w[3]; }
+    }
+    void two(uint32_t b, double u[2]) const {     // lambertian, direct
+        if (backend != ORACLE_RNG_PHILOX) { u[0] = seq->uniform(); u[1] = seq->uniform(); return; }
+        uint32_t lo, hi;
+        bounce_bits(b, lo, hi);
+        u[0] = u01_from_bits(lo); u[1] = u01_from_bits(hi);
+    }
+    void three(uint32_t b, double u[3]) const {   // metal, direct: three 21-bit uniforms
+        if (backend != ORACLE_RNG_PHILOX) { for (int i = 0; i < 3; ++i) u[i] = seq->uniform(); return; }
+        uint32_t lo, hi;
+        bounce_bits(b, lo, hi);
+        u[0] = u21_from_bits(lo >> 11); u[1] = u21_from_bits(hi >> 11);
+        u[2] = u21_from_bits(((lo & 0x7FFu) << 10) | (hi & 0x3FFu));
+    }
+    double one(uint32_t b) const {                // dielectric
+        if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
+        uint32_t lo, hi;
+        bounce_bits(b, lo, hi);
+        return u01_from_bits(lo);
+    }
+    void reject(uint32_t b, uint32_t j, double u[3]) const {  // iteration j of a rejection loop
+        if (backend != ORACLE_RNG_PHILOX) { for (int i = 0; i < 3; ++i) u[i] = seq->uniform(); return; }
+        uint32_t w[4];
+        words(sample, b, (TAG_REJECT << 24) | j, w);
+        for (int i = 0; i < 3; ++i) u[i] = u01_from_bits(w[i]);
     }
 };
 
@@ -409,27 +470,26 @@ struct Sampler {
     int mode;
     Counters& cnt;
 
-    // random_in_unit_sphere, vec3.rs:424-430; block offset `first`
+    // random_in_unit_sphere, vec3.rs:424-430
     V3 in_unit_sphere(uint32_t bounce) const {
-        double u[4];
+        double u[3];
         if (mode == RC_SAMPLER_REJECTION) {
             for (uint32_t j = 0;; ++j) {
-                dr.block(TAG_SAMPLE, bounce, j, 3, u);
+                dr.reject(bounce, j, u);
                 cnt.c.rejection_iters++;
                 V3 v = v3(2.0 * u[0] - 1.0, 2.0 * u[1] - 1.0, 2.0 * u[2] - 1.0);  // random_range(-1,1)
                 if (length_squared(v) >= 1.0) continue;
                 return v;
             }
         }
-        dr.block(TAG_SAMPLE, bounce, 0, 3, u);
-        V3 d = sphere_direct(u[0], u[1]);
-        return std::cbrt(u[2]) * d;
+        dr.three(bounce, u);
+        return std::cbrt(u[2]) * sphere_direct(u[0], u[1]);
     }
     // random_unit_vector, vec3.rs:442-444
     V3 unit_vec(uint32_t bounce) const {
         if (mode == RC_SAMPLER_REJECTION) return unit_vector(in_unit_sphere(bounce));
-        double u[4];
-        dr.block(TAG_SAMPLE, bounce, 0, 2, u);
+        double u[2];
+        dr.two(bounce, u);
         return sphere_direct(u[0], u[1]);
     }
     static V3 sphere_direct(double u1, double u2) {
@@ -470,9 +530,7 @@ bool scatter(const rc_scene& sc, const Ray& ray, const HitRecord& rec, uint32_t 
         bool cannot_refract = refraction_ratio * sin_theta > 1.0;
         bool do_reflect = cannot_refract;
         if (!do_reflect) {  // the RNG is drawn only if refraction is possible (short-circuit ||)
-            double u[4];
-            smp.dr.block(TAG_SAMPLE, bounce, 0, 1, u);
-            do_reflect = oracle_reflectance(cos_theta, refraction_ratio) > u[0];
+            do_reflect = oracle_reflectance(cos_theta, refraction_ratio) > smp.dr.one(bounce);
         }
         V3 direction = do_reflect ? reflect(unit_direction, rec.normal)
                                   : refract(unit_direction, rec.normal, refraction_ratio);
@@ -558,45 +616,27 @@ RayImageData trace_sample(const rc_scene& sc, const rc_camera& cam, const rc_par
     if (p.fixed_jitter) {
         v = ((double)y + 0.5) / (double)(p.height - 1);
     } else {
-        double b[4];
-        if (dr.backend == ORACLE_RNG_PHILOX) {
-            dr.block(TAG_SAMPLE, 0, 0, 4, b);
-            v = ((double)y + b[0]) / (double)(p.height - 1);  // cpu.rs:39-40
+        v = ((double)y + dr.v_jitter()) / (double)(p.height - 1);  // cpu.rs:39-40
+        // camera.rs:327: the reference samples the lens even when lens_radius
+        // is 0; the offset is then exactly 0, so the draw is skipped here as on
+        // the GPU (with counter-based streams nothing shifts).
+        if (cam.lens_radius != 0.0 || dr.backend != ORACLE_RNG_PHILOX) {
+            double q[3];
             if (p.sampler == RC_SAMPLER_REJECTION) {
                 for (uint32_t j = 1;; ++j) {  // random_in_unit_disk, util.rs:25-39
-                    double q[4];
-                    dr.block(TAG_SAMPLE, 0, j, 2, q);
+                    dr.lens(j, q);
                     cnt.c.rejection_iters++;
                     dx = 2.0 * q[0] - 1.0; dy = 2.0 * q[1] - 1.0;
                     if (dx * dx + dy * dy >= 1.0) continue;
                     break;
                 }
             } else {
-                double r = std::sqrt(b[1]), phi = 2.0 * PI * b[2];
+                dr.lens(0, q);
+                double r = std::sqrt(q[0]), phi = 2.0 * PI * q[1];
                 dx = r * std::cos(phi); dy = r * std::sin(phi);
             }
-            time = cam.time_a + (cam.time_b - cam.time_a) * b[3];  // camera.rs:335
-        } else {
-            // sequential stream in the reference's call order:
-            // v jitter, disk loop, time
-            dr.block(TAG_SAMPLE, 0, 0, 1, b);
-            v = ((double)y + b[0]) / (double)(p.height - 1);
-            if (p.sampler == RC_SAMPLER_REJECTION) {
-                for (;;) {
-                    dr.block(TAG_SAMPLE, 0, 0, 2, b);
-                    cnt.c.rejection_iters++;
-                    dx = 2.0 * b[0] - 1.0; dy = 2.0 * b[1] - 1.0;
-                    if (dx * dx + dy * dy >= 1.0) continue;
-                    break;
-                }
-            } else {
-                dr.block(TAG_SAMPLE, 0, 0, 2, b);
-                double r = std::sqrt(b[0]), phi = 2.0 * PI * b[1];
-                dx = r * std::cos(phi); dy = r * std::sin(phi);
-            }
-            dr.block(TAG_SAMPLE, 0, 0, 1, b);
-            time = cam.time_a + (cam.time_b - cam.time_a) * b[0];
         }
+        time = cam.time_a + (cam.time_b - cam.time_a) * dr.time_u();  // camera.rs:335
     }
     Ray ray = get_ray(cam, u_pix, v, dx, dy, time);
     cnt.c.samples++;
@@ -605,9 +645,7 @@ RayImageData trace_sample(const rc_scene& sc, const rc_camera& cam, const rc_par
 
 double pixel_u(const rc_params& p, const Draws& dr, int x) {
     if (p.fixed_jitter) return ((double)x + 0.5) / (double)(p.width - 1);
-    double b[4];
-    dr.block(TAG_PIXEL, 0, 0, 1, b);
-    return ((double)x + b[0]) / (double)(p.width - 1);  // cpu.rs:35-36, once per pixel
+    return ((double)x + dr.pixel_jitter()) / (double)(p.width - 1);  // cpu.rs:35-36, once per pixel
 }
 
 struct Tile { int x, y, w, h; };

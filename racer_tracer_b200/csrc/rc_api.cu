@@ -1,0 +1,785 @@
+// rc_api.cu — implementation of the C ABI declared in include/racer_cuda.h.
+// Host-side orchestration only: table conversion (f64 -> fp32), uploads,
+// kernel launches, multi-device partitioning.  No CPU rendering path exists.
+#include "../../include/racer_cuda.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_kernels.cuh"
+#include "rt_wavefront.cuh"
+#include "rc_multi.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(RC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t assign(const std::vector<T>& h) {
+        release();
+        n = h.size();
+        if (n == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    cudaError_t resize(size_t count) {
+        if (count == n && p) return cudaSuccess;
+        release();
+        n = count;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(&p, n * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct DeviceState {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<DevPrim> prims;
+    DevBuf<DevNode> nodes;
+    DevBuf<DevTexture> textures;
+    DevBuf<DevInstance> instances;
+    DevBuf<float4> perlin;
+    DevBuf<uint8_t> perm;
+    DevBuf<DevPrimD> prims_d;
+    DevBuf<int> prim_kind;
+    DevBuf<uint32_t> prim_id;
+    DevBuf<DevNodeD> nodes_d;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> tex;
+    DevBuf<float> accum;
+    DevBuf<double> out64;
+    DevBuf<unsigned long long> counter;
+    WavefrontState wf;
+    int sm_count = 0, clock_khz = 0;
+};
+
+}  // namespace
+
+struct rc_ctx {
+    std::vector<DeviceState> devs;
+    KParams kp;             // scene part filled at upload (device pointers of device 0 patched per launch)
+    AovParamsD aov;
+    int mode = RT_MODE_CONST_LINEAR;
+    size_t smem_bytes = 0;
+    bool has_scene = false, has_camera = false;
+    rc_camera camera;
+    rc_stats stats;
+    MultiState multi;
+};
+
+namespace {
+
+void free_scene(DeviceState& d) {
+    cudaSetDevice(d.device);
+    for (auto t : d.tex) cudaDestroyTextureObject(t);
+    for (auto a : d.arrays) cudaFreeArray(a);
+    d.tex.clear();
+    d.arrays.clear();
+    d.prims.release(); d.nodes.release(); d.textures.release(); d.instances.release();
+    d.perlin.release(); d.perm.release(); d.prims_d.release(); d.prim_kind.release();
+    d.prim_id.release(); d.nodes_d.release();
+}
+
+int validate_scene(const rc_scene* s) {
+    if (!s) return fail(RC_ERR_INVALID, "scene is NULL");
+    if (s->n_prims < 0 || s->n_materials < 0 || s->n_textures < 0 || s->n_images < 0 || s->n_perlin < 0 || s->n_nodes < 0)
+        return fail(RC_ERR_INVALID, "negative table size");
+    if (s->n_prims > 0 && (!s->prim_type || !s->prim_data || !s->prim_material || !s->prim_id))
+        return fail(RC_ERR_INVALID, "primitive arrays missing");
+    if (s->n_images > RT_MAX_IMAGES) return fail(RC_ERR_INVALID, "more than 8 image textures");
+    if (s->n_prims >= (1 << 24)) return fail(RC_ERR_INVALID, "too many primitives");
+    for (int i = 0; i < s->n_prims; ++i) {
+        if (s->prim_type[i] < 0 || s->prim_type[i] > 3) return fail(RC_ERR_INVALID, "unknown primitive type");
+        int m = s->prim_material[i];
+        if (m < 0 || m >= s->n_materials) return fail(RC_ERR_INVALID, "primitive material index out of range");
+        if (s->prim_id[i] == 0) return fail(RC_ERR_INVALID, "object id 0 is reserved for a miss");
+        if (s->prim_instance && s->n_instances > 0 && s->prim_instance[i] >= s->n_instances)
+            return fail(RC_ERR_INVALID, "primitive instance index out of range");
+    }
+    for (int i = 0; i < s->n_materials; ++i) {
+        const rc_material& m = s->materials[i];
+        if (m.type < 0 || m.type > 3) return fail(RC_ERR_INVALID, "unknown material type");
+        if (m.type != RC_MAT_DIELECTRIC && (m.texture < 0 || m.texture >= s->n_textures))
+            return fail(RC_ERR_INVALID, "material texture index out of range");
+    }
+    for (int i = 0; i < s->n_textures; ++i) {
+        const rc_texture& t = s->textures[i];
+        if (t.type < 0 || t.type > 3) return fail(RC_ERR_INVALID, "unknown texture type");
+        if (t.type == RC_TEX_CHECKER && (t.a < 0 || t.a >= s->n_textures || t.b < 0 || t.b >= s->n_textures))
+            return fail(RC_ERR_INVALID, "checker child texture out of range");
+        if (t.type == RC_TEX_IMAGE && (t.a < 0 || t.a >= s->n_images)) return fail(RC_ERR_INVALID, "image index out of range");
+        if (t.type == RC_TEX_NOISE && (t.a < 0 || t.a >= s->n_perlin)) return fail(RC_ERR_INVALID, "perlin index out of range");
+    }
+    for (int i = 0; i < s->n_nodes; ++i) {
+        const rc_bvh_node& n = s->nodes[i];
+        if (n.left >= 0) {
+            if (n.left != i + 1 || n.right <= n.left || n.right >= s->n_nodes)
+                return fail(RC_ERR_INVALID, "BVH nodes must be stored in pre-order (left child = index + 1)");
+        } else {
+            int first = ~n.left;
+            if (first < 0 || n.right < 1 || n.right > 127 || first + n.right > s->n_prims)
+                return fail(RC_ERR_INVALID, "BVH leaf range out of bounds");
+        }
+    }
+    if (s->n_instances > 0 && s->prim_instance)
+        for (int i = 0; i < s->n_prims; ++i)
+            if (s->prim_instance[i] >= 0)
+                return fail(RC_ERR_INVALID, "instanced primitives (Box/RotateY/Translate) are not supported by this build");
+    return RC_OK;
+}
+
+inline float4 f4(double x, double y, double z, float w) { return make_float4((float)x, (float)y, (float)z, w); }
+inline float bits(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline float ubits(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+
+// next float toward -inf / +inf, then a relative pad: the fp32 boxes must
+// contain the f64 boxes and tolerate fp32 slab arithmetic
+inline float pad_lo(double v, double ext) { return (float)(v - (1e-6 * ext + 1e-6 * std::fabs(v) + 1e-30)); }
+inline float pad_hi(double v, double ext) { return (float)(v + (1e-6 * ext + 1e-6 * std::fabs(v) + 1e-30)); }
+
+void set_skip(const rc_scene* s, int i, int skip, std::vector<int>& out) {
+    out[i] = skip;
+    const rc_bvh_node& n = s->nodes[i];
+    if (n.left >= 0) {
+        set_skip(s, n.left, n.right, out);
+        set_skip(s, n.right, skip, out);
+    }
+}
+
+int pick_mode(const rc_scene* s, size_t& smem_bytes) {
+    const char* force = std::getenv("RC_SCENE_MODE");  // experiments: const | smem | global | smemlin
+    size_t perlin_bytes = (size_t)s->n_perlin * (256 * 16 + 768);
+    size_t bvh_bytes = (size_t)s->n_nodes * sizeof(DevNode) + (size_t)s->n_prims * sizeof(DevPrim);
+    int mode;
+    if (s->n_prims <= RT_MAX_CONST_PRIMS) mode = RT_MODE_CONST_LINEAR;
+    else if (s->n_nodes > 0 && bvh_bytes + perlin_bytes <= 200 * 1024) mode = RT_MODE_SMEM_BVH;
+    else if (s->n_nodes > 0) mode = RT_MODE_GLOBAL_BVH;
+    else mode = RT_MODE_SMEM_LINEAR;
+    if (force) {
+        std::string f(force);
+        if (f == "const" && s->n_prims <= RT_MAX_CONST_PRIMS) mode = RT_MODE_CONST_LINEAR;
+        else if (f == "smem" && s->n_nodes > 0) mode = RT_MODE_SMEM_BVH;
+        else if (f == "global" && s->n_nodes > 0) mode = RT_MODE_GLOBAL_BVH;
+        else if (f == "smemlin") mode = RT_MODE_SMEM_LINEAR;
+    }
+    smem_bytes = perlin_bytes;
+    if (mode == RT_MODE_SMEM_BVH) smem_bytes += bvh_bytes;
+    if (mode == RT_MODE_SMEM_LINEAR) smem_bytes += (size_t)s->n_prims * sizeof(DevPrim);
+    return mode;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return RC_OK;
+}
+
+template <int MODE>
+int launch_mega_mode(const KParams& kp, float* accum, int sampler, int rounds, int blocks, size_t smem, cudaStream_t st) {
+#define RC_LAUNCH(S, R)                                                                         \
+    do {                                                                                        \
+        int rc__ = set_smem(megakernel_render<MODE, S, R>, smem);                               \
+        if (rc__ != RC_OK) return rc__;                                                         \
+        megakernel_render<MODE, S, R><<<blocks, RT_BLOCK, smem, st>>>(kp, accum);               \
+    } while (0)
+    if (rounds == 7) { if (sampler == RC_SAMPLER_REJECTION) RC_LAUNCH(1, 7); else RC_LAUNCH(0, 7); }
+    else { if (sampler == RC_SAMPLER_REJECTION) RC_LAUNCH(1, 10); else RC_LAUNCH(0, 10); }
+#undef RC_LAUNCH
+    CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}
+
+int launch_mega(int mode, const KParams& kp, float* accum, int sampler, int rounds, int blocks, size_t smem, cudaStream_t st) {
+    switch (mode) {
+    case RT_MODE_CONST_LINEAR: return launch_mega_mode<RT_MODE_CONST_LINEAR>(kp, accum, sampler, rounds, blocks, smem, st);
+    case RT_MODE_SMEM_BVH: return launch_mega_mode<RT_MODE_SMEM_BVH>(kp, accum, sampler, rounds, blocks, smem, st);
+    case RT_MODE_GLOBAL_BVH: return launch_mega_mode<RT_MODE_GLOBAL_BVH>(kp, accum, sampler, rounds, blocks, smem, st);
+    default: return launch_mega_mode<RT_MODE_SMEM_LINEAR>(kp, accum, sampler, rounds, blocks, smem, st);
+    }
+}
+
+int check_params(const rc_params* p) {
+    if (!p) return fail(RC_ERR_INVALID, "params is NULL");
+    if (p->width < 2 || p->height < 2) return fail(RC_ERR_INVALID, "width and height must be >= 2 (u = x/(W-1), cpu.rs:35-40)");
+    if (p->samples < 1) return fail(RC_ERR_INVALID, "samples must be >= 1");
+    if (p->max_depth < 0) return fail(RC_ERR_INVALID, "max_depth must be >= 0");
+    if (p->world < 0 || p->rank < 0 || (p->world > 0 && p->rank >= p->world)) return fail(RC_ERR_INVALID, "bad rank/world");
+    if (p->rng_rounds != 0 && p->rng_rounds != 7 && p->rng_rounds != 10) return fail(RC_ERR_INVALID, "rng_rounds must be 0, 7 or 10");
+    if (p->variant != RC_VARIANT_MEGAKERNEL && p->variant != RC_VARIANT_WAVEFRONT) return fail(RC_ERR_INVALID, "unknown variant");
+    if (p->sampler != RC_SAMPLER_DIRECT && p->sampler != RC_SAMPLER_REJECTION) return fail(RC_ERR_INVALID, "unknown sampler");
+    if (p->split != RC_SPLIT_TILES && p->split != RC_SPLIT_SAMPLES) return fail(RC_ERR_INVALID, "unknown split");
+    return RC_OK;
+}
+
+// Fill the per-launch part of KParams for participant `part` of `parts`.
+void partition(KParams& kp, const rc_params* p, int part, int parts) {
+    kp.width = p->width; kp.height = p->height;
+    kp.max_depth = p->max_depth;
+    kp.fixed_jitter = p->fixed_jitter;
+    kp.key0 = (uint32_t)p->seed; kp.key1 = (uint32_t)(p->seed >> 32);
+    kp.tile_w = RT_TILE_W; kp.tile_h = RT_TILE_H;
+    kp.tiles_x = (p->width + RT_TILE_W - 1) / RT_TILE_W;
+    int tiles_y = (p->height + RT_TILE_H - 1) / RT_TILE_H;
+    int total = kp.tiles_x * tiles_y;
+    if (p->split == RC_SPLIT_SAMPLES) {
+        // contiguous sample slices; every participant traces all tiles
+        kp.tile_first = 0; kp.tile_stride = 1; kp.n_tiles = total;
+        long long lo = (long long)p->samples * part / parts, hi = (long long)p->samples * (part + 1) / parts;
+        kp.s_begin = (int)lo; kp.s_end = (int)hi;
+    } else {
+        // interleaved tiles: tile k -> participant k mod parts
+        kp.tile_first = part; kp.tile_stride = parts;
+        kp.n_tiles = part < total ? (total - part + parts - 1) / parts : 0;
+        kp.s_begin = 0; kp.s_end = p->samples;
+    }
+}
+
+bool cancelled(const volatile int32_t* cancel) { return cancel && *cancel != 0; }
+
+// Trace this context's share into each device's own accumulation buffer
+// (device 0 uses `accum0`).  Does not gather.
+int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile int32_t* cancel, bool& was_cancelled) {
+    was_cancelled = false;
+    const int n_dev = (int)ctx->devs.size();
+    const int world = p->world > 0 ? p->world : 1;
+    const int parts = world * n_dev;
+    const int rounds = p->rng_rounds ? p->rng_rounds : 10;
+    uint64_t launches = 0;
+    for (int k = 0; k < n_dev; ++k) {
+        DeviceState& d = ctx->devs[k];
+        CUDA_TRY(cudaSetDevice(d.device));
+        if (k == 0) CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.counter.p, 0, sizeof(unsigned long long), d.stream));
+    }
+    // passes: one launch per device when no cancel flag is given, otherwise
+    // slices of the sample range with a poll in between (do_cancel per row,
+    // src/renderer/cpu.rs:55-62)
+    for (int k = 0; k < n_dev; ++k) {
+        DeviceState& d = ctx->devs[k];
+        CUDA_TRY(cudaSetDevice(d.device));
+        KParams kp = ctx->kp;
+        kp.prims = d.prims.p; kp.nodes = d.nodes.p; kp.textures = d.textures.p; kp.instances = d.instances.p;
+        kp.perlin = d.perlin.p; kp.perlin_perm = d.perm.p;
+        for (size_t i = 0; i < d.tex.size(); ++i) kp.images[i] = d.tex[i];
+        kp.segment_counter = d.counter.p;
+        partition(kp, p, p->rank * n_dev + k, parts);
+        float* accum = (k == 0) ? accum0 : d.accum.p;
+        if (kp.n_tiles == 0 || kp.s_end <= kp.s_begin) continue;
+        if (p->variant == RC_VARIANT_WAVEFRONT) {
+            int rc = wavefront_render(d.wf, ctx->mode, kp, accum, p->sampler, rounds, ctx->smem_bytes, d.stream, d.sm_count, launches);
+            if (rc != RC_OK) return fail(rc, "wavefront launch failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
+            continue;
+        }
+        const int s0 = kp.s_begin, s1 = kp.s_end;
+        const int step = cancel ? 32 : (s1 - s0);
+        for (int s = s0; s < s1; s += step) {
+            kp.s_begin = s; kp.s_end = s + step < s1 ? s + step : s1;
+            int rc = launch_mega(ctx->mode, kp, accum, p->sampler, rounds, kp.n_tiles, ctx->smem_bytes, d.stream);
+            if (rc != RC_OK) return rc;
+            ++launches;
+            if (cancel && n_dev == 1) {
+                CUDA_TRY(cudaStreamSynchronize(d.stream));
+                if (cancelled(cancel)) { was_cancelled = true; return RC_OK; }
+            }
+        }
+    }
+    ctx->stats.kernel_launches = launches;
+    return RC_OK;
+}
+
+int ensure_accum(rc_ctx* ctx, const rc_params* p, bool device0_too) {
+    size_t n = (size_t)p->width * p->height * 3;
+    for (size_t k = device0_too ? 0 : 1; k < ctx->devs.size(); ++k) {
+        DeviceState& d = ctx->devs[k];
+        CUDA_TRY(cudaSetDevice(d.device));
+        CUDA_TRY(d.accum.resize(n));
+        CUDA_TRY(cudaMemsetAsync(d.accum.p, 0, n * sizeof(float), d.stream));
+    }
+    return RC_OK;
+}
+
+int finish_stats(rc_ctx* ctx, const rc_params* p) {
+    DeviceState& d0 = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d0.device));
+    CUDA_TRY(cudaEventRecord(d0.ev1, d0.stream));
+    CUDA_TRY(cudaEventSynchronize(d0.ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, d0.ev0, d0.ev1));
+    ctx->stats.gpu_ms = ms;
+    uint64_t segs = 0;
+    for (auto& d : ctx->devs) {
+        unsigned long long v = 0;
+        CUDA_TRY(cudaSetDevice(d.device));
+        CUDA_TRY(cudaMemcpy(&v, d.counter.p, sizeof(v), cudaMemcpyDeviceToHost));
+        segs += v;
+    }
+    ctx->stats.segments = segs;
+    const int world = p->world > 0 ? p->world : 1;
+    ctx->stats.samples = (uint64_t)p->width * p->height * p->samples / world;
+    CUDA_TRY(cudaSetDevice(d0.device));
+    return RC_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* rc_last_error(void) { return g_last_error.c_str(); }
+int rc_abi_version(void) { return RC_ABI_VERSION; }
+
+int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
+    if (!out) return fail(RC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RC_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                          " (there is no CPU fallback for the render path)");
+    if (n <= 0) n = 1;
+    rc_ctx* ctx = new rc_ctx();
+    std::memset(&ctx->kp, 0, sizeof(ctx->kp));
+    std::memset(&ctx->aov, 0, sizeof(ctx->aov));
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->devs.resize(n);
+    for (int k = 0; k < n; ++k) {
+        DeviceState& d = ctx->devs[k];
+        d.device = devices ? devices[k] : k;
+        if (d.device < 0 || d.device >= count) {
+            delete ctx;
+            return fail(RC_ERR_NO_DEVICE, "device ordinal out of range");
+        }
+        cudaError_t err = cudaSetDevice(d.device);
+        if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (err == cudaSuccess) err = cudaEventCreate(&d.ev0);
+        if (err == cudaSuccess) err = cudaEventCreate(&d.ev1);
+        if (err == cudaSuccess) err = d.counter.resize(1);
+        cudaDeviceProp prop;
+        if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, d.device);
+        if (err != cudaSuccess) {
+            delete ctx;
+            return fail(RC_ERR_CUDA, std::string("device setup failed: ") + cudaGetErrorString(err));
+        }
+        d.sm_count = prop.multiProcessorCount;
+        d.clock_khz = prop.clockRate;
+    }
+    ctx->stats.n_devices = n;
+    ctx->stats.sm_count = ctx->devs[0].sm_count;
+    ctx->stats.sm_clock_khz = ctx->devs[0].clock_khz;
+    int rc = multi_init(ctx->multi, ctx->devs.size(), [&](size_t k) { return ctx->devs[k].device; });
+    if (rc != RC_OK) {
+        delete ctx;
+        return fail(rc, "peer access setup failed");
+    }
+    cudaSetDevice(ctx->devs[0].device);
+    *out = ctx;
+    return RC_OK;
+}
+
+int rc_destroy(rc_ctx* ctx) {
+    if (!ctx) return RC_OK;
+    multi_destroy(ctx->multi);
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.device);
+        cudaDeviceSynchronize();
+        free_scene(d);
+        d.accum.release(); d.out64.release(); d.counter.release();
+        wavefront_release(d.wf);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+    return RC_OK;
+}
+
+int rc_set_stream(rc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
+    DeviceState& d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    if (d.own_stream && d.stream) CUDA_TRY(cudaStreamDestroy(d.stream));
+    d.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    d.own_stream = false;
+    return RC_OK;
+}
+
+int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
+    if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
+    int rc = validate_scene(s);
+    if (rc != RC_OK) return rc;
+
+    // ---- fp32 + f64 primitive tables ----
+    std::vector<DevPrim> prims(s->n_prims);
+    std::vector<DevPrimD> prims_d(s->n_prims);
+    std::vector<int> kinds(s->n_prims);
+    std::vector<uint32_t> ids(s->n_prims);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < s->n_prims; ++i) {
+        const double* d = s->prim_data + 5 * (size_t)i;
+        const rc_material& m = s->materials[s->prim_material[i]];
+        int type = s->prim_type[i];
+        DevPrim& p = prims[i];
+        DevPrimD& q = prims_d[i];
+        for (int k = 0; k < 4; ++k) q.a[k] = d[k];
+        if (type == RC_PRIM_SPHERE) {
+            double cc = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] - d[3] * d[3];
+            p.a = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
+            p.b.x = (float)cc;
+            q.k_or_cc = cc;
+        } else {
+            p.a = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
+            p.b.x = (float)d[4];
+            q.k_or_cc = d[4];
+        }
+        p.b.y = (float)m.param;
+        int tex_type = RT_TEX_SOLID, tex_index = -1;
+        double col[3] = {1.0, 1.0, 1.0};
+        if (m.type != RC_MAT_DIELECTRIC) {
+            const rc_texture& t = s->textures[m.texture];
+            tex_type = t.type;
+            tex_index = m.texture;
+            if (t.type == RC_TEX_SOLID) { col[0] = t.color[0]; col[1] = t.color[1]; col[2] = t.color[2]; tex_index = -1; }
+        }
+        int inst = (s->prim_instance && s->n_instances > 0) ? s->prim_instance[i] : -1;
+        int packed = type | (m.type << 4) | (tex_type << 8) | ((inst + 1) << 12);
+        p.b.z = bits(packed);
+        p.b.w = bits(tex_index);
+        p.c = f4(col[0], col[1], col[2], ubits(s->prim_id[i]));
+        kinds[i] = type;
+        ids[i] = s->prim_id[i];
+        if (s->prim_aabb)
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = std::fmin(lo[a], s->prim_aabb[6 * i + a]);
+                hi[a] = std::fmax(hi[a], s->prim_aabb[6 * i + 3 + a]);
+            }
+    }
+    // ---- threaded BVH ----
+    std::vector<DevNode> nodes(s->n_nodes);
+    std::vector<DevNodeD> nodes_d(s->n_nodes);
+    if (s->n_nodes > 0) {
+        std::vector<int> skip(s->n_nodes, s->n_nodes);
+        set_skip(s, 0, s->n_nodes, skip);
+        for (int i = 0; i < s->n_nodes; ++i) {
+            const rc_bvh_node& n = s->nodes[i];
+            int leaf = n.left < 0 ? ((~n.left) | (n.right << 24)) : -1;
+            double ext = 0;
+            for (int a = 0; a < 3; ++a) ext = std::fmax(ext, n.bmax[a] - n.bmin[a]);
+            nodes[i].lo = make_float4(pad_lo(n.bmin[0], ext), pad_lo(n.bmin[1], ext), pad_lo(n.bmin[2], ext), bits(skip[i]));
+            nodes[i].hi = make_float4(pad_hi(n.bmax[0], ext), pad_hi(n.bmax[1], ext), pad_hi(n.bmax[2], ext), bits(leaf));
+            for (int a = 0; a < 3; ++a) { nodes_d[i].lo[a] = n.bmin[a]; nodes_d[i].hi[a] = n.bmax[a]; }
+            nodes_d[i].skip = skip[i];
+            nodes_d[i].leaf = leaf;
+        }
+    }
+    std::vector<DevTexture> textures(s->n_textures);
+    for (int i = 0; i < s->n_textures; ++i) {
+        const rc_texture& t = s->textures[i];
+        textures[i].type = t.type; textures[i].a = t.a; textures[i].b = t.b;
+        textures[i].scale = (float)t.scale;
+        textures[i].color = f4(t.color[0], t.color[1], t.color[2], 0.f);
+    }
+    std::vector<float4> perlin((size_t)s->n_perlin * 256);
+    std::vector<uint8_t> perm((size_t)s->n_perlin * 768);
+    for (int k = 0; k < s->n_perlin; ++k)
+        for (int i = 0; i < 256; ++i) {
+            const rc_perlin& pl = s->perlin[k];
+            perlin[(size_t)k * 256 + i] = f4(pl.ran_vec[i][0], pl.ran_vec[i][1], pl.ran_vec[i][2], 0.f);
+            perm[(size_t)k * 768 + i] = (uint8_t)(pl.perm_x[i] & 255);
+            perm[(size_t)k * 768 + 256 + i] = (uint8_t)(pl.perm_y[i] & 255);
+            perm[(size_t)k * 768 + 512 + i] = (uint8_t)(pl.perm_z[i] & 255);
+        }
+
+    KParams& kp = ctx->kp;
+    kp.n_prims = s->n_prims; kp.n_nodes = s->n_nodes; kp.n_perlin = s->n_perlin;
+    kp.bg_a = f4(s->bg_a[0], s->bg_a[1], s->bg_a[2], bits(s->bg_type));
+    kp.bg_b = f4(s->bg_b[0], s->bg_b[1], s->bg_b[2], 0.f);
+    for (int i = 0; i < RT_MAX_CONST_PRIMS; ++i)
+        if (i < s->n_prims) kp.cprims[i] = prims[i]; else std::memset(&kp.cprims[i], 0, sizeof(DevPrim));
+    for (int i = 0; i < RT_MAX_IMAGES; ++i) {
+        kp.image_w[i] = i < s->n_images ? s->images[i].width : 0;
+        kp.image_h[i] = i < s->n_images ? s->images[i].height : 0;
+    }
+    ctx->mode = pick_mode(s, ctx->smem_bytes);
+    ctx->aov.n_prims = s->n_prims; ctx->aov.n_nodes = s->n_nodes;
+
+    for (auto& d : ctx->devs) {
+        free_scene(d);
+        CUDA_TRY(cudaSetDevice(d.device));
+        CUDA_TRY(d.prims.assign(prims));
+        CUDA_TRY(d.nodes.assign(nodes));
+        CUDA_TRY(d.textures.assign(textures));
+        CUDA_TRY(d.perlin.assign(perlin));
+        CUDA_TRY(d.perm.assign(perm));
+        CUDA_TRY(d.prims_d.assign(prims_d));
+        CUDA_TRY(d.prim_kind.assign(kinds));
+        CUDA_TRY(d.prim_id.assign(ids));
+        CUDA_TRY(d.nodes_d.assign(nodes_d));
+        for (int i = 0; i < s->n_images; ++i) {
+            // image textures as CUDA texture objects: point filter, clamp, u8 -> float/255
+            // (src/texture/image.rs:28-51, Q21)
+            const rc_image& im = s->images[i];
+            if (im.width <= 0 || im.height <= 0 || !im.rgba) return fail(RC_ERR_INVALID, "empty image texture");
+            cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+            cudaArray_t arr;
+            CUDA_TRY(cudaMallocArray(&arr, &desc, im.width, im.height));
+            d.arrays.push_back(arr);
+            CUDA_TRY(cudaMemcpy2DToArray(arr, 0, 0, im.rgba, (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyHostToDevice));
+            cudaResourceDesc res;
+            std::memset(&res, 0, sizeof(res));
+            res.resType = cudaResourceTypeArray;
+            res.res.array.array = arr;
+            cudaTextureDesc td;
+            std::memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;
+            td.readMode = cudaReadModeNormalizedFloat;
+            td.normalizedCoords = 0;
+            cudaTextureObject_t tex;
+            CUDA_TRY(cudaCreateTextureObject(&tex, &res, &td, nullptr));
+            d.tex.push_back(tex);
+        }
+    }
+    CUDA_TRY(cudaSetDevice(ctx->devs[0].device));
+    ctx->has_scene = true;
+    return RC_OK;
+}
+
+int rc_set_camera(rc_ctx* ctx, const rc_camera* c) {
+    if (!ctx || !c) return fail(RC_ERR_INVALID, "ctx or camera is NULL");
+    ctx->camera = *c;
+    auto v3f = [](const double* p) { return mk3<float>((float)p[0], (float)p[1], (float)p[2]); };
+    auto v3d = [](const double* p) { return mk3<double>(p[0], p[1], p[2]); };
+    // (upper_left_corner - origin) is formed in f64 here so the fp32 kernels
+    // never subtract two large, nearly equal coordinates
+    double rel[3] = {c->upper_left_corner[0] - c->origin[0], c->upper_left_corner[1] - c->origin[1],
+                     c->upper_left_corner[2] - c->origin[2]};
+    DevCamera<float>& f = ctx->kp.cam;
+    f.origin = v3f(c->origin); f.upper_left_corner = v3f(rel); f.right = v3f(c->right); f.up = v3f(c->up);
+    f.horizontal = v3f(c->horizontal); f.vertical = v3f(c->vertical);
+    f.lens_radius = (float)c->lens_radius; f.time_a = (float)c->time_a; f.time_b = (float)c->time_b;
+    ctx->kp.lens_enabled = c->lens_radius != 0.0;
+    DevCamera<double>& g = ctx->aov.cam;
+    g.origin = v3d(c->origin); g.upper_left_corner = v3d(c->upper_left_corner); g.right = v3d(c->right); g.up = v3d(c->up);
+    g.horizontal = v3d(c->horizontal); g.vertical = v3d(c->vertical);
+    g.lens_radius = c->lens_radius; g.time_a = c->time_a; g.time_b = c->time_b;
+    ctx->has_camera = true;
+    return RC_OK;
+}
+
+int rc_render_accumulate(rc_ctx* ctx, const rc_params* p, float* d_accum, const volatile int32_t* cancel) {
+    if (!ctx || !d_accum) return fail(RC_ERR_INVALID, "ctx or d_accum is NULL");
+    int rc = check_params(p);
+    if (rc != RC_OK) return rc;
+    if (!ctx->has_scene || !ctx->has_camera) return fail(RC_ERR_STATE, "upload a scene and set a camera first");
+    if (cancelled(cancel)) return fail(RC_ERR_CANCELLED, "cancel flag set before the render started");
+    rc = ensure_accum(ctx, p, false);
+    if (rc != RC_OK) return rc;
+    bool was_cancelled = false;
+    rc = trace_share(ctx, p, d_accum, cancel, was_cancelled);
+    if (rc != RC_OK) return rc;
+    if (!was_cancelled && ctx->devs.size() > 1) {
+        rc = multi_gather(ctx->multi, p->split, (size_t)p->width * p->height * 3, d_accum,
+                          [&](size_t k) { return ctx->devs[k].accum.p; },
+                          [&](size_t k) { return ctx->devs[k].stream; },
+                          [&](size_t k) { return ctx->devs[k].device; });
+        if (rc != RC_OK) return fail(rc, std::string("multi-device gather failed: ") + multi_error(ctx->multi));
+    }
+    return finish_stats(ctx, p);
+}
+
+int rc_finalize(rc_ctx* ctx, const float* d_accum, int32_t width, int32_t height, int32_t samples, float* d_rgb) {
+    if (!ctx || !d_accum || !d_rgb || samples < 1) return fail(RC_ERR_INVALID, "bad finalize arguments");
+    DeviceState& d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    size_t n = (size_t)width * height * 3;
+    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(d_accum, d_rgb, n, 1.0f / (float)samples);
+    CUDA_TRY(cudaGetLastError());
+    return RC_OK;
+}
+
+int rc_render(rc_ctx* ctx, const rc_params* p, double* out_rgb, const volatile int32_t* cancel) {
+    if (!ctx || !out_rgb) return fail(RC_ERR_INVALID, "ctx or out_rgb is NULL");
+    int rc = check_params(p);
+    if (rc != RC_OK) return rc;
+    if (!ctx->has_scene || !ctx->has_camera) return fail(RC_ERR_STATE, "upload a scene and set a camera first");
+    if (cancelled(cancel)) return fail(RC_ERR_CANCELLED, "cancel flag set before the render started");
+    DeviceState& d0 = ctx->devs[0];
+    size_t n = (size_t)p->width * p->height * 3;
+    rc = ensure_accum(ctx, p, true);
+    if (rc != RC_OK) return rc;
+    bool was_cancelled = false;
+    rc = trace_share(ctx, p, d0.accum.p, cancel, was_cancelled);
+    if (rc != RC_OK) return rc;
+    if (was_cancelled) return RC_OK;  // a cancelled render writes nothing, cpu.rs:55-62
+    if (ctx->devs.size() > 1) {
+        rc = multi_gather(ctx->multi, p->split, n, d0.accum.p,
+                          [&](size_t k) { return ctx->devs[k].accum.p; },
+                          [&](size_t k) { return ctx->devs[k].stream; },
+                          [&](size_t k) { return ctx->devs[k].device; });
+        if (rc != RC_OK) return fail(rc, std::string("multi-device gather failed: ") + multi_error(ctx->multi));
+    }
+    CUDA_TRY(cudaSetDevice(d0.device));
+    CUDA_TRY(d0.out64.resize(n));
+    finalize_to_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d0.stream>>>(d0.accum.p, d0.out64.p, n, 1.0 / (double)p->samples);
+    CUDA_TRY(cudaGetLastError());
+    rc = finish_stats(ctx, p);
+    if (rc != RC_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, d0.out64.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(cudaStreamSynchronize(d0.stream));
+    return RC_OK;
+}
+
+int rc_postprocess(rc_ctx* ctx, const rc_tone_map* tm, const double* rgb, int32_t width, int32_t height,
+                   uint8_t* rgba, double* rgb_out) {
+    if (!ctx || !tm || !rgb || width < 1 || height < 1) return fail(RC_ERR_INVALID, "bad postprocess arguments");
+    if (tm->type < 0 || tm->type > 3) return fail(RC_ERR_INVALID, "unknown tone map");
+    DeviceState& d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    size_t np = (size_t)width * height;
+    DevBuf<double> in, mapped;
+    DevBuf<uint8_t> q;
+    CUDA_TRY(in.resize(np * 3));
+    CUDA_TRY(mapped.resize(np * 3));
+    CUDA_TRY(q.resize(np * 4));
+    ToneParams tp;
+    std::memset(&tp, 0, sizeof(tp));
+    tp.type = tm->type;
+    tp.max_white_pow = tm->max_white * tm->max_white;  // reinhard.rs:10-14
+    tp.A = tm->hable[0]; tp.B = tm->hable[1]; tp.C = tm->hable[2]; tp.D = tm->hable[3]; tp.E = tm->hable[4]; tp.F = tm->hable[5];
+    tp.toe_angle = tp.E / tp.F;  // hable.rs:43-50
+    tp.exposure_bias = tm->exposure_bias;
+    {
+        double x = tm->linear_white_point;
+        tp.white_scale = 1.0 / (((x * (tp.A * x + tp.C * tp.B) + tp.D * tp.E) / (x * (tp.A * x + tp.B) + tp.D * tp.F)) - tp.toe_angle);
+    }
+    for (int i = 0; i < 9; ++i) { tp.aces_in[i] = tm->aces_in[i]; tp.aces_out[i] = tm->aces_out[i]; }
+    cudaError_t e = cudaMemcpyAsync(in.p, rgb, np * 3 * sizeof(double), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) {
+        postprocess_kernel<<<(unsigned)((np + 255) / 256), 256, 0, d.stream>>>(tp, in.p, np, q.p, mapped.p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && rgba) e = cudaMemcpyAsync(rgba, q.p, np * 4, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && rgb_out) e = cudaMemcpyAsync(rgb_out, mapped.p, np * 3 * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    in.release(); mapped.release(); q.release();
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, std::string("postprocess: ") + cudaGetErrorString(e));
+    return RC_OK;
+}
+
+int rc_primary_aov(rc_ctx* ctx, const rc_params* p, int32_t precision, uint32_t* id, double* t, double* normal, double* point) {
+    if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
+    int rc = check_params(p);
+    if (rc != RC_OK) return rc;
+    if (precision != 32 && precision != 64) return fail(RC_ERR_INVALID, "precision must be 32 or 64");
+    if (!ctx->has_scene || !ctx->has_camera) return fail(RC_ERR_STATE, "upload a scene and set a camera first");
+    DeviceState& d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    size_t np = (size_t)p->width * p->height;
+    DevBuf<uint32_t> d_id;
+    DevBuf<double> d_t, d_n, d_p;
+    CUDA_TRY(d_id.resize(np)); CUDA_TRY(d_t.resize(np)); CUDA_TRY(d_n.resize(np * 3)); CUDA_TRY(d_p.resize(np * 3));
+    if (precision == 32) {
+        KParams kp = ctx->kp;
+        kp.prims = d.prims.p; kp.nodes = d.nodes.p; kp.textures = d.textures.p; kp.instances = d.instances.p;
+        kp.perlin = d.perlin.p; kp.perlin_perm = d.perm.p;
+        kp.segment_counter = nullptr;
+        rc_params q = *p;
+        q.fixed_jitter = 1; q.split = RC_SPLIT_TILES;
+        partition(kp, &q, 0, 1);
+        kp.n_perlin = 0;  // no texture work in the AOV: skip the Perlin staging
+        size_t smem = ctx->smem_bytes - (size_t)ctx->kp.n_perlin * (256 * 16 + 768);
+        switch (ctx->mode) {
+        case RT_MODE_CONST_LINEAR:
+            primary_aov_kernel<RT_MODE_CONST_LINEAR><<<kp.n_tiles, RT_BLOCK, smem, d.stream>>>(kp, d_id.p, d_t.p, d_n.p, d_p.p);
+            break;
+        case RT_MODE_SMEM_BVH:
+            rc = set_smem(primary_aov_kernel<RT_MODE_SMEM_BVH>, smem);
+            if (rc != RC_OK) return rc;
+            primary_aov_kernel<RT_MODE_SMEM_BVH><<<kp.n_tiles, RT_BLOCK, smem, d.stream>>>(kp, d_id.p, d_t.p, d_n.p, d_p.p);
+            break;
+        case RT_MODE_GLOBAL_BVH:
+            primary_aov_kernel<RT_MODE_GLOBAL_BVH><<<kp.n_tiles, RT_BLOCK, smem, d.stream>>>(kp, d_id.p, d_t.p, d_n.p, d_p.p);
+            break;
+        default:
+            rc = set_smem(primary_aov_kernel<RT_MODE_SMEM_LINEAR>, smem);
+            if (rc != RC_OK) return rc;
+            primary_aov_kernel<RT_MODE_SMEM_LINEAR><<<kp.n_tiles, RT_BLOCK, smem, d.stream>>>(kp, d_id.p, d_t.p, d_n.p, d_p.p);
+        }
+    } else {
+        AovParamsD ap = ctx->aov;
+        ap.width = p->width; ap.height = p->height;
+        ap.prims = d.prims_d.p; ap.prim_kind = d.prim_kind.p; ap.prim_id = d.prim_id.p; ap.nodes = d.nodes_d.p;
+        dim3 block(16, 8), grid((p->width + 15) / 16, (p->height + 7) / 8);
+        primary_aov_kernel_f64<<<grid, block, 0, d.stream>>>(ap, d_id.p, d_t.p, d_n.p, d_p.p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && id) e = cudaMemcpyAsync(id, d_id.p, np * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, d_t.p, np * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && normal) e = cudaMemcpyAsync(normal, d_n.p, np * 3 * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && point) e = cudaMemcpyAsync(point, d_p.p, np * 3 * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    d_id.release(); d_t.release(); d_n.release(); d_p.release();
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, std::string("primary_aov: ") + cudaGetErrorString(e));
+    return RC_OK;
+}
+
+int rc_fp32_peak(rc_ctx* ctx, double* tflops, double* lane_ginstr_per_s) {
+    if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
+    DeviceState& d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    DevBuf<float> out;
+    const int blocks = d.sm_count * 8, threads = 256, iters = 4096;
+    CUDA_TRY(out.resize((size_t)blocks * threads));
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
+        fma_peak_kernel<<<blocks, threads, 0, d.stream>>>(out.p, iters, 0.999f, 0.001f);
+        CUDA_TRY(cudaEventRecord(d.ev1, d.stream));
+        CUDA_TRY(cudaEventSynchronize(d.ev1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    out.release();
+    double fmas = (double)blocks * threads * (double)iters * 64.0;
+    if (lane_ginstr_per_s) *lane_ginstr_per_s = fmas / (best_ms * 1e-3) / 1e9;
+    if (tflops) *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+    return RC_OK;
+}
+
+int rc_get_stats(rc_ctx* ctx, rc_stats* out) {
+    if (!ctx || !out) return fail(RC_ERR_INVALID, "ctx or out is NULL");
+    *out = ctx->stats;
+    return RC_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

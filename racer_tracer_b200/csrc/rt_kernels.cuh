@@ -1,0 +1,565 @@
+// rt_kernels.cuh — the kernels of the render path.
+//
+//   megakernel_render   one thread per pixel, loops over that pixel's samples
+//                       with path regeneration; path state lives in registers
+//   primary_aov_kernel  one ray per pixel, same ray-gen and closest hit
+//   finalize_kernel     Vec3::scale_sqrt (src/vec3.rs:119-125)
+//   postprocess_kernel  tone map + RGBA quantise (src/tone_map/*.rs,
+//                       src/image_action/png.rs:21-31)
+//
+// The wavefront kernels live in rt_wavefront.cuh.
+#pragma once
+#include "rt_scene.cuh"
+
+#define RT_TILE_W 16
+#define RT_TILE_H 8
+#define RT_BLOCK 128
+
+#define RT_MODE_CONST_LINEAR 0   // primitives in the constant bank, linear loop
+#define RT_MODE_SMEM_BVH 1       // nodes + primitives staged in shared memory
+#define RT_MODE_GLOBAL_BVH 2     // nodes + primitives read from global memory
+#define RT_MODE_SMEM_LINEAR 3    // primitives staged in shared memory, linear loop
+
+// ---------------------------------------------------------------------------
+// Shared-memory staging of the scene tables (coalesced 16-byte copies).
+// Layout of the dynamic shared segment: [nodes][prims][perlin grads][perms]
+// ---------------------------------------------------------------------------
+struct SmemLayout {
+    const DevNode* nodes;
+    const DevPrim* prims;
+    const float4* perlin;
+    const uint8_t* perm;
+};
+
+template <int MODE>
+RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
+    SmemLayout L;
+    L.nodes = P.nodes; L.prims = P.prims; L.perlin = P.perlin; L.perm = P.perlin_perm;
+    float4* dst = reinterpret_cast<float4*>(smem);
+    if (MODE == RT_MODE_SMEM_BVH) {
+        const float4* src = reinterpret_cast<const float4*>(P.nodes);
+        for (int i = threadIdx.x; i < P.n_nodes * 2; i += blockDim.x) dst[i] = __ldg(src + i);
+        L.nodes = reinterpret_cast<const DevNode*>(dst);
+        dst += P.n_nodes * 2;
+    }
+    if (MODE == RT_MODE_SMEM_BVH || MODE == RT_MODE_SMEM_LINEAR) {
+        const float4* src = reinterpret_cast<const float4*>(P.prims);
+        for (int i = threadIdx.x; i < P.n_prims * 3; i += blockDim.x) dst[i] = __ldg(src + i);
+        L.prims = reinterpret_cast<const DevPrim*>(dst);
+        dst += P.n_prims * 3;
+    }
+    if (P.n_perlin > 0) {
+        for (int i = threadIdx.x; i < P.n_perlin * 256; i += blockDim.x) dst[i] = __ldg(P.perlin + i);
+        L.perlin = dst;
+        dst += P.n_perlin * 256;
+        const uint32_t* ps = reinterpret_cast<const uint32_t*>(P.perlin_perm);
+        uint32_t* pd = reinterpret_cast<uint32_t*>(dst);
+        for (int i = threadIdx.x; i < P.n_perlin * 192; i += blockDim.x) pd[i] = __ldg(ps + i);
+        L.perm = reinterpret_cast<const uint8_t*>(pd);
+    }
+    __syncthreads();
+    return L;
+}
+
+template <int MODE, class Scene>
+RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& t) {
+    if constexpr (MODE == RT_MODE_CONST_LINEAR || MODE == RT_MODE_SMEM_LINEAR) return closest_hit_linear(S, P.n_prims, r, last_prim, t);
+    else return closest_hit_bvh(S, P.n_nodes, r, last_prim, t);
+}
+
+// ---------------------------------------------------------------------------
+// Ray generation: src/renderer/cpu.rs:35-40 + Camera::get_ray (camera.rs:326-337)
+// ---------------------------------------------------------------------------
+struct PixelCtx {
+    vec3f dir0;        // upper_left_corner + u*horizontal - origin, fixed per pixel (Q1)
+    uint32_t pixel;
+    int px, py;
+};
+
+template <int ROUNDS>
+RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
+    PixelCtx c;
+    c.px = px; c.py = py;
+    c.pixel = (uint32_t)(py * P.width + px);
+    float ujit = 0.5f;
+    if (!P.fixed_jitter) ujit = u24(philox4x32<ROUNDS>(c.pixel, 0u, 0u, RT_TAG_PIXEL << 24, P.key0, P.key1).x);
+    float u = ((float)px + ujit) / (float)(P.width - 1);  // once per pixel, cpu.rs:35-36
+    // cam.upper_left_corner holds (upper_left_corner - origin), formed in f64 on the host
+    c.dir0 = P.cam.upper_left_corner + u * P.cam.horizontal;
+    return c;
+}
+
+RT_D float pick_word(uint4 w, int i) { return u24(i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w))); }
+
+template <int SAMPLER, int ROUNDS>
+RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit, vec3f& o, vec3f& d) {
+    float v = ((float)c.py + vjit) / (float)(P.height - 1);  // cpu.rs:39-40
+    d = c.dir0 - v * P.cam.vertical;
+    o = P.cam.origin;
+    if (P.lens_enabled && !P.fixed_jitter) {  // camera.rs:327-328; skipped when lens_radius == 0 (offset = 0)
+        float dx, dy;
+        if (SAMPLER == 1) {  // random_in_unit_disk, util.rs:25-39
+            for (uint32_t j = 1;; ++j) {
+                uint4 w = philox4x32<ROUNDS>(c.pixel, sample, 0u, (RT_TAG_LENS << 24) | j, P.key0, P.key1);
+                dx = 2.0f * u24(w.x) - 1.0f; dy = 2.0f * u24(w.y) - 1.0f;
+                if (dx * dx + dy * dy >= 1.0f) continue;
+                break;
+            }
+        } else {
+            uint4 w = philox4x32<ROUNDS>(c.pixel, sample, 0u, RT_TAG_LENS << 24, P.key0, P.key1);
+            float r = sqrtf(u24(w.x)), s, cs;
+            sincospif(2.0f * u24(w.y), &s, &cs);
+            dx = r * cs; dy = r * s;
+        }
+        vec3f offset = (P.cam.lens_radius * dx) * P.cam.right + (P.cam.lens_radius * dy) * P.cam.up;
+        o = o + offset;
+        d = d - offset;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Shade one hit: emission + scatter (src/renderer.rs:59-69, src/material/*.rs).
+// Returns true if the path continues with (o, d) and throughput T updated;
+// `emit` receives the emitted radiance.
+// ---------------------------------------------------------------------------
+template <int SAMPLER, int ROUNDS, class Scene>
+RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const RngCtx& R, int prim,
+                    const RayT<float>& r, float t, uint32_t bounce, uint2 rnd, vec3f& o, vec3f& d,
+                    vec3f& T, vec3f& emit) {
+    Hit h = make_hit(S, prim, r, t);
+    float4 pb = S.pb(prim), pc = S.pc(prim);
+    int mat = kinds_mat(pb.z);
+    vec3f col = mk3(pc.x, pc.y, pc.z);
+    if (kinds_tex(pb.z) != RT_TEX_SOLID) col = texture_value(P, X, S, __float_as_int(pb.w), prim, h);
+    emit = mk3(0.0f, 0.0f, 0.0f);
+    if (mat == RT_MAT_LIGHT) {  // diffuse_light.rs:25-36
+        emit = col;
+        return false;
+    }
+    vec3f nd;
+    if (mat == RT_MAT_LAMBERTIAN) {  // lambertian.rs:25-39
+        vec3f rv;
+        if (SAMPLER == 1) rv = unit_vector(reject_in_unit_sphere<ROUNDS>(R, bounce));
+        else rv = sphere_direct(u24(rnd.x), u24(rnd.y));
+        nd = h.n + rv;
+        const float s = 1e-8f;  // near_zero, vec3.rs:127-130
+        if (fabsf(nd.x) < s && fabsf(nd.y) < s && fabsf(nd.z) < s) nd = h.n;
+    } else if (mat == RT_MAT_METAL) {  // metal.rs:25-44
+        vec3f rv;
+        if (SAMPLER == 1) rv = reject_in_unit_sphere<ROUNDS>(R, bounce);
+        else {
+            uint32_t a = rnd.x, b = rnd.y;
+            float u3 = u21(((a & 0x7FFu) << 10) | (b & 0x3FFu));
+            rv = cbrtf(u3) * sphere_direct(u21(a >> 11), u21(b >> 11));
+        }
+        vec3f refl = reflect(unit_vector(r.d), h.n);
+        nd = refl + pb.y * rv;
+        if (dot(nd, h.n) < 0.0f) return false;
+    } else {  // dialectric.rs:25-56
+        float ratio = h.front_face ? __frcp_rn(pb.y) : pb.y;
+        vec3f ud = unit_vector(r.d);
+        float cos_theta = fminf(-dot(ud, h.n), 1.0f);
+        float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+        bool do_reflect = ratio * sin_theta > 1.0f;
+        if (!do_reflect) {
+            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            r0 = r0 * r0;
+            float m = 1.0f - cos_theta, m2 = m * m;
+            float refl = r0 + (1.0f - r0) * (m2 * m2 * m);  // powf(5), dialectric.rs:17-22
+            do_reflect = refl > u24(rnd.x);
+        }
+        if (do_reflect) nd = reflect(ud, h.n);
+        else {  // refract, vec3.rs:416-422
+            vec3f perp = ratio * (ud + cos_theta * h.n);
+            vec3f par = (-sqrtf(fabsf(1.0f - length_squared(perp)))) * h.n;
+            nd = perp + par;
+        }
+        col = mk3(1.0f, 1.0f, 1.0f);
+    }
+    T = T * col;
+    o = h.p;
+    d = nd;
+    return true;
+}
+
+// The 64 random bits of bounce b (1-based): block (b+1)>>1, words (x,y) for
+// odd b and (z,w) for even b.  `cache` carries the second half between calls.
+template <int ROUNDS>
+RT_D uint2 bounce_bits(const RngCtx& R, uint32_t bounce, uint2& cache) {
+    if (bounce & 1u) {
+        uint4 w = philox4x32<ROUNDS>(R.pixel, R.sample, (bounce + 1u) >> 1, RT_TAG_BOUNCE << 24, R.key0, R.key1);
+        cache = make_uint2(w.z, w.w);
+        return make_uint2(w.x, w.y);
+    }
+    return cache;
+}
+
+// ---------------------------------------------------------------------------
+// Megakernel.  Block = 128 threads = one 16x8 pixel tile; each warp owns an
+// 8x4 sub-tile so its lanes trace neighbouring pixels.  A lane runs all the
+// samples [s_begin, s_end) of its pixel: when a path ends the lane starts the
+// next sample in the same loop iteration (path regeneration), so lanes idle
+// only at the very end of the tile.  Radiance sums stay in registers and are
+// added to the accumulation buffer once.
+// ---------------------------------------------------------------------------
+template <int MODE, int SAMPLER, int ROUNDS>
+__global__ void __launch_bounds__(RT_BLOCK)
+megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SmemLayout L = stage_scene<MODE>(P, smem);
+    TexCtx X; X.perlin = L.perlin; X.perm = L.perm;
+
+    const int tile = P.tile_first + blockIdx.x * P.tile_stride;
+    const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tx * RT_TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * RT_TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    const bool valid = px < P.width && py < P.height;
+
+    PixelCtx pc = pixel_setup<ROUNDS>(P, valid ? px : 0, valid ? py : 0);
+    RngCtx R; R.key0 = P.key0; R.key1 = P.key1; R.pixel = pc.pixel; R.sample = 0;
+
+    vec3f sum = mk3(0.0f, 0.0f, 0.0f);
+    vec3f o = mk3(0.0f, 0.0f, 0.0f), d = o, T = o, Lr = o;
+    int s = valid ? P.s_begin : P.s_end;
+    bool alive = false;
+    int depth_left = 0, last_prim = -1;
+    uint32_t bounce = 0;
+    uint2 cache = make_uint2(0u, 0u);
+    uint4 vj = make_uint4(0u, 0u, 0u, 0u);
+    int vj_block = -1;
+    unsigned nseg = 0;
+
+#pragma unroll 1
+    while (true) {
+        if (!alive && s < P.s_end) {
+            // ---- regenerate: next sample of this pixel ----
+            float vjit = 0.5f;
+            if (!P.fixed_jitter) {
+                if ((s >> 2) != vj_block) {
+                    vj_block = s >> 2;
+                    vj = philox4x32<ROUNDS>(pc.pixel, (uint32_t)vj_block, 0u, RT_TAG_VJIT << 24, P.key0, P.key1);
+                }
+                vjit = pick_word(vj, s & 3);
+            }
+            R.sample = (uint32_t)s;
+            camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d);
+            T = mk3(1.0f, 1.0f, 1.0f);
+            Lr = mk3(0.0f, 0.0f, 0.0f);
+            depth_left = P.max_depth;
+            bounce = 0; last_prim = -1;
+            alive = true;
+            ++s;
+            if (depth_left == 0) {  // renderer.rs:48-56
+                sum = sum + mk3(1.0f, 1.0f, 1.0f);
+                alive = false;
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) {
+            if (!__any_sync(0xffffffffu, s < P.s_end)) break;
+            continue;
+        }
+        if (alive) {
+            RayT<float> r = make_ray(o, d);
+            float t;
+            int prim;
+            if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
+            else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; prim = closest_hit<MODE>(P, S, r, last_prim, t); }
+            ++nseg;
+            if (prim < 0) {  // renderer.rs:78-88
+                Lr = Lr + T * background_color(P, d);
+                alive = false;
+            } else {
+                ++bounce;
+                uint2 rnd = bounce_bits<ROUNDS>(R, bounce, cache);
+                vec3f emit;
+                bool cont;
+                if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); cont = shade_hit<SAMPLER, ROUNDS>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, emit); }
+                else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; cont = shade_hit<SAMPLER, ROUNDS>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, emit); }
+                // emitted + attenuation * ray_color(...), renderer.rs:60-69 (emit is zero unless the
+                // material is a light, which never scatters)
+                if (!cont) { Lr = Lr + T * emit; alive = false; }
+                else {
+                    last_prim = prim;
+                    if (--depth_left == 0) { Lr = Lr + T; alive = false; }  // white at depth 0
+                }
+            }
+            if (!alive) sum = sum + Lr;
+        }
+    }
+    if (valid) {
+        float* a = accum + 3 * (size_t)pc.pixel;
+        a[0] += sum.x; a[1] += sum.y; a[2] += sum.z;
+    }
+    // segment statistics: one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
+    if (lane == 0 && P.segment_counter) atomicAdd(P.segment_counter, (unsigned long long)nseg);
+}
+
+// ---------------------------------------------------------------------------
+// Primary-visibility AOV (RayImageData, src/renderer.rs:33-39): fixed jitter,
+// one closest hit per pixel through the renderer's fp32 code.
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(RT_BLOCK)
+primary_aov_kernel(const __grid_constant__ KParams P, uint32_t* __restrict__ id, double* __restrict__ t_out,
+                   double* __restrict__ normal, double* __restrict__ point) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SmemLayout L = stage_scene<MODE>(P, smem);
+    const int tile = P.tile_first + blockIdx.x * P.tile_stride;
+    const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = tx * RT_TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * RT_TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    if (px >= P.width || py >= P.height) return;
+    PixelCtx pc = pixel_setup<10>(P, px, py);
+    vec3f o, d;
+    camera_ray<0, 10>(P, pc, 0u, 0.5f, o, d);
+    RayT<float> r = make_ray(o, d);
+    float t;
+    int prim;
+    Hit h;
+    uint32_t oid = 0;
+    if (MODE == RT_MODE_CONST_LINEAR) {
+        ConstScene S(P);
+        prim = closest_hit<MODE>(P, S, r, -1, t);
+        if (prim >= 0) { h = make_hit(S, prim, r, t); oid = (uint32_t)__float_as_int(S.pc(prim).w); }
+    } else {
+        PtrScene S; S.prims = L.prims; S.nodes = L.nodes;
+        prim = closest_hit<MODE>(P, S, r, -1, t);
+        if (prim >= 0) { h = make_hit(S, prim, r, t); oid = (uint32_t)__float_as_int(S.pc(prim).w); }
+    }
+    size_t i = pc.pixel;
+    if (prim < 0) {
+        if (id) id[i] = 0;
+        if (t_out) t_out[i] = 1.7976931348623157e308;
+        if (normal) { normal[3 * i] = 0; normal[3 * i + 1] = 0; normal[3 * i + 2] = 0; }
+        if (point) { point[3 * i] = 0; point[3 * i + 1] = 0; point[3 * i + 2] = 0; }
+        return;
+    }
+    if (id) id[i] = oid;
+    if (t_out) t_out[i] = (double)t;
+    if (normal) { normal[3 * i] = h.n.x; normal[3 * i + 1] = h.n.y; normal[3 * i + 2] = h.n.z; }
+    if (point) { point[3 * i] = h.p.x; point[3 * i + 1] = h.p.y; point[3 * i + 2] = h.p.z; }
+}
+
+// f64 primary visibility in the REFERENCE's operation order: round-to-nearest
+// f64 adds / multiplies / divides with no FMA contraction, the direct sphere
+// quadratic of sphere.rs:39-58, the per-axis Aabb::hit of aabb.rs:42-59 and
+// the left-to-right direction sum of camera.rs:329-334.  It exists to show
+// that ids (and t, normals) are bit-identical to the CPU restatement when the
+// arithmetic is the reference's; the renderer itself runs the fp32 code above.
+struct AovParamsD {
+    DevCamera<double> cam;   // upper_left_corner is the real corner here
+    int width, height, n_prims, n_nodes;
+    const DevPrimD* prims;
+    const int* prim_kind;    // RT_PRIM_*
+    const uint32_t* prim_id;
+    const DevNodeD* nodes;
+};
+
+RT_D double sd_add(double a, double b) { return __dadd_rn(a, b); }
+RT_D double sd_sub(double a, double b) { return __dsub_rn(a, b); }
+RT_D double sd_mul(double a, double b) { return __dmul_rn(a, b); }
+RT_D double sd_div(double a, double b) { return __ddiv_rn(a, b); }
+RT_D double sd_dot(Vec3T<double> a, Vec3T<double> b) { return sd_add(sd_add(sd_mul(a.x, b.x), sd_mul(a.y, b.y)), sd_mul(a.z, b.z)); }
+RT_D Vec3T<double> sd_sub3(Vec3T<double> a, Vec3T<double> b) { return mk3(sd_sub(a.x, b.x), sd_sub(a.y, b.y), sd_sub(a.z, b.z)); }
+RT_D Vec3T<double> sd_add3(Vec3T<double> a, Vec3T<double> b) { return mk3(sd_add(a.x, b.x), sd_add(a.y, b.y), sd_add(a.z, b.z)); }
+RT_D Vec3T<double> sd_scale(double s, Vec3T<double> a) { return mk3(sd_mul(s, a.x), sd_mul(s, a.y), sd_mul(s, a.z)); }
+
+// obj_hit in reference order; returns t or -1
+RT_D double prim_test_d(const AovParamsD& P, int i, Vec3T<double> o, Vec3T<double> d, double t_min, double t_max) {
+    const DevPrimD& p = P.prims[i];
+    int type = P.prim_kind[i];
+    if (type == RT_PRIM_SPHERE) {  // sphere.rs:39-58
+        Vec3T<double> oc = sd_sub3(o, mk3(p.a[0], p.a[1], p.a[2]));
+        double a = sd_dot(d, d), half_b = sd_dot(oc, d);
+        double c = sd_sub(sd_dot(oc, oc), sd_mul(p.a[3], p.a[3]));
+        double disc = sd_sub(sd_mul(half_b, half_b), sd_mul(a, c));
+        if (disc < 0.0) return -1.0;
+        double sqrtd = __dsqrt_rn(disc);
+        double root = sd_div(sd_sub(-half_b, sqrtd), a);
+        if (root < t_min || t_max < root) {
+            root = sd_div(sd_add(-half_b, sqrtd), a);
+            if (root < t_min || t_max < root) return -1.0;
+        }
+        return root;
+    }
+    double on, dn, oa, da, ob, db;  // xy_rect.rs:29-41 etc.
+    if (type == RT_PRIM_XY) { on = o.z; dn = d.z; oa = o.x; da = d.x; ob = o.y; db = d.y; }
+    else if (type == RT_PRIM_XZ) { on = o.y; dn = d.y; oa = o.x; da = d.x; ob = o.z; db = d.z; }
+    else { on = o.x; dn = d.x; oa = o.y; da = d.y; ob = o.z; db = d.z; }
+    double t = sd_div(sd_sub(p.k_or_cc, on), dn);
+    if (t < t_min || t > t_max) return -1.0;
+    double pa = sd_add(oa, sd_mul(t, da)), pb = sd_add(ob, sd_mul(t, db));
+    if (pa < p.a[0] || pa > p.a[1] || pb < p.a[2] || pb > p.a[3]) return -1.0;
+    return t;
+}
+
+// Aabb::hit, aabb.rs:42-59
+RT_D bool aabb_hit_d(const DevNodeD& n, Vec3T<double> o, Vec3T<double> d, double t_min, double t_max) {
+    for (int a = 0; a < 3; ++a) {
+        double inv_d = sd_div(1.0, axis_of(d, a));
+        double t0 = sd_mul(sd_sub(n.lo[a], axis_of(o, a)), inv_d);
+        double t1 = sd_mul(sd_sub(n.hi[a], axis_of(o, a)), inv_d);
+        if (inv_d < 0.0) { double tmp = t0; t0 = t1; t1 = tmp; }
+        double mn = t0 > t_min ? t0 : t_min;
+        double mx = t1 < t_max ? t1 : t_max;
+        if (mx <= mn) return false;
+    }
+    return true;
+}
+
+__global__ void primary_aov_kernel_f64(const __grid_constant__ AovParamsD P, uint32_t* __restrict__ id,
+                                       double* __restrict__ t_out, double* __restrict__ normal,
+                                       double* __restrict__ point) {
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= P.width || py >= P.height) return;
+    double u = sd_div(sd_add((double)px, 0.5), (double)(P.width - 1));
+    double v = sd_div(sd_add((double)py, 0.5), (double)(P.height - 1));
+    // upper_left_corner + u*horizontal - v*vertical - origin - offset (offset = 0), camera.rs:329-334
+    Vec3T<double> d = sd_sub3(sd_sub3(sd_add3(P.cam.upper_left_corner, sd_scale(u, P.cam.horizontal)),
+                                      sd_scale(v, P.cam.vertical)), P.cam.origin);
+    Vec3T<double> o = P.cam.origin;
+    const double t_min = RT_T_MIN;
+    double best_t = __longlong_as_double(0x7ff0000000000000LL);
+    int best = -1;
+    if (P.n_nodes == 0) {
+        for (int i = 0; i < P.n_prims; ++i) {
+            double t = prim_test_d(P, i, o, d, t_min, best_t);
+            if (t >= 0.0) { best_t = t; best = i; }
+        }
+    } else {
+        int i = 0;
+        while (i < P.n_nodes) {
+            const DevNodeD& n = P.nodes[i];
+            if (aabb_hit_d(n, o, d, t_min, best_t)) {
+                if (n.leaf >= 0) {
+                    int first = n.leaf & 0xffffff, count = n.leaf >> 24;
+                    for (int p = first; p < first + count; ++p) {
+                        double t = prim_test_d(P, p, o, d, t_min, best_t);
+                        if (t >= 0.0) { best_t = t; best = p; }
+                    }
+                    i = n.skip;
+                } else i = i + 1;
+            } else i = n.skip;
+        }
+    }
+    size_t i = (size_t)py * P.width + px;
+    if (best < 0) {
+        if (id) id[i] = 0;
+        if (t_out) t_out[i] = 1.7976931348623157e308;
+        if (normal) { normal[3 * i] = 0; normal[3 * i + 1] = 0; normal[3 * i + 2] = 0; }
+        if (point) { point[3 * i] = 0; point[3 * i + 1] = 0; point[3 * i + 2] = 0; }
+        return;
+    }
+    const DevPrimD& p = P.prims[best];
+    int type = P.prim_kind[best];
+    Vec3T<double> hp = sd_add3(o, sd_scale(best_t, d)), on;   // Ray::at
+    if (type == RT_PRIM_SPHERE) {
+        Vec3T<double> pc = sd_sub3(hp, mk3(p.a[0], p.a[1], p.a[2]));
+        on = mk3(sd_div(pc.x, p.a[3]), sd_div(pc.y, p.a[3]), sd_div(pc.z, p.a[3]));  // sphere.rs:61
+    } else on = mk3(type == RT_PRIM_YZ ? 1.0 : 0.0, type == RT_PRIM_XZ ? 1.0 : 0.0, type == RT_PRIM_XY ? 1.0 : 0.0);
+    bool front = sd_dot(d, on) < 0.0;
+    Vec3T<double> n = front ? on : -on;
+    if (id) id[i] = P.prim_id[best];
+    if (t_out) t_out[i] = best_t;
+    if (normal) { normal[3 * i] = n.x; normal[3 * i + 1] = n.y; normal[3 * i + 2] = n.z; }
+    if (point) { point[3 * i] = hp.x; point[3 * i + 1] = hp.y; point[3 * i + 2] = hp.z; }
+}
+
+// ---------------------------------------------------------------------------
+// Vec3::scale_sqrt, src/vec3.rs:119-125
+// ---------------------------------------------------------------------------
+__global__ void finalize_kernel(const float* __restrict__ accum, float* __restrict__ rgb, size_t n, float scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rgb[i] = sqrtf(scale * accum[i]);
+}
+
+__global__ void finalize_to_f64_kernel(const float* __restrict__ accum, double* __restrict__ rgb, size_t n, double scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rgb[i] = sqrt(scale * (double)accum[i]);
+}
+
+// ---------------------------------------------------------------------------
+// Tone map + quantise.  f64, like the reference's ScreenBuffer thread
+// (src/image_buffer.rs:147-153) — it runs once per pixel, not per sample.
+// ---------------------------------------------------------------------------
+struct ToneParams {
+    int type;
+    double max_white_pow;
+    double A, B, C, D, E, F, toe_angle, exposure_bias, white_scale;
+    double aces_in[9], aces_out[9];
+};
+
+RT_D double hable_partial(const ToneParams& t, double x) {  // hable.rs:52-62
+    return ((x * (t.A * x + t.C * t.B) + t.D * t.E) / (x * (t.A * x + t.B) + t.D * t.F)) - t.toe_angle;
+}
+
+RT_D double aces_fit(double x) {  // aces.rs:26-30
+    double a = x * (x + 0.0245786) - 0.000090537;
+    double b = x * (0.983729 * x + 0.4329510) + 0.238081;
+    return a / b;
+}
+
+// Rust `f64 as u32`: saturating, NaN -> 0 (png.rs:24-26)
+RT_D uint32_t f64_as_u32(double v) {
+    if (!(v == v) || v <= 0.0) return 0u;
+    if (v >= 4294967295.0) return 4294967295u;
+    return (uint32_t)v;
+}
+
+__global__ void postprocess_kernel(const __grid_constant__ ToneParams tp, const double* __restrict__ rgb,
+                                   size_t n_pixels, uint8_t* __restrict__ rgba, double* __restrict__ mapped) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    double r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+    if (tp.type == 1) {  // reinhard.rs:16-42
+        double l_old = r * 0.2126 + g * 0.7152 + b * 0.0722;
+        double numerator = l_old * (1.0 + (l_old / tp.max_white_pow));
+        double l_new = numerator / (1.0 + l_old);
+        double s = l_new / l_old;
+        r *= s; g *= s; b *= s;
+    } else if (tp.type == 2) {  // hable.rs:64-80
+        r = hable_partial(tp, r * tp.exposure_bias) * tp.white_scale;
+        g = hable_partial(tp, g * tp.exposure_bias) * tp.white_scale;
+        b = hable_partial(tp, b * tp.exposure_bias) * tp.white_scale;
+    } else if (tp.type == 3) {  // aces.rs:18-55
+        const double* m = tp.aces_in;
+        double x = aces_fit(m[0] * r + m[1] * g + m[2] * b);
+        double y = aces_fit(m[3] * r + m[4] * g + m[5] * b);
+        double z = aces_fit(m[6] * r + m[7] * g + m[8] * b);
+        const double* q = tp.aces_out;
+        r = q[0] * x + q[1] * y + q[2] * z;
+        g = q[3] * x + q[4] * y + q[5] * z;
+        b = q[6] * x + q[7] * y + q[8] * z;
+    }
+    if (mapped) { mapped[3 * i] = r; mapped[3 * i + 1] = g; mapped[3 * i + 2] = b; }
+    if (rgba) {
+        uint32_t val = (f64_as_u32(r * 255.0) << 24) | (f64_as_u32(g * 255.0) << 16) | (f64_as_u32(b * 255.0) << 8) | 255u;
+        rgba[4 * i] = (uint8_t)(val >> 24); rgba[4 * i + 1] = (uint8_t)(val >> 16);
+        rgba[4 * i + 2] = (uint8_t)(val >> 8); rgba[4 * i + 3] = (uint8_t)val;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// FP32 FMA micro-benchmark: 16 independent FFMA chains per thread, register
+// only.  Gives the measured non-tensor FP32 issue peak used as the roofline
+// denominator.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = fmaf(x[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += x[k];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}

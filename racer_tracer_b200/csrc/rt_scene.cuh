@@ -1,0 +1,458 @@
+// rt_scene.cuh — device-side scene layout and the per-ray building blocks:
+// closest hit (linear list or threaded BVH), hit-record reconstruction,
+// textures, materials and background.  Everything is templated on the scalar
+// so the primary-visibility AOV can instantiate the very same intersectors in
+// f64.  Reference citations are relative to /root/reference/racer-tracer/.
+#pragma once
+#include "rt_math.cuh"
+
+// ---------------------------------------------------------------------------
+// Layout.  A primitive is three 16-byte words (float4 / double4-as-2x):
+//   a: sphere (cx, cy, cz, r)            rect (a0, a1, b0, b1)
+//   b: sphere (|c|^2 - r^2, -, -, -)     rect (k, -, -, -);  b.y = material
+//      parameter (fuzz / refraction index), b.z = packed kinds, b.w = texture
+//      index (non-solid) or -1
+//   c: (r, g, b) of a solid-colour texture (albedo or emission), c.w = bits of
+//      the canonical object id
+// packed kinds (b.z bits): [0:4) prim type, [4:8) material type, [8:12)
+// texture type, [12:32) instance index + 1 (0 = none)
+// ---------------------------------------------------------------------------
+#define RT_PRIM_SPHERE 0
+#define RT_PRIM_XY 1
+#define RT_PRIM_XZ 2
+#define RT_PRIM_YZ 3
+#define RT_MAT_LAMBERTIAN 0
+#define RT_MAT_METAL 1
+#define RT_MAT_DIELECTRIC 2
+#define RT_MAT_LIGHT 3
+#define RT_TEX_SOLID 0
+#define RT_TEX_CHECKER 1
+#define RT_TEX_IMAGE 2
+#define RT_TEX_NOISE 3
+
+#define RT_MAX_CONST_PRIMS 40   // primitives kept in the kernel-parameter constant bank
+#define RT_MAX_IMAGES 8
+#define RT_T_MIN 0.001          // src/renderer.rs:58
+
+struct DevPrim {      // fp32 primitive record, 48 B
+    float4 a, b, c;
+};
+
+struct DevPrimD {     // f64 geometry of the same primitive (AOV f64 instantiation)
+    double a[4];
+    double k_or_cc;
+};
+
+struct DevNode {      // threaded BVH node, pre-order; 32 B
+    float4 lo;        // bmin.xyz, w = bits(skip index)
+    float4 hi;        // bmax.xyz, w = bits(leaf: first | count << 24; inner: -1)
+};
+
+struct DevNodeD {
+    double lo[3], hi[3];
+    int skip, leaf;
+};
+
+struct DevTexture {   // 32 B
+    int type, a, b;
+    float scale;
+    float4 color;
+};
+
+struct DevInstance {  // src/geometry/rotate_y.rs, translate.rs
+    float sin_theta, cos_theta, ox, oy, oz;
+    int flags;
+};
+
+template <typename T>
+struct DevCamera {    // CameraSharedData, src/camera.rs:57-72 (the fields get_ray reads)
+    Vec3T<T> origin, upper_left_corner, right, up, horizontal, vertical;
+    T lens_radius, time_a, time_b;
+};
+
+// Kernel parameters: passed by value (constant bank), < 4 KB.
+struct KParams {
+    DevCamera<float> cam;
+    float4 bg_a, bg_b;          // background colours; bg_a.w = bits(bg type)
+    int width, height;
+    int s_begin, s_end;         // sample range traced by this launch
+    int max_depth;
+    int fixed_jitter;
+    uint32_t key0, key1;        // Philox key = seed
+    int tile_first, tile_stride, n_tiles;   // interleaved tile partition
+    int tiles_x, tile_w, tile_h;
+    int n_prims, n_nodes;
+    int n_perlin;
+    int lens_enabled;
+    const DevPrim* prims;       // all primitives (global memory)
+    const DevNode* nodes;       // threaded BVH (global memory)
+    const DevTexture* textures;
+    const DevInstance* instances;
+    const float4* perlin;       // n_perlin x 256 gradients (xyz, w unused)
+    const uint8_t* perlin_perm; // n_perlin x 3 x 256
+    cudaTextureObject_t images[RT_MAX_IMAGES];
+    int image_w[RT_MAX_IMAGES], image_h[RT_MAX_IMAGES];
+    unsigned long long* segment_counter;
+    DevPrim cprims[RT_MAX_CONST_PRIMS];   // copy of prims for the linear constant-bank path
+};
+
+// ---------------------------------------------------------------------------
+// Scene accessors.  ConstScene reads primitives from the kernel parameters
+// (uniform addresses in the linear loop -> constant-bank operands, no load
+// instructions); SmemScene reads primitives and nodes staged in shared
+// memory; GlobalScene reads them through the read-only path.
+// ---------------------------------------------------------------------------
+struct ConstScene {
+    const KParams& P;
+    RT_D ConstScene(const KParams& p) : P(p) {}
+    RT_D float4 pa(int i) const { return P.cprims[i].a; }
+    RT_D float4 pb(int i) const { return P.cprims[i].b; }
+    RT_D float4 pc(int i) const { return P.cprims[i].c; }
+    RT_D float4 nlo(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }  // no BVH in the constant bank
+    RT_D float4 nhi(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+
+struct PtrScene {  // shared or global, decided by where the pointers point
+    const DevPrim* prims;
+    const DevNode* nodes;
+    RT_D float4 pa(int i) const { return prims[i].a; }
+    RT_D float4 pb(int i) const { return prims[i].b; }
+    RT_D float4 pc(int i) const { return prims[i].c; }
+    RT_D float4 nlo(int i) const { return nodes[i].lo; }
+    RT_D float4 nhi(int i) const { return nodes[i].hi; }
+};
+
+RT_D int kinds_prim(float packed) { return __float_as_int(packed) & 15; }
+RT_D int kinds_mat(float packed) { return (__float_as_int(packed) >> 4) & 15; }
+RT_D int kinds_tex(float packed) { return (__float_as_int(packed) >> 8) & 15; }
+RT_D int kinds_inst(float packed) { return (int)((unsigned)__float_as_int(packed) >> 12) - 1; }
+
+// ---------------------------------------------------------------------------
+// Primitive tests.  `self` marks the primitive the ray starts on.
+//
+// fp32 adaptation of the reference's f64 behaviour (DESIGN.md "fp32"): in f64
+// a scattered ray re-tests the surface it leaves and finds the root t ~ 1e-13,
+// which t_min = 0.001 rejects (src/renderer.rs:58).  In fp32 the origin sits
+// up to ~1e-4 off the surface, so that root can exceed t_min at grazing
+// angles.  We therefore give the departed primitive the limit the f64 code
+// converges to: a rectangle cannot be re-hit, and a sphere is solved with
+// c = |oc|^2 - r^2 = 0 exactly (roots 0 and -2b/a).
+// ---------------------------------------------------------------------------
+
+// src/geometry/sphere.rs:39-58.  Returns the accepted root or -1.
+//
+// Two fp32-robust evaluations of the same quadratic, picked per ray:
+//   far from the sphere (|oc|^2 > 2.6 r^2): the discriminant is formed from
+//     l = oc - (b/a) d, the centre-to-ray vector, as a (r^2 - |l|^2) — no
+//     b^2 - a c cancellation for small spheres seen from far away (clown);
+//   near or inside it: c = |o|^2 - 2 o.ctr + (|ctr|^2 - r^2) with the last
+//     term precomputed in f64 on the host — no |oc|^2 - r^2 cancellation for
+//     the radius-1000 ground spheres seen from just above their surface.
+// Both use the stable root formula q = -(b + sign(b) sqrt(disc)); t = q/a, c/q.
+#define RT_SPHERE_FAR_RATIO 2.6f
+template <typename T>
+RT_D T sphere_hit(Vec3T<T> o, Vec3T<T> d, T a, T inv_a, Vec3T<T> ctr, T radius, T cc, bool self, T t_min, T t_max) {
+    Vec3T<T> oc = o - ctr;
+    T b = dot(oc, d);  // half_b
+    T oc2 = dot(oc, oc), r2 = radius * radius;
+    T c, disc;
+    if (oc2 > T(RT_SPHERE_FAR_RATIO) * r2) {
+        T ba = b * inv_a;
+        Vec3T<T> l = mk3<T>(oc.x - ba * d.x, oc.y - ba * d.y, oc.z - ba * d.z);
+        disc = a * (r2 - dot(l, l));
+        c = oc2 - r2;
+    } else {
+        Vec3T<T> o2 = mk3<T>(o.x - T(2) * ctr.x, o.y - T(2) * ctr.y, o.z - T(2) * ctr.z);
+        c = self ? T(0) : (dot(o, o2) + cc);
+        disc = b * b - a * c;
+    }
+    if (!(disc >= T(0))) return T(-1);
+    T s = rt_sqrt(disc);
+    T q = b < T(0) ? (s - b) : -(b + s);
+    T r_qa = q * inv_a;
+    T r_cq = c / q;
+    T near_root = b < T(0) ? r_cq : r_qa;
+    T far_root = b < T(0) ? r_qa : r_cq;
+    // "nearest root that lies in the acceptable range", sphere.rs:51-58
+    if (near_root >= t_min && near_root <= t_max) return near_root;
+    if (far_root >= t_min && far_root <= t_max) return far_root;
+    return T(-1);
+}
+
+// Outward normal (p - ctr)/r of an accepted sphere hit (sphere.rs:61), formed
+// from small-magnitude vectors so that it keeps fp32 precision for small
+// spheres far from the origin: (l -+ (sqrt(disc)/a) d)/r in the far case,
+// (oc + t d)/r otherwise.
+RT_D vec3f sphere_normal(vec3f o, vec3f d, float a, float inv_a, vec3f ctr, float radius, float t) {
+    vec3f oc = o - ctr;
+    float oc2 = dot(oc, oc), r2 = radius * radius;
+    float inv_r = __frcp_rn(radius);
+    if (oc2 > RT_SPHERE_FAR_RATIO * r2) {
+        float b = dot(oc, d);
+        float ba = b * inv_a;
+        vec3f l = mk3(oc.x - ba * d.x, oc.y - ba * d.y, oc.z - ba * d.z);
+        float h = sqrtf(fmaxf(0.0f, (r2 - dot(l, l)) * inv_a));   // |t - t_closest|
+        float dt = (t < -ba) ? -h : h;                            // near or far root
+        return mk3((l.x + dt * d.x) * inv_r, (l.y + dt * d.y) * inv_r, (l.z + dt * d.z) * inv_r);
+    }
+    return mk3((oc.x + t * d.x) * inv_r, (oc.y + t * d.y) * inv_r, (oc.z + t * d.z) * inv_r);
+}
+
+// src/geometry/xy_rect.rs:29-41 (and xz_rect.rs, yz_rect.rs): plane distance,
+// range test, inclusive bounds test.  Returns t or -1.
+template <typename T>
+RT_D T rect_hit(int type, Vec3T<T> o, Vec3T<T> d, Vec3T<T> inv_d, T a0, T a1, T b0, T b1, T k, T t_min, T t_max) {
+    T on, in, oa, da, ob, db;
+    if (type == RT_PRIM_XY) { on = o.z; in = inv_d.z; oa = o.x; da = d.x; ob = o.y; db = d.y; }
+    else if (type == RT_PRIM_XZ) { on = o.y; in = inv_d.y; oa = o.x; da = d.x; ob = o.z; db = d.z; }
+    else { on = o.x; in = inv_d.x; oa = o.y; da = d.y; ob = o.z; db = d.z; }
+    T t = (k - on) * in;
+    if (!(t >= t_min && t <= t_max)) return T(-1);
+    T pa = oa + t * da, pb = ob + t * db;
+    if (pa < a0 || pa > a1 || pb < b0 || pb > b1) return T(-1);
+    return t;
+}
+
+template <typename T>
+struct RayT {
+    Vec3T<T> o, d, inv_d;
+    T a, inv_a;  // |d|^2 and its reciprocal
+};
+
+template <typename T>
+RT_D RayT<T> make_ray(Vec3T<T> o, Vec3T<T> d) {
+    RayT<T> r;
+    r.o = o; r.d = d;
+    r.inv_d = mk3<T>(rt_rcp(d.x), rt_rcp(d.y), rt_rcp(d.z));
+    r.a = dot(d, d);
+    r.inv_a = rt_rcp(r.a);
+    return r;
+}
+
+// One primitive of the fp32 tables against a ray; returns t or -1.
+template <class Scene>
+RT_D float prim_test(const Scene& S, int i, const RayT<float>& r, int last_prim, float t_max) {
+    float4 a = S.pa(i), b = S.pb(i);
+    int type = kinds_prim(b.z);
+    bool self = (i == last_prim);
+    if (type == RT_PRIM_SPHERE)
+        return sphere_hit<float>(r.o, r.d, r.a, r.inv_a, mk3(a.x, a.y, a.z), a.w, b.x, self, (float)RT_T_MIN, t_max);
+    if (self) return -1.0f;
+    return rect_hit<float>(type, r.o, r.d, r.inv_d, a.x, a.y, a.z, a.w, b.x, (float)RT_T_MIN, t_max);
+}
+
+// Linear closest hit in index order: the later primitive wins an exact tie
+// (`t <= closest`), as src/shared_scene.rs:37-53 and sphere.rs:53.
+template <class Scene>
+RT_D int closest_hit_linear(const Scene& S, int n_prims, const RayT<float>& r, int last_prim, float& best_t) {
+    int best = -1;
+    best_t = __int_as_float(0x7f800000);
+#pragma unroll 1
+    for (int i = 0; i < n_prims; ++i) {
+        float t = prim_test(S, i, r, last_prim, best_t);
+        if (t >= 0.0f) { best_t = t; best = i; }
+    }
+    return best;
+}
+
+// Slab test against [t_min, t_max]; conservative with respect to
+// src/aabb.rs:42-59 (which clips every axis against the original interval and
+// so accepts a superset).  Boxes are padded at upload, see rc_api.cu.
+RT_D bool aabb_hit(float4 lo, float4 hi, const RayT<float>& r, float t_max) {
+    float tx0 = (lo.x - r.o.x) * r.inv_d.x, tx1 = (hi.x - r.o.x) * r.inv_d.x;
+    float ty0 = (lo.y - r.o.y) * r.inv_d.y, ty1 = (hi.y - r.o.y) * r.inv_d.y;
+    float tz0 = (lo.z - r.o.z) * r.inv_d.z, tz1 = (hi.z - r.o.z) * r.inv_d.z;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), (float)RT_T_MIN));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), t_max));
+    return tn <= tf;
+}
+
+// Threaded pre-order BVH: left child = i + 1, `skip` = next node when this
+// subtree is done.  Visits left before right with a shrinking t_max, exactly
+// the order of Node::hit (src/bvh_node.rs:112-132).
+template <class Scene>
+RT_D int closest_hit_bvh(const Scene& S, int n_nodes, const RayT<float>& r, int last_prim, float& best_t) {
+    int best = -1;
+    best_t = __int_as_float(0x7f800000);
+    int i = 0;
+#pragma unroll 1
+    while (i < n_nodes) {
+        float4 lo = S.nlo(i), hi = S.nhi(i);
+        int leaf = __float_as_int(hi.w);
+        if (aabb_hit(lo, hi, r, best_t)) {
+            if (leaf >= 0) {
+                int first = leaf & 0xffffff, count = leaf >> 24;
+                for (int p = first; p < first + count; ++p) {
+                    float t = prim_test(S, p, r, last_prim, best_t);
+                    if (t >= 0.0f) { best_t = t; best = p; }
+                }
+                i = __float_as_int(lo.w);
+            } else {
+                i = i + 1;
+            }
+        } else {
+            i = __float_as_int(lo.w);
+        }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------
+// Hit record (src/geometry.rs:17-57) rebuilt from (ray, t, primitive).
+// ---------------------------------------------------------------------------
+struct Hit {
+    vec3f p, n;        // point, face normal
+    vec3f outward;     // outward normal (sphere uv, sphere.rs:61-63)
+    bool front_face;
+};
+
+template <class Scene>
+RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t) {
+    Hit h;
+    float4 a = S.pa(prim), b = S.pb(prim);
+    int type = kinds_prim(b.z);
+    h.p = r.o + t * r.d;  // Ray::at
+    if (type == RT_PRIM_SPHERE) {
+        vec3f ctr = mk3(a.x, a.y, a.z);
+        h.outward = sphere_normal(r.o, r.d, r.a, r.inv_a, ctr, a.w, t);  // sphere.rs:61
+        h.p = ctr + a.w * h.outward;   // the point on the surface that normal belongs to
+    } else {
+        h.outward = mk3(type == RT_PRIM_YZ ? 1.0f : 0.0f, type == RT_PRIM_XZ ? 1.0f : 0.0f,
+                        type == RT_PRIM_XY ? 1.0f : 0.0f);
+        // keep the point on the plane (the reference's f64 ray.at(t) lands on it to 1e-13)
+        if (type == RT_PRIM_XY) h.p.z = b.x; else if (type == RT_PRIM_XZ) h.p.y = b.x; else h.p.x = b.x;
+    }
+    h.front_face = dot(r.d, h.outward) < 0.0f;  // geometry.rs:49-56
+    h.n = h.front_face ? h.outward : -h.outward;
+    return h;
+}
+
+// uv on demand: sphere.rs:20-27, xy_rect.rs:42-43 (only image textures read it)
+template <class Scene>
+RT_D void hit_uv(const Scene& S, int prim, const Hit& h, float& u, float& v) {
+    float4 a = S.pa(prim), b = S.pb(prim);
+    int type = kinds_prim(b.z);
+    const float PI_F = 3.14159265358979323846f;
+    if (type == RT_PRIM_SPHERE) {
+        float theta = acosf(fminf(fmaxf(-h.outward.y, -1.0f), 1.0f));
+        float phi = atan2f(-h.outward.z, h.outward.x) + PI_F;
+        u = phi / (2.0f * PI_F);
+        v = theta / PI_F;
+    } else {
+        float pa = type == RT_PRIM_YZ ? h.p.y : h.p.x;
+        float pb = type == RT_PRIM_XY ? h.p.y : h.p.z;
+        u = (pa - a.x) / (a.y - a.x);
+        v = (pb - a.z) / (a.w - a.z);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Textures — src/texture/*.rs
+// ---------------------------------------------------------------------------
+// Perlin::noise + perlin_interp, src/texture/noise.rs:57-96.  `grad` and
+// `perm` point at this texture's tables (shared memory when staged).
+RT_D float perlin_noise(const float4* grad, const uint8_t* perm, vec3f p) {
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                int idx = perm[(i + di) & 255] ^ perm[256 + ((j + dj) & 255)] ^ perm[512 + ((k + dk) & 255)];
+                float4 g = grad[idx];
+                float wx = u - (float)di, wy = v - (float)dj, wz = w - (float)dk;
+                float bl = (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww);
+                accum += bl * (g.x * wx + g.y * wy + g.z * wz);
+            }
+    return accum;
+}
+
+// Perlin::turbulence, src/texture/noise.rs:98-109
+RT_D float perlin_turbulence(const float4* grad, const uint8_t* perm, vec3f p, int depth) {
+    float accum = 0.0f, weight = 1.0f;
+#pragma unroll 1
+    for (int i = 0; i < depth; ++i) {
+        accum += weight * perlin_noise(grad, perm, p);
+        weight *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(accum);
+}
+
+struct TexCtx {            // where the Perlin tables live for this kernel
+    const float4* perlin;  // n_perlin x 256
+    const uint8_t* perm;   // n_perlin x 768
+};
+
+// Texture::value for a non-solid texture index (solid colours are folded into
+// the primitive record).  Checker children are resolved iteratively.
+template <class Scene>
+RT_D vec3f texture_value(const KParams& P, const TexCtx& X, const Scene& S, int tex, int prim, const Hit& h) {
+    DevTexture t = P.textures[tex];
+#pragma unroll 1
+    for (int level = 0; level < 4 && t.type == RT_TEX_CHECKER; ++level) {
+        // checkered.rs:32-43 — world-space sines, odd if negative
+        float sines = sinf(h.p.x * t.scale) * sinf(h.p.y * t.scale) * sinf(h.p.z * t.scale);
+        t = P.textures[sines < 0.0f ? t.b : t.a];
+    }
+    if (t.type == RT_TEX_IMAGE) {  // image.rs:28-51: nearest texel, v flipped, clamped
+        float u, v;
+        hit_uv(S, prim, h, u, v);
+        u = fminf(fmaxf(u, 0.0f), 1.0f);
+        v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+        float fw = (float)P.image_w[t.a], fh = (float)P.image_h[t.a];
+        float fi = u * fw, fj = v * fh;
+        if (fi >= fw) fi = fw - 1.0f;
+        if (fj >= fh) fj = fh - 1.0f;
+        float4 px = tex2D<float4>(P.images[t.a], floorf(fi) + 0.5f, floorf(fj) + 0.5f);
+        return mk3(px.x, px.y, px.z);
+    }
+    if (t.type == RT_TEX_NOISE) {  // noise.rs:26-33
+        float turb = perlin_turbulence(X.perlin + 256 * t.a, X.perm + 768 * t.a, h.p, t.b);
+        float s = 0.5f * (1.0f + sinf(t.scale * h.p.z + 10.0f * turb));
+        return mk3(t.color.x * s, t.color.y * s, t.color.z * s);
+    }
+    return mk3(t.color.x, t.color.y, t.color.z);  // solid_color.rs:24-28
+}
+
+// BackgroundColor::color, src/background_color.rs:27-48
+RT_D vec3f background_color(const KParams& P, vec3f d) {
+    if (__float_as_int(P.bg_a.w) == 0) {  // Sky
+        float t = 0.5f * (d.y * rsqrtf(dot(d, d)) + 1.0f);
+        return mk3((1.0f - t) * P.bg_a.x + t * P.bg_b.x, (1.0f - t) * P.bg_a.y + t * P.bg_b.y,
+                   (1.0f - t) * P.bg_a.z + t * P.bg_b.z);
+    }
+    return mk3(P.bg_a.x, P.bg_a.y, P.bg_a.z);
+}
+
+// ---------------------------------------------------------------------------
+// Samplers.  DIRECT: inverse transforms of the distributions the reference's
+// rejection loops produce.  REJECTION: those loops themselves, one Philox
+// block per iteration (src/vec3.rs:424-444, src/util.rs:25-39).
+// ---------------------------------------------------------------------------
+struct RngCtx {
+    uint32_t key0, key1, pixel, sample;
+};
+
+RT_D vec3f sphere_direct(float u1, float u2) {
+    float z = 1.0f - 2.0f * u1;
+    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    return mk3(r * c, r * s, z);
+}
+
+template <int ROUNDS>
+RT_D vec3f reject_in_unit_sphere(const RngCtx& R, uint32_t bounce) {  // vec3.rs:424-430
+    for (uint32_t j = 0;; ++j) {
+        uint4 w = philox4x32<ROUNDS>(R.pixel, R.sample, bounce, (RT_TAG_REJECT << 24) | j, R.key0, R.key1);
+        vec3f v = mk3(2.0f * u24(w.x) - 1.0f, 2.0f * u24(w.y) - 1.0f, 2.0f * u24(w.z) - 1.0f);
+        if (length_squared(v) >= 1.0f) continue;
+        return v;
+    }
+}

@@ -706,6 +706,12 @@ class CudaRenderer:
             pt.ctypes.data_as(C.POINTER(C.c_double))))
         return ids, t, nrm, pt
 
+    def fp32_peak(self):
+        """(TFLOP/s, G lane-instr/s) of the FFMA micro-benchmark on device 0."""
+        tf, gi = C.c_double(), C.c_double()
+        capi.check(self.lib, self.lib.rc_fp32_peak(self.ctx, C.byref(tf), C.byref(gi)))
+        return tf.value, gi.value
+
     def stats(self) -> capi.rc_stats:
         s = capi.rc_stats()
         capi.check(self.lib, self.lib.rc_get_stats(self.ctx, C.byref(s)))

@@ -1,0 +1,50 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SCENES = ["three_balls", "emissive", "noise_and_textures", "cornell_box", "clown"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+def scene_path(name):
+    return os.path.join(GOLDEN, "scenes", name + ".yml")
+
+
+@pytest.fixture(scope="session")
+def cfg():
+    from racer_tracer_b200 import harness
+    return harness.load_config(os.path.join(GOLDEN, "config.yml"))
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.lib()
+    return O
+
+
+@pytest.fixture(scope="session")
+def cuda_lib():
+    """libracer_cuda.so, built in-tree if missing (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as ge
+    from racer_tracer_b200 import capi
+    if not os.path.exists(capi.LIB_PATH):
+        ge.build()
+    return capi.load()
+
+
+@pytest.fixture(scope="session")
+def renderer(cuda_lib):
+    from racer_tracer_b200 import harness
+    r = harness.CudaRenderer([0])
+    yield r
+    r.close()

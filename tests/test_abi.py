@@ -1,0 +1,91 @@
+"""The C-ABI shared library loads and exports every symbol include/racer_cuda.h
+declares; without a GPU the entry points fail loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from racer_tracer_b200 import capi, harness
+
+HEADER = os.path.join(ROOT, "include", "racer_cuda.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_python_binding_agree():
+    assert declared_symbols() == sorted(capi.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    for name in declared_symbols():
+        assert name in exported, f"{name} is declared in racer_cuda.h but not exported"
+        assert hasattr(cuda_lib, name)
+    assert cuda_lib.rc_abi_version() == 1
+    assert not any(s.startswith("oracle_") for s in exported), "the product must not contain the oracle"
+
+
+def test_struct_layouts_match_the_header(cuda_lib):
+    """sizeof of every ctypes mirror equals the C compiler's sizeof."""
+    src = r'''
+    #include <stdio.h>
+    #include "racer_cuda.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rc_material), sizeof(rc_texture),
+             sizeof(rc_image), sizeof(rc_perlin), sizeof(rc_instance), sizeof(rc_bvh_node), sizeof(rc_scene),
+             sizeof(rc_camera), sizeof(rc_params), sizeof(rc_tone_map), sizeof(rc_stats));
+      return 0; }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    mirrors = [capi.rc_material, capi.rc_texture, capi.rc_image, capi.rc_perlin, capi.rc_instance,
+               capi.rc_bvh_node, capi.rc_scene, capi.rc_camera, capi.rc_params, capi.rc_tone_map, capi.rc_stats]
+    assert sizes == [C.sizeof(m) for m in mirrors]
+
+
+def test_no_gpu_means_a_loud_error_not_a_fallback(cuda_lib):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    ctx = C.c_void_p()
+    st = cuda_lib.rc_create(None, 1, C.byref(ctx))
+    assert st == capi.RC_ERR_NO_DEVICE
+    assert b"no CPU fallback" in cuda_lib.rc_last_error()
+    with pytest.raises(capi.RacerCudaError):
+        harness.CudaRenderer([0])
+
+
+def test_null_arguments_are_rejected(cuda_lib):
+    assert cuda_lib.rc_create(None, 1, None) == capi.RC_ERR_INVALID
+    assert cuda_lib.rc_upload_scene(None, None) == capi.RC_ERR_INVALID
+    assert cuda_lib.rc_destroy(None) == capi.RC_OK
+    p = harness.make_params(4, 4, 1, 1)
+    assert cuda_lib.rc_render(None, C.byref(p), None, None) == capi.RC_ERR_INVALID
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under racer_tracer_b200/ may import, link or open oracle/."""
+    pkg = os.path.join(ROOT, "racer_tracer_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".sh")):
+                text = open(os.path.join(d, f), errors="replace").read()
+                assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+    out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out

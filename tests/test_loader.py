@@ -1,0 +1,169 @@
+"""Host-side logic: YAML scene/config loading, flattening, canonical ids, BVH
+(src/scene/yml.rs, src/config.rs, src/camera.rs:393-464, src/bvh_node.rs)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SCENES, scene_path
+from racer_tracer_b200 import capi, harness
+
+
+def load(name, **kw):
+    return harness.load_scene(scene_path(name), **kw)
+
+
+def test_config_yml(cfg):
+    assert (cfg.render.samples, cfg.render.max_depth) == (200, 20)          # config.yml:8-13
+    assert (cfg.render.num_threads_width, cfg.render.num_threads_height) == (10, 10)
+    assert (cfg.preview.samples, cfg.preview.max_depth, cfg.preview.scale) == (40, 10, 4)
+    assert (cfg.width, cfg.height) == (600, 600)
+    assert harness.make_tone_map(cfg.tone_map).type == capi.RC_TONE_ACES       # config.yml:36-38
+
+
+@pytest.mark.parametrize("name,n_prims,kinds", [
+    ("three_balls", 5, {capi.RC_PRIM_SPHERE: 5}),
+    ("emissive", 4, {capi.RC_PRIM_SPHERE: 3, capi.RC_PRIM_XY_RECT: 1}),
+    ("noise_and_textures", 4, {capi.RC_PRIM_SPHERE: 4}),
+    ("cornell_box", 6, {capi.RC_PRIM_YZ_RECT: 2, capi.RC_PRIM_XZ_RECT: 3, capi.RC_PRIM_XY_RECT: 1}),
+    ("clown", 23, {capi.RC_PRIM_SPHERE: 23}),
+])
+def test_scene_inventory(name, n_prims, kinds):
+    fs = load(name)
+    assert fs.c.n_prims == n_prims
+    types = fs.np["prim_type"]
+    assert {k: int((types == k).sum()) for k in kinds} == kinds
+
+
+def test_canonical_ids_follow_sorted_lowercased_keys():
+    fs = load("cornell_box")
+    assert fs.object_keys == ["light", "piece_1", "piece_2", "piece_3", "piece_4", "piece_5"]
+    ids = sorted(int(i) for i in fs.np["prim_id"])
+    assert ids == [(k << 3) for k in range(1, 7)]                     # (object << 3) | side, side 0
+    two = load("two_balls")                                           # keys SphereA / SphereB
+    assert two.object_keys == ["spherea", "sphereb"]
+
+
+def test_cornell_materials_and_background():
+    fs = load("cornell_box")
+    c = fs.c
+    assert c.bg_type == capi.RC_BG_SOLID and list(c.bg_a) == [0.0, 0.0, 0.0]
+    by_key = {}
+    for i in range(c.n_prims):
+        key = fs.object_keys[(int(fs.np["prim_id"][i]) >> 3) - 1]
+        m = fs.materials[int(fs.np["prim_material"][i])]
+        by_key[key] = (m.type, list(fs.textures[m.texture].color))
+    assert by_key["light"] == (capi.RC_MAT_DIFFUSE_LIGHT, [15.0, 15.0, 15.0])
+    assert by_key["piece_1"] == (capi.RC_MAT_LAMBERTIAN, [0.12, 0.45, 0.15])
+    assert by_key["piece_2"] == (capi.RC_MAT_LAMBERTIAN, [0.65, 0.05, 0.05])
+    assert fs.tone_map_cfg is None       # inherits Aces from config.yml (Q25)
+
+
+def test_default_background_is_the_sky():
+    c = load("three_balls").c
+    assert c.bg_type == capi.RC_BG_SKY and list(c.bg_a) == [1.0, 1.0, 1.0] and list(c.bg_b) == [0.5, 0.7, 1.0]
+
+
+def test_camera_merge_scene_overrides_config(cfg):
+    fs = load("three_balls")
+    cam = harness.merged_camera(fs.camera_cfg, cfg.camera)
+    assert cam == {"vfov": 20.0, "aperture": 0.1, "focus_distance": 10.0, "pos": [0.0, 2.0, 10.0],
+                   "look_at": [0.0, 0.0, 0.0]}
+    assert harness.merged_camera(None, None) == {"vfov": 20.0, "aperture": 0.0, "focus_distance": 1000.0,
+                                                 "pos": [0.0, 0.0, 0.0], "look_at": [0.0, 0.0, -1.0]}
+    assert harness.merged_camera({"vfov": 33}, cfg.camera)["focus_distance"] == 10000.0
+
+
+def test_tone_map_scene_overrides_config(cfg):
+    job = harness.prepare_job(scene_path("three_balls"), cfg)
+    assert job.tone_map.type == capi.RC_TONE_NONE                     # three_balls.yml tone_map: None
+    job = harness.prepare_job(scene_path("cornell_box"), cfg)
+    assert job.tone_map.type == capi.RC_TONE_ACES and (job.width, job.height) == (600, 600)
+
+
+def test_textures_checker_image_noise():
+    fs = load("noise_and_textures")
+    kinds = sorted(t.type for t in fs.textures)
+    assert kinds == [capi.RC_TEX_SOLID, capi.RC_TEX_SOLID, capi.RC_TEX_CHECKER, capi.RC_TEX_IMAGE, capi.RC_TEX_NOISE]
+    ck = next(t for t in fs.textures if t.type == capi.RC_TEX_CHECKER)
+    assert list(fs.textures[ck.a].color) == [0.5, 1.0, 0.5] and list(fs.textures[ck.b].color) == [0.8, 0.8, 0.8]
+    assert ck.scale == 10.0
+    nz = next(t for t in fs.textures if t.type == capi.RC_TEX_NOISE)
+    assert (nz.b, nz.scale, list(nz.color)) == (7, 4.0, [1.0, 1.0, 1.0])
+    w, h, px = fs.images[0]
+    assert (w, h) == (1024, 512) and px.shape == (512, 1024, 4) and (px[..., 3] == 255).all()
+
+
+@pytest.mark.parametrize("name", SCENES + ["two_balls"])
+def test_bvh_is_a_valid_preorder_tree(name):
+    fs = load(name)
+    nodes, n = fs.nodes, fs.c.n_prims
+    assert len(nodes) == 2 * n - 1
+    seen = []
+
+    def walk(i):
+        nd = nodes[i]
+        if nd.left < 0:
+            first = ~nd.left
+            assert nd.right == 1
+            seen.append(first)
+            box = fs.np["prim_aabb"][first]
+            assert list(nd.bmin) == list(box[:3]) and list(nd.bmax) == list(box[3:])
+            return np.array(nd.bmin), np.array(nd.bmax)
+        assert nd.left == i + 1 and nd.right > nd.left
+        lo_l, hi_l = walk(nd.left)
+        lo_r, hi_r = walk(nd.right)
+        assert np.array_equal(np.minimum(lo_l, lo_r), np.array(nd.bmin))     # aabb.rs:95-114
+        assert np.array_equal(np.maximum(hi_l, hi_r), np.array(nd.bmax))
+        return np.array(nd.bmin), np.array(nd.bmax)
+    walk(0)
+    assert seen == list(range(n))       # primitives are stored in DFS leaf order
+
+
+def test_rect_and_sphere_boxes():
+    fs = load("cornell_box")
+    i = [k for k in range(6) if fs.object_keys[(int(fs.np["prim_id"][k]) >> 3) - 1] == "light"][0]
+    assert list(fs.np["prim_aabb"][i]) == [213.0, 554.0 - 0.0001, 227.0, 343.0, 554.0 + 0.0001, 332.0]   # xz_rect.rs:51-56
+    fs = load("three_balls")
+    i = [k for k in range(5) if fs.object_keys[(int(fs.np["prim_id"][k]) >> 3) - 1] == "dialectric_inner"][0]
+    assert list(fs.np["prim_data"][i]) == [-1.0, 0.0, -1.0, -0.4, 0.0]
+    assert list(fs.np["prim_aabb"][i]) == [-1.4, -0.4, -1.4, -0.6, 0.4, -0.6]    # Aabb::new orders min/max (aabb.rs:10-26)
+
+
+def test_loader_errors(tmp_path):
+    bad = tmp_path / "bad.yml"
+    bad.write_text("textures: {}\nmaterials: {}\ngeometry:\n  a:\n    Sphere: {pos: [0,0,0], radius: 1, material: nope}\n")
+    with pytest.raises(harness.SceneLoadError, match="UnknownMaterial"):
+        harness.load_scene(str(bad))
+    bad.write_text("textures: {}\nmaterials:\n  m:\n    Lambertian: {texture: t}\ngeometry: {}\n")
+    with pytest.raises(harness.SceneLoadError, match='Failed to find texture "t" for lambertian material "m"'):
+        harness.load_scene(str(bad))
+    bad.write_text("materials: {}\ngeometry: {}\n")
+    with pytest.raises(harness.SceneLoadError, match="textures"):
+        harness.load_scene(str(bad))
+
+
+def test_box_rotate_translate_flattening(tmp_path):
+    """Box -> six rects in Boxx::new order; RotateY/Translate entries are keyed by
+    their child's name (Q26); RotateY keeps the reference's bounding-box formula (Q14)."""
+    f = tmp_path / "boxes.yml"
+    f.write_text("""
+textures: {w: {SolidColor: {color: {color: [0.7, 0.7, 0.7]}}}}
+materials: {w: {Lambertian: {texture: w}}}
+geometry:
+  box1: {Box: {min: {pos: [0, 0, 0]}, max: {pos: [165, 330, 165]}, material: w}}
+  rot:  {RotateY: {key: box1, degrees: 15}}
+  mov:  {Translate: {key: box1, pos: [265, 0, 295]}}
+""")
+    fs = harness.load_scene(str(f))
+    assert fs.c.n_prims == 6 and fs.object_keys == ["box1"]
+    assert [int(i) for i in fs.np["prim_id"]] == [8 + s for s in range(6)]
+    assert [int(t) for t in fs.np["prim_type"]] == [1, 1, 2, 2, 3, 3]
+    assert list(fs.np["prim_data"][0]) == [0, 165, 0, 330, 165] and list(fs.np["prim_data"][5]) == [0, 330, 0, 165, 0]
+    inst = fs.instances[0]
+    assert inst.flags == 3 and list(inst.offset) == [265.0, 0.0, 295.0]
+    assert inst.sin_theta == pytest.approx(np.sin(np.radians(15))) and inst.cos_theta == pytest.approx(np.cos(np.radians(15)))
+    s, c = np.sin(np.radians(15)), np.cos(np.radians(15))
+    xs = [c * x + s + z for x in (0, 165) for z in (0, 165)]           # `cos*x + sin + z` verbatim
+    assert fs.np["prim_aabb"][0][0] == pytest.approx(min(xs) + 265) and fs.np["prim_aabb"][0][3] == pytest.approx(max(xs) + 265)
+    assert len(fs.nodes) == 1 and fs.nodes[0].right == 6
