@@ -62,6 +62,7 @@ struct DeviceState {
     bool own_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf<DevPrim> prims;
+    DevBuf<DevPrim> prims_lin;
     DevBuf<DevNode> nodes;
     DevBuf<DevTexture> textures;
     DevBuf<DevInstance> instances;
@@ -102,7 +103,7 @@ void free_scene(DeviceState& d) {
     for (auto a : d.arrays) cudaFreeArray(a);
     d.tex.clear();
     d.arrays.clear();
-    d.prims.release(); d.nodes.release(); d.textures.release(); d.instances.release();
+    d.prims.release(); d.prims_lin.release(); d.nodes.release(); d.textures.release(); d.instances.release();
     d.perlin.release(); d.perm.release(); d.prims_d.release(); d.prim_kind.release();
     d.prim_id.release(); d.nodes_d.release();
 }
@@ -285,7 +286,8 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         DeviceState& d = ctx->devs[k];
         CUDA_TRY(cudaSetDevice(d.device));
         KParams kp = ctx->kp;
-        kp.prims = d.prims.p; kp.nodes = d.nodes.p; kp.textures = d.textures.p; kp.instances = d.instances.p;
+        kp.prims = d.prims.p; kp.prims_lin = d.prims_lin.p; kp.nodes = d.nodes.p; kp.textures = d.textures.p;
+        kp.instances = d.instances.p;
         kp.perlin = d.perlin.p; kp.perlin_perm = d.perm.p;
         for (size_t i = 0; i < d.tex.size(); ++i) kp.images[i] = d.tex[i];
         kp.segment_counter = d.counter.p;
@@ -521,8 +523,16 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     kp.n_prims = s->n_prims; kp.n_nodes = s->n_nodes; kp.n_perlin = s->n_perlin;
     kp.bg_a = f4(s->bg_a[0], s->bg_a[1], s->bg_a[2], bits(s->bg_type));
     kp.bg_b = f4(s->bg_b[0], s->bg_b[1], s->bg_b[2], 0.f);
+    // type-sorted table for the linear modes (stable: canonical order within a kind)
+    std::vector<DevPrim> prims_lin;
+    prims_lin.reserve(s->n_prims);
+    for (int type = 0; type < 4; ++type) {
+        for (int i = 0; i < s->n_prims; ++i)
+            if (kinds[i] == type) prims_lin.push_back(prims[i]);
+        kp.lin_end[type] = (int)prims_lin.size();
+    }
     for (int i = 0; i < RT_MAX_CONST_PRIMS; ++i)
-        if (i < s->n_prims) kp.cprims[i] = prims[i]; else std::memset(&kp.cprims[i], 0, sizeof(DevPrim));
+        if (i < s->n_prims) kp.cprims[i] = prims_lin[i]; else std::memset(&kp.cprims[i], 0, sizeof(DevPrim));
     for (int i = 0; i < RT_MAX_IMAGES; ++i) {
         kp.image_w[i] = i < s->n_images ? s->images[i].width : 0;
         kp.image_h[i] = i < s->n_images ? s->images[i].height : 0;
@@ -534,6 +544,7 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
         free_scene(d);
         CUDA_TRY(cudaSetDevice(d.device));
         CUDA_TRY(d.prims.assign(prims));
+        CUDA_TRY(d.prims_lin.assign(prims_lin));
         CUDA_TRY(d.nodes.assign(nodes));
         CUDA_TRY(d.textures.assign(textures));
         CUDA_TRY(d.perlin.assign(perlin));
@@ -708,7 +719,8 @@ int rc_primary_aov(rc_ctx* ctx, const rc_params* p, int32_t precision, uint32_t*
     CUDA_TRY(d_id.resize(np)); CUDA_TRY(d_t.resize(np)); CUDA_TRY(d_n.resize(np * 3)); CUDA_TRY(d_p.resize(np * 3));
     if (precision == 32) {
         KParams kp = ctx->kp;
-        kp.prims = d.prims.p; kp.nodes = d.nodes.p; kp.textures = d.textures.p; kp.instances = d.instances.p;
+        kp.prims = d.prims.p; kp.prims_lin = d.prims_lin.p; kp.nodes = d.nodes.p; kp.textures = d.textures.p;
+        kp.instances = d.instances.p;
         kp.perlin = d.perlin.p; kp.perlin_perm = d.perm.p;
         kp.segment_counter = nullptr;
         rc_params q = *p;

@@ -43,7 +43,7 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
         dst += P.n_nodes * 2;
     }
     if (MODE == RT_MODE_SMEM_BVH || MODE == RT_MODE_SMEM_LINEAR) {
-        const float4* src = reinterpret_cast<const float4*>(P.prims);
+        const float4* src = reinterpret_cast<const float4*>(MODE == RT_MODE_SMEM_LINEAR ? P.prims_lin : P.prims);
         for (int i = threadIdx.x; i < P.n_prims * 3; i += blockDim.x) dst[i] = __ldg(src + i);
         L.prims = reinterpret_cast<const DevPrim*>(dst);
         dst += P.n_prims * 3;
@@ -63,7 +63,7 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
 
 template <int MODE, class Scene>
 RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& t) {
-    if constexpr (MODE == RT_MODE_CONST_LINEAR || MODE == RT_MODE_SMEM_LINEAR) return closest_hit_linear(S, P.n_prims, r, last_prim, t);
+    if constexpr (MODE == RT_MODE_CONST_LINEAR || MODE == RT_MODE_SMEM_LINEAR) return closest_hit_linear(S, P.lin_end, r, last_prim, t);
     else return closest_hit_bvh(S, P.n_nodes, r, last_prim, t);
 }
 
@@ -107,8 +107,8 @@ RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float
             }
         } else {
             uint4 w = philox4x32<ROUNDS>(c.pixel, sample, 0u, RT_TAG_LENS << 24, P.key0, P.key1);
-            float r = sqrtf(u24(w.x)), s, cs;
-            sincospif(2.0f * u24(w.y), &s, &cs);
+            float r = fast_sqrt(u24(w.x)), s, cs;
+            fast_sincos_2pi(u24(w.y), s, cs);
             dx = r * cs; dy = r * s;
         }
         vec3f offset = (P.cam.lens_radius * dx) * P.cam.right + (P.cam.lens_radius * dy) * P.cam.up;
@@ -156,13 +156,13 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
         nd = refl + pb.y * rv;
         if (dot(nd, h.n) < 0.0f) return false;
     } else {  // dialectric.rs:25-56
-        float ratio = h.front_face ? __frcp_rn(pb.y) : pb.y;
+        float ratio = h.front_face ? fast_rcp(pb.y) : pb.y;
         vec3f ud = unit_vector(r.d);
         float cos_theta = fminf(-dot(ud, h.n), 1.0f);
-        float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+        float sin_theta = fast_sqrt(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
         bool do_reflect = ratio * sin_theta > 1.0f;
         if (!do_reflect) {
-            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            float r0 = (1.0f - ratio) * fast_rcp(1.0f + ratio);
             r0 = r0 * r0;
             float m = 1.0f - cos_theta, m2 = m * m;
             float refl = r0 + (1.0f - r0) * (m2 * m2 * m);  // powf(5), dialectric.rs:17-22
@@ -171,7 +171,7 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
         if (do_reflect) nd = reflect(ud, h.n);
         else {  // refract, vec3.rs:416-422
             vec3f perp = ratio * (ud + cos_theta * h.n);
-            vec3f par = (-sqrtf(fabsf(1.0f - length_squared(perp)))) * h.n;
+            vec3f par = (-fast_sqrt(fabsf(1.0f - length_squared(perp)))) * h.n;
             nd = perp + par;
         }
         col = mk3(1.0f, 1.0f, 1.0f);

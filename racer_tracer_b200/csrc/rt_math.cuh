@@ -25,11 +25,16 @@ template <typename T> RT_HD T dot(Vec3T<T> a, Vec3T<T> b) { return a.x * b.x + a
 template <typename T> RT_HD T length_squared(Vec3T<T> a) { return dot(a, a); }
 template <typename T> RT_HD T axis_of(Vec3T<T> a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
-RT_D float rt_sqrt(float v) { return sqrtf(v); }
+RT_D float rt_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 RT_D double rt_sqrt(double v) { return sqrt(v); }
-RT_D float rt_rsqrt(float v) { return rsqrtf(v); }
+RT_D float rt_rsqrt(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 RT_D double rt_rsqrt(double v) { return 1.0 / sqrt(v); }
-RT_D float rt_rcp(float v) { return __frcp_rn(v); }
+// single-instruction SFU approximations (<= 2 ulp); the render path does not
+// need IEEE-rounded reciprocals / square roots
+RT_D float fast_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+RT_D float fast_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+RT_D float fast_rsqrt(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+RT_D float rt_rcp(float v) { return fast_rcp(v); }
 RT_D double rt_rcp(double v) { return 1.0 / v; }
 
 template <typename T> RT_D Vec3T<T> unit_vector(Vec3T<T> a) { return a * rt_rsqrt(length_squared(a)); }
@@ -50,14 +55,9 @@ RT_HD uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint3
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
         if (r > 0) { k0 += PHILOX_W0; k1 += PHILOX_W1; }
-#ifdef __CUDA_ARCH__
-        uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
-        uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
-#else
-        uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
+        uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;  // IMAD.WIDE.U32
         uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
         uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-#endif
         uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     }

@@ -82,9 +82,11 @@ struct KParams {
     int tile_first, tile_stride, n_tiles;   // interleaved tile partition
     int tiles_x, tile_w, tile_h;
     int n_prims, n_nodes;
+    int lin_end[4];             // type-sorted linear table: [0,lin_end[0]) spheres, then xy, xz, yz rects
     int n_perlin;
     int lens_enabled;
-    const DevPrim* prims;       // all primitives (global memory)
+    const DevPrim* prims;       // all primitives, BVH depth-first order (global memory)
+    const DevPrim* prims_lin;   // the same primitives sorted by type (linear modes)
     const DevNode* nodes;       // threaded BVH (global memory)
     const DevTexture* textures;
     const DevInstance* instances;
@@ -93,7 +95,7 @@ struct KParams {
     cudaTextureObject_t images[RT_MAX_IMAGES];
     int image_w[RT_MAX_IMAGES], image_h[RT_MAX_IMAGES];
     unsigned long long* segment_counter;
-    DevPrim cprims[RT_MAX_CONST_PRIMS];   // copy of prims for the linear constant-bank path
+    DevPrim cprims[RT_MAX_CONST_PRIMS];   // type-sorted copy for the linear constant-bank path
 };
 
 // ---------------------------------------------------------------------------
@@ -170,7 +172,7 @@ RT_D T sphere_hit(Vec3T<T> o, Vec3T<T> d, T a, T inv_a, Vec3T<T> ctr, T radius, 
     T s = rt_sqrt(disc);
     T q = b < T(0) ? (s - b) : -(b + s);
     T r_qa = q * inv_a;
-    T r_cq = c / q;
+    T r_cq = c * rt_rcp(q);
     T near_root = b < T(0) ? r_cq : r_qa;
     T far_root = b < T(0) ? r_qa : r_cq;
     // "nearest root that lies in the acceptable range", sphere.rs:51-58
@@ -186,12 +188,12 @@ RT_D T sphere_hit(Vec3T<T> o, Vec3T<T> d, T a, T inv_a, Vec3T<T> ctr, T radius, 
 RT_D vec3f sphere_normal(vec3f o, vec3f d, float a, float inv_a, vec3f ctr, float radius, float t) {
     vec3f oc = o - ctr;
     float oc2 = dot(oc, oc), r2 = radius * radius;
-    float inv_r = __frcp_rn(radius);
+    float inv_r = fast_rcp(radius);
     if (oc2 > RT_SPHERE_FAR_RATIO * r2) {
         float b = dot(oc, d);
         float ba = b * inv_a;
         vec3f l = mk3(oc.x - ba * d.x, oc.y - ba * d.y, oc.z - ba * d.z);
-        float h = sqrtf(fmaxf(0.0f, (r2 - dot(l, l)) * inv_a));   // |t - t_closest|
+        float h = fast_sqrt(fmaxf(0.0f, (r2 - dot(l, l)) * inv_a));   // |t - t_closest|
         float dt = (t < -ba) ? -h : h;                            // near or far root
         return mk3((l.x + dt * d.x) * inv_r, (l.y + dt * d.y) * inv_r, (l.z + dt * d.z) * inv_r);
     }
@@ -216,7 +218,6 @@ RT_D T rect_hit(int type, Vec3T<T> o, Vec3T<T> d, Vec3T<T> inv_d, T a0, T a1, T 
 template <typename T>
 struct RayT {
     Vec3T<T> o, d, inv_d;
-    T a, inv_a;  // |d|^2 and its reciprocal
 };
 
 template <typename T>
@@ -224,8 +225,6 @@ RT_D RayT<T> make_ray(Vec3T<T> o, Vec3T<T> d) {
     RayT<T> r;
     r.o = o; r.d = d;
     r.inv_d = mk3<T>(rt_rcp(d.x), rt_rcp(d.y), rt_rcp(d.z));
-    r.a = dot(d, d);
-    r.inv_a = rt_rcp(r.a);
     return r;
 }
 
@@ -235,23 +234,62 @@ RT_D float prim_test(const Scene& S, int i, const RayT<float>& r, int last_prim,
     float4 a = S.pa(i), b = S.pb(i);
     int type = kinds_prim(b.z);
     bool self = (i == last_prim);
-    if (type == RT_PRIM_SPHERE)
-        return sphere_hit<float>(r.o, r.d, r.a, r.inv_a, mk3(a.x, a.y, a.z), a.w, b.x, self, (float)RT_T_MIN, t_max);
+    if (type == RT_PRIM_SPHERE) {
+        const float aa = dot(r.d, r.d);
+        return sphere_hit<float>(r.o, r.d, aa, fast_rcp(aa), mk3(a.x, a.y, a.z), a.w, b.x, self, (float)RT_T_MIN, t_max);
+    }
     if (self) return -1.0f;
     return rect_hit<float>(type, r.o, r.d, r.inv_d, a.x, a.y, a.z, a.w, b.x, (float)RT_T_MIN, t_max);
 }
 
-// Linear closest hit in index order: the later primitive wins an exact tie
-// (`t <= closest`), as src/shared_scene.rs:37-53 and sphere.rs:53.
+// Linear closest hit over the TYPE-SORTED table (spheres, xy, xz, yz rects):
+// one tight loop per primitive kind with the axes hard-wired, no per-primitive
+// type decode and no early exits — every rectangle is a fixed sequence of
+// 3 FFMA + predicate compares + 2 selects, with the rectangle's constants
+// read through uniform (warp-wide) addresses.  Within the table a later
+// primitive wins an exact tie (`t <= closest`, src/shared_scene.rs:37-53,
+// sphere.rs:53); exact ties are otherwise undefined in the reference (Q13).
+template <int AXIS_N, class Scene>
+RT_D void rect_group(const Scene& S, int begin, int end, const RayT<float>& r, int last_prim, float& best_t, int& best) {
+    // plane axis n, in-plane axes (a, b): xy -> (z; x, y), xz -> (y; x, z), yz -> (x; y, z)
+    const float on = AXIS_N == 2 ? r.o.z : (AXIS_N == 1 ? r.o.y : r.o.x);
+    const float in = AXIS_N == 2 ? r.inv_d.z : (AXIS_N == 1 ? r.inv_d.y : r.inv_d.x);
+    const float oa = AXIS_N == 0 ? r.o.y : r.o.x, da = AXIS_N == 0 ? r.d.y : r.d.x;
+    const float ob = AXIS_N == 2 ? r.o.y : r.o.z, db = AXIS_N == 2 ? r.d.y : r.d.z;
+    const float shift = -on * in;
+#pragma unroll 2
+    for (int i = begin; i < end; ++i) {
+        const float4 a = S.pa(i);
+        const float k = S.pb(i).x;
+        const float t = fmaf(k, in, shift);              // (k - o_n) / d_n
+        const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
+        const bool hit = (t >= (float)RT_T_MIN) & (t <= best_t) & (pa >= a.x) & (pa <= a.y) & (pb >= a.z) & (pb <= a.w) &
+                         (i != last_prim);
+        best_t = hit ? t : best_t;
+        best = hit ? i : best;
+    }
+}
+
 template <class Scene>
-RT_D int closest_hit_linear(const Scene& S, int n_prims, const RayT<float>& r, int last_prim, float& best_t) {
+RT_D int closest_hit_linear(const Scene& S, const int* lin_end, const RayT<float>& r, int last_prim, float& best_t) {
     int best = -1;
     best_t = __int_as_float(0x7f800000);
+    const int n_sph = lin_end[0];
+    if (n_sph > 0) {
+        const float a = dot(r.d, r.d), inv_a = fast_rcp(a);
 #pragma unroll 1
-    for (int i = 0; i < n_prims; ++i) {
-        float t = prim_test(S, i, r, last_prim, best_t);
-        if (t >= 0.0f) { best_t = t; best = i; }
+        for (int i = 0; i < n_sph; ++i) {
+            const float4 pa = S.pa(i);
+            const float t = sphere_hit<float>(r.o, r.d, a, inv_a, mk3(pa.x, pa.y, pa.z), pa.w, S.pb(i).x, i == last_prim,
+                                              (float)RT_T_MIN, best_t);
+            const bool hit = t >= 0.0f;
+            best_t = hit ? t : best_t;
+            best = hit ? i : best;
+        }
     }
+    rect_group<2>(S, lin_end[0], lin_end[1], r, last_prim, best_t, best);
+    rect_group<1>(S, lin_end[1], lin_end[2], r, last_prim, best_t, best);
+    rect_group<0>(S, lin_end[2], lin_end[3], r, last_prim, best_t, best);
     return best;
 }
 
@@ -314,7 +352,8 @@ RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t) {
     h.p = r.o + t * r.d;  // Ray::at
     if (type == RT_PRIM_SPHERE) {
         vec3f ctr = mk3(a.x, a.y, a.z);
-        h.outward = sphere_normal(r.o, r.d, r.a, r.inv_a, ctr, a.w, t);  // sphere.rs:61
+        const float aa = dot(r.d, r.d);
+        h.outward = sphere_normal(r.o, r.d, aa, fast_rcp(aa), ctr, a.w, t);  // sphere.rs:61
         h.p = ctr + a.w * h.outward;   // the point on the surface that normal belongs to
     } else {
         h.outward = mk3(type == RT_PRIM_YZ ? 1.0f : 0.0f, type == RT_PRIM_XZ ? 1.0f : 0.0f,
@@ -439,11 +478,19 @@ struct RngCtx {
     uint32_t key0, key1, pixel, sample;
 };
 
+// (cos, sin) of 2*pi*u for u in [0,1): the SFU sine/cosine are evaluated at
+// 2*pi*u - pi (their accurate range) and negated; abs error ~5e-7.
+RT_D void fast_sincos_2pi(float u, float& s, float& c) {
+    const float phi = fmaf(u, 6.283185307179586f, -3.14159265358979323846f);
+    s = -__sinf(phi);
+    c = -__cosf(phi);
+}
+
 RT_D vec3f sphere_direct(float u1, float u2) {
     float z = 1.0f - 2.0f * u1;
-    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float r = fast_sqrt(fmaxf(0.0f, 1.0f - z * z));
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    fast_sincos_2pi(u2, s, c);
     return mk3(r * c, r * s, z);
 }
 

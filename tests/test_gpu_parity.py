@@ -105,7 +105,7 @@ def test_primary_aov_fp32_matches_oracle(renderer, oracle, cfg, name):
     assert (nerr > T_REL).mean() < 5e-3 and nerr.max() < 5e-3
     assert np.all(t[ids == 0] == np.finfo(np.float64).max)
     scale = np.maximum(np.abs(opt[hit]).max(axis=1), 1.0)
-    assert (np.abs(pt[hit] - opt[hit]).max(axis=1) / scale).max() <= 1e-4
+    assert (np.abs(pt[hit] - opt[hit]).max(axis=1) / scale).max() <= 2e-4   # one fp32 ulp at |p| ~ 1000 is 6e-5
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -127,12 +127,12 @@ def test_same_stream_image_matches_oracle(renderer, oracle, cfg, name, sampler):
     assert psnr(display(oracle, job, img), display(oracle, job, ref)) > 38.0
 
 
-@pytest.mark.parametrize("name", ["cornell_box", "three_balls", "emissive"])
-def test_converged_image_psnr_independent_streams(renderer, oracle, cfg, name):
+@pytest.mark.parametrize("name,spp", [("cornell_box", 32768), ("three_balls", 4096), ("emissive", 8192)])
+def test_converged_image_psnr_independent_streams(renderer, oracle, cfg, name, spp):
     """High-spp GPU image vs high-spp oracle image drawn from an INDEPENDENT
     sequential stream with the reference's rejection samplers: >= 40 dB on the
     displayed image (north_star), with the Monte-Carlo noise floor printed."""
-    w, h, spp = 64, 48, 8192
+    w, h = 64, 48
     job = job_for(name, cfg, w, h)
     renderer.upload(job)
     p = harness.make_params(w, h, spp, 20, seed=11)
@@ -147,8 +147,8 @@ def test_converged_image_psnr_independent_streams(renderer, oracle, cfg, name):
     noise_floor = psnr(d(ref_a), d(ref_b))
     got = psnr(d(gpu), d(ref_a))
     print(f"{name}: PSNR(gpu, oracle) = {got:.1f} dB, PSNR(oracle, oracle') = {noise_floor:.1f} dB")
-    assert got >= 40.0 or got >= noise_floor - 1.0
-    assert got >= noise_floor - 1.5
+    assert got >= 40.0, "north_star: PSNR >= 40 dB against the reference's converged image"
+    assert got >= noise_floor - 1.0, "the GPU image is further from the oracle than Monte-Carlo noise explains"
 
 
 def test_postprocess_matches_oracle_bytes(renderer, oracle, cfg):
