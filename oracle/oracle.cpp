@@ -67,8 +67,9 @@ struct Ray {  // src/ray.rs
 // ---------------------------------------------------------------------------
 // RNG.  The reference draws from rand::thread_rng() (src/util.rs:9-23), which
 // is OS-seeded and unreproducible.  Two back ends replace it:
-//   Philox4x32 keyed (seed) with counter (pixel, sample, bounce, tag|block) —
-//   the streams the GPU consumes (DESIGN.md "RNG streams");
+//   Philox2x32 keyed by the seed with counter (pixel | j, sample | bounce | tag) —
+//   the streams the GPU consumes (DESIGN.md "RNG streams"); Philox4x32 is kept
+//   for the Perlin gradient tables the host derives from the seed;
 //   xoshiro256** — an independent sequential stream drawn in call order.
 // ---------------------------------------------------------------------------
 inline void philox4x32(const uint32_t c_in[4], const uint32_t k_in[2], int rounds, uint32_t out[4]) {
@@ -85,6 +86,19 @@ inline void philox4x32(const uint32_t c_in[4], const uint32_t k_in[2], int round
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Philox2x32-R, same paper: 64-bit counter, 32-bit key
+inline void philox2x32(uint32_t c0, uint32_t c1, uint32_t key, int rounds, uint32_t out[2]) {
+    const uint32_t M = 0xD256D193u, W = 0x9E3779B9u;
+    for (int r = 0; r < rounds; ++r) {
+        if (r > 0) key += W;
+        uint64_t p = (uint64_t)M * c0;
+        uint32_t hi = (uint32_t)(p >> 32), lo = (uint32_t)p;
+        c0 = hi ^ key ^ c1;
+        c1 = lo;
+    }
+    out[0] = c0; out[1] = c1;
 }
 
 inline double u01_from_bits(uint32_t x) { return (double)(x >> 8) * (1.0 / 16777216.0); }
@@ -108,13 +122,15 @@ struct Xoshiro {
     double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }  // gen::<f64>()
 };
 
-// Stream tags (counter word 3, bits 24..31) — DESIGN.md "RNG streams"; the
-// GPU (racer_tracer_b200/csrc/rt_math.cuh) uses the same table.
-const uint32_t TAG_PIXEL = 1u;   // (pixel, 0, 0, tag): x -> per-pixel u jitter
-const uint32_t TAG_VJIT = 3u;    // (pixel, sample>>2, 0, tag): word sample&3 -> v jitter
-const uint32_t TAG_LENS = 4u;    // (pixel, sample, 0, tag|j): x,y -> lens disk; z -> time
-const uint32_t TAG_BOUNCE = 5u;  // (pixel, sample, (b+1)>>1, tag): b odd -> (x,y), even -> (z,w)
-const uint32_t TAG_REJECT = 6u;  // (pixel, sample, b, tag|j): x,y,z of rejection iteration j
+// Philox2x32 counter layout — DESIGN.md "RNG streams"; the GPU
+// (racer_tracer_b200/csrc/rt_math.cuh) uses the same table:
+//   c0 = pixel (24 bits) | rejection iteration j << 24
+//   c1 = sample (24 bits) | bounce (6 bits) << 24 | tag << 30
+//   key = seed_lo ^ seed_hi
+const uint32_t TAG_PATH = 0u;    // bounce 0: x -> v jitter, y -> ray time; bounce b >= 1: the event's 64 bits
+const uint32_t TAG_PIXEL = 1u;   // x -> per-pixel u jitter
+const uint32_t TAG_LENS = 2u;    // j = 0: direct lens sample; j >= 1: rejection iteration j
+const uint32_t TAG_REJECT = 3u;  // (bounce b, iteration j): three 21-bit uniforms
 
 inline double u21_from_bits(uint32_t x) { return (double)x * (1.0 / 2097152.0); }  // x < 2^21
 
@@ -123,71 +139,66 @@ inline double u21_from_bits(uint32_t x) { return (double)x * (1.0 / 2097152.0); 
 // ORACLE_RNG_SEQUENTIAL each request pulls the next uniforms of the stream.
 struct Draws {
     int backend;
-    uint32_t key[2];
+    uint32_t key;
     int rounds;
     uint32_t pixel, sample;
     Xoshiro* seq;
 
-    void words(uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
-        uint32_t ctr[4] = {pixel, c1, c2, c3};
-        philox4x32(ctr, key, rounds, out);
+    void words(uint32_t j, uint32_t smp, uint32_t bounce, uint32_t tag, uint32_t out[2]) const {
+        philox2x32(pixel | (j << 24), smp | (bounce << 24) | (tag << 30), key, rounds, out);
+    }
+    static void split21(const uint32_t w[2], double u[3]) {
+        u[0] = u21_from_bits(w[0] >> 11); u[1] = u21_from_bits(w[1] >> 11);
+        u[2] = u21_from_bits(((w[0] & 0x7FFu) << 10) | (w[1] & 0x3FFu));
     }
     double pixel_jitter() const {  // cpu.rs:35-36
         if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
-        uint32_t w[4];
-        words(0u, 0u, TAG_PIXEL << 24, w);
+        uint32_t w[2];
+        words(0u, 0u, 0u, TAG_PIXEL, w);
         return u01_from_bits(w[0]);
     }
     double v_jitter() const {  // cpu.rs:39-40
         if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
-        uint32_t w[4];
-        words(sample >> 2, 0u, TAG_VJIT << 24, w);
-        return u01_from_bits(w[sample & 3u]);
+        uint32_t w[2];
+        words(0u, sample, 0u, TAG_PATH, w);
+        return u01_from_bits(w[0]);
     }
-    // j = 0: the direct lens sample (u1, u2) and the time draw; j >= 1: the
-    // j-th iteration of random_in_unit_disk
-    void lens(uint32_t j, double u[3]) const {
-        if (backend != ORACLE_RNG_PHILOX) { u[0] = seq->uniform(); u[1] = seq->uniform(); u[2] = 0.0; return; }
-        uint32_t w[4];
-        words(sample, 0u, (TAG_LENS << 24) | j, w);
-        for (int i = 0; i < 3; ++i) u[i] = u01_from_bits(w[i]);
+    // j = 0: the direct lens sample (u1, u2); j >= 1: the j-th iteration of random_in_unit_disk
+    void lens(uint32_t j, double u[2]) const {
+        if (backend != ORACLE_RNG_PHILOX) { u[0] = seq->uniform(); u[1] = seq->uniform(); return; }
+        uint32_t w[2];
+        words(j, sample, 0u, TAG_LENS, w);
+        u[0] = u01_from_bits(w[0]); u[1] = u01_from_bits(w[1]);
     }
-    double time_u() const {
+    double time_u() const {  // camera.rs:335
         if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
-        double u[3];
-        lens(0, u);
-        return u[2];
-    }
-    // the 64 random bits of bounce b (1-based)
-    void bounce_bits(uint32_t b, uint32_t& lo, uint32_t& hi) const {
-        uint32_t w[4];
-        words(sample, (b + 1u) >> 1, TAG_BOUNCE << 24, w);
-        if (b & 1u) { lo = w[0]; hi = w[1]; } else { lo = w[2]; hi = w[3]; }
+        uint32_t w[2];
+        words(0u, sample, 0u, TAG_PATH, w);
+        return u01_from_bits(w[1]);
     }
     void two(uint32_t b, double u[2]) const {     // lambertian, direct
         if (backend != ORACLE_RNG_PHILOX) { u[0] = seq->uniform(); u[1] = seq->uniform(); return; }
-        uint32_t lo, hi;
-        bounce_bits(b, lo, hi);
-        u[0] = u01_from_bits(lo); u[1] = u01_from_bits(hi);
+        uint32_t w[2];
+        words(0u, sample, b, TAG_PATH, w);
+        u[0] = u01_from_bits(w[0]); u[1] = u01_from_bits(w[1]);
     }
     void three(uint32_t b, double u[3]) const {   // metal, direct: three 21-bit uniforms
         if (backend != ORACLE_RNG_PHILOX) { for (int i = 0; i < 3; ++i) u[i] = seq->uniform(); return; }
-        uint32_t lo, hi;
-        bounce_bits(b, lo, hi);
-        u[0] = u21_from_bits(lo >> 11); u[1] = u21_from_bits(hi >> 11);
-        u[2] = u21_from_bits(((lo & 0x7FFu) << 10) | (hi & 0x3FFu));
+        uint32_t w[2];
+        words(0u, sample, b, TAG_PATH, w);
+        split21(w, u);
     }
     double one(uint32_t b) const {                // dielectric
         if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
-        uint32_t lo, hi;
-        bounce_bits(b, lo, hi);
-        return u01_from_bits(lo);
+        uint32_t w[2];
+        words(0u, sample, b, TAG_PATH, w);
+        return u01_from_bits(w[0]);
     }
     void reject(uint32_t b, uint32_t j, double u[3]) const {  // iteration j of a rejection loop
         if (backend != ORACLE_RNG_PHILOX) { for (int i = 0; i < 3; ++i) u[i] = seq->uniform(); return; }
-        uint32_t w[4];
-        words(sample, b, (TAG_REJECT << 24) | j, w);
-        for (int i = 0; i < 3; ++i) u[i] = u01_from_bits(w[i]);
+        uint32_t w[2];
+        words(j, sample, b, TAG_REJECT, w);
+        split21(w, u);
     }
 };
 
@@ -621,7 +632,7 @@ RayImageData trace_sample(const rc_scene& sc, const rc_camera& cam, const rc_par
         // is 0; the offset is then exactly 0, so the draw is skipped here as on
         // the GPU (with counter-based streams nothing shifts).
         if (cam.lens_radius != 0.0 || dr.backend != ORACLE_RNG_PHILOX) {
-            double q[3];
+            double q[2];
             if (p.sampler == RC_SAMPLER_REJECTION) {
                 for (uint32_t j = 1;; ++j) {  // random_in_unit_disk, util.rs:25-39
                     dr.lens(j, q);
@@ -761,8 +772,7 @@ int oracle_render(const rc_scene* scene, const rc_camera* camera, const rc_param
                     int x = tile.x + col, y = tile.y + row;
                     Draws dr;
                     dr.backend = opt.rng;
-                    dr.key[0] = (uint32_t)params->seed;
-                    dr.key[1] = (uint32_t)(params->seed >> 32);
+                    dr.key = (uint32_t)params->seed ^ (uint32_t)(params->seed >> 32);
                     dr.rounds = rounds;
                     dr.pixel = (uint32_t)(y * params->width + x);
                     dr.sample = 0;
@@ -836,8 +846,7 @@ int oracle_sample_radiance(const rc_scene* scene, const rc_camera* camera, const
         Counters cnt;
         Draws dr;
         dr.backend = ORACLE_RNG_PHILOX;
-        dr.key[0] = (uint32_t)params->seed;
-        dr.key[1] = (uint32_t)(params->seed >> 32);
+        dr.key = (uint32_t)params->seed ^ (uint32_t)(params->seed >> 32);
         dr.rounds = rounds;
         dr.pixel = (uint32_t)pixel_idx[i];
         dr.sample = 0;
@@ -895,6 +904,10 @@ void oracle_quantise_rgba(const double* rgb, int64_t n_pixels, uint8_t* rgba) {
 
 void oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int32_t rounds, uint32_t out[4]) {
     philox4x32(ctr, key, rounds, out);
+}
+
+void oracle_philox2x32(const uint32_t ctr[2], uint32_t key, int32_t rounds, uint32_t out[2]) {
+    philox2x32(ctr[0], ctr[1], key, rounds, out);
 }
 
 int oracle_aabb_hit(const double bmin[3], const double bmax[3], const double origin[3],

@@ -85,6 +85,7 @@ void oracle_quantise_rgba(const double* rgb, int64_t n_pixels, uint8_t* rgba);
 
 /* ---- unit-level entry points for known-answer tests --------------------- */
 void oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int32_t rounds, uint32_t out[4]);
+void oracle_philox2x32(const uint32_t ctr[2], uint32_t key, int32_t rounds, uint32_t out[2]);
 /* Aabb::hit, src/aabb.rs:42-59 */
 int oracle_aabb_hit(const double bmin[3], const double bmax[3], const double origin[3],
                     const double dir[3], double t_min, double t_max);

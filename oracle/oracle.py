@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
         L.oracle_quantise_rgba.restype = None
         L.oracle_philox4x32.argtypes = [C.c_uint32 * 4, C.c_uint32 * 2, C.c_int32, C.c_uint32 * 4]
         L.oracle_philox4x32.restype = None
+        L.oracle_philox2x32.argtypes = [C.c_uint32 * 2, C.c_uint32, C.c_int32, C.c_uint32 * 2]
+        L.oracle_philox2x32.restype = None
         L.oracle_aabb_hit.argtypes = [_d3, _d3, _d3, _d3, C.c_double, C.c_double]
         L.oracle_prim_hit.argtypes = [C.POINTER(rc_scene), C.c_int32, _d3, _d3, C.c_double, C.c_double,
                                       C.c_double * 10]

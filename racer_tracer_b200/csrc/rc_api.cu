@@ -174,18 +174,18 @@ void set_skip(const rc_scene* s, int i, int skip, std::vector<int>& out) {
     }
 }
 
-int pick_mode(const rc_scene* s, size_t& smem_bytes) {
+int pick_mode(const rc_scene* s, bool rects_fit, size_t& smem_bytes) {
     const char* force = std::getenv("RC_SCENE_MODE");  // experiments: const | smem | global | smemlin
     size_t perlin_bytes = (size_t)s->n_perlin * (256 * 16 + 768);
     size_t bvh_bytes = (size_t)s->n_nodes * sizeof(DevNode) + (size_t)s->n_prims * sizeof(DevPrim);
     int mode;
-    if (s->n_prims <= RT_MAX_CONST_PRIMS) mode = RT_MODE_CONST_LINEAR;
+    if (s->n_prims <= RT_MAX_CONST_PRIMS && rects_fit) mode = RT_MODE_CONST_LINEAR;
     else if (s->n_nodes > 0 && bvh_bytes + perlin_bytes <= 200 * 1024) mode = RT_MODE_SMEM_BVH;
     else if (s->n_nodes > 0) mode = RT_MODE_GLOBAL_BVH;
     else mode = RT_MODE_SMEM_LINEAR;
     if (force) {
         std::string f(force);
-        if (f == "const" && s->n_prims <= RT_MAX_CONST_PRIMS) mode = RT_MODE_CONST_LINEAR;
+        if (f == "const" && s->n_prims <= RT_MAX_CONST_PRIMS && rects_fit) mode = RT_MODE_CONST_LINEAR;
         else if (f == "smem" && s->n_nodes > 0) mode = RT_MODE_SMEM_BVH;
         else if (f == "global" && s->n_nodes > 0) mode = RT_MODE_GLOBAL_BVH;
         else if (f == "smemlin") mode = RT_MODE_SMEM_LINEAR;
@@ -233,6 +233,9 @@ int check_params(const rc_params* p) {
     if (p->max_depth < 0) return fail(RC_ERR_INVALID, "max_depth must be >= 0");
     if (p->world < 0 || p->rank < 0 || (p->world > 0 && p->rank >= p->world)) return fail(RC_ERR_INVALID, "bad rank/world");
     if (p->rng_rounds != 0 && p->rng_rounds != 7 && p->rng_rounds != 10) return fail(RC_ERR_INVALID, "rng_rounds must be 0, 7 or 10");
+    if ((long long)p->width * p->height > (1 << 24)) return fail(RC_ERR_INVALID, "more than 2^24 pixels (RNG counter layout)");
+    if (p->samples > (1 << 24)) return fail(RC_ERR_INVALID, "more than 2^24 samples per pixel (RNG counter layout)");
+    if (p->max_depth > 63) return fail(RC_ERR_INVALID, "max_depth > 63 (RNG counter layout)");
     if (p->variant != RC_VARIANT_MEGAKERNEL && p->variant != RC_VARIANT_WAVEFRONT) return fail(RC_ERR_INVALID, "unknown variant");
     if (p->sampler != RC_SAMPLER_DIRECT && p->sampler != RC_SAMPLER_REJECTION) return fail(RC_ERR_INVALID, "unknown sampler");
     if (p->split != RC_SPLIT_TILES && p->split != RC_SPLIT_SAMPLES) return fail(RC_ERR_INVALID, "unknown split");
@@ -244,7 +247,8 @@ void partition(KParams& kp, const rc_params* p, int part, int parts) {
     kp.width = p->width; kp.height = p->height;
     kp.max_depth = p->max_depth;
     kp.fixed_jitter = p->fixed_jitter;
-    kp.key0 = (uint32_t)p->seed; kp.key1 = (uint32_t)(p->seed >> 32);
+    kp.key = (uint32_t)p->seed ^ (uint32_t)(p->seed >> 32);
+    kp.inv_wm1 = 1.0f / (float)(p->width - 1); kp.inv_hm1 = 1.0f / (float)(p->height - 1);
     kp.tile_w = RT_TILE_W; kp.tile_h = RT_TILE_H;
     kp.tiles_x = (p->width + RT_TILE_W - 1) / RT_TILE_W;
     int tiles_y = (p->height + RT_TILE_H - 1) / RT_TILE_H;
@@ -533,11 +537,22 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     }
     for (int i = 0; i < RT_MAX_CONST_PRIMS; ++i)
         if (i < s->n_prims) kp.cprims[i] = prims_lin[i]; else std::memset(&kp.cprims[i], 0, sizeof(DevPrim));
+    std::memset(kp.crect_bounds, 0, sizeof(kp.crect_bounds));
+    std::memset(kp.crect_k, 0, sizeof(kp.crect_k));
+    bool rects_fit = true;
+    for (int g = 0; g < 3; ++g) {
+        int begin = kp.lin_end[g], n = kp.lin_end[g + 1] - begin;
+        if (n > RT_MAX_CONST_RECTS) { rects_fit = false; continue; }
+        for (int j = 0; j < n; ++j) {
+            kp.crect_bounds[g][j] = prims_lin[begin + j].a;
+            kp.crect_k[g][j] = prims_lin[begin + j].b.x;
+        }
+    }
     for (int i = 0; i < RT_MAX_IMAGES; ++i) {
         kp.image_w[i] = i < s->n_images ? s->images[i].width : 0;
         kp.image_h[i] = i < s->n_images ? s->images[i].height : 0;
     }
-    ctx->mode = pick_mode(s, ctx->smem_bytes);
+    ctx->mode = pick_mode(s, rects_fit, ctx->smem_bytes);
     ctx->aov.n_prims = s->n_prims; ctx->aov.n_nodes = s->n_nodes;
 
     for (auto& d : ctx->devs) {

@@ -63,7 +63,8 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
 
 template <int MODE, class Scene>
 RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& t) {
-    if constexpr (MODE == RT_MODE_CONST_LINEAR || MODE == RT_MODE_SMEM_LINEAR) return closest_hit_linear(S, P.lin_end, r, last_prim, t);
+    if constexpr (MODE == RT_MODE_CONST_LINEAR) return closest_hit_linear<true>(P, S, r, last_prim, t);
+    else if constexpr (MODE == RT_MODE_SMEM_LINEAR) return closest_hit_linear<false>(P, S, r, last_prim, t);
     else return closest_hit_bvh(S, P.n_nodes, r, last_prim, t);
 }
 
@@ -82,31 +83,30 @@ RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
     c.px = px; c.py = py;
     c.pixel = (uint32_t)(py * P.width + px);
     float ujit = 0.5f;
-    if (!P.fixed_jitter) ujit = u24(philox4x32<ROUNDS>(c.pixel, 0u, 0u, RT_TAG_PIXEL << 24, P.key0, P.key1).x);
+    if (!P.fixed_jitter) ujit = u24(philox2x32<ROUNDS>(c.pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.key).x);
     float u = ((float)px + ujit) / (float)(P.width - 1);  // once per pixel, cpu.rs:35-36
     // cam.upper_left_corner holds (upper_left_corner - origin), formed in f64 on the host
     c.dir0 = P.cam.upper_left_corner + u * P.cam.horizontal;
     return c;
 }
 
-RT_D float pick_word(uint4 w, int i) { return u24(i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w))); }
-
+// Primary ray of one sample.  `w` = the sample's start block (x -> v jitter).
 template <int SAMPLER, int ROUNDS>
 RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit, vec3f& o, vec3f& d) {
-    float v = ((float)c.py + vjit) / (float)(P.height - 1);  // cpu.rs:39-40
+    float v = ((float)c.py + vjit) * P.inv_hm1;  // cpu.rs:39-40
     d = c.dir0 - v * P.cam.vertical;
     o = P.cam.origin;
     if (P.lens_enabled && !P.fixed_jitter) {  // camera.rs:327-328; skipped when lens_radius == 0 (offset = 0)
         float dx, dy;
         if (SAMPLER == 1) {  // random_in_unit_disk, util.rs:25-39
             for (uint32_t j = 1;; ++j) {
-                uint4 w = philox4x32<ROUNDS>(c.pixel, sample, 0u, (RT_TAG_LENS << 24) | j, P.key0, P.key1);
+                uint2 w = philox2x32<ROUNDS>(c.pixel | (j << 24), rt_ctr1(sample, 0u, RT_TAG_LENS), P.key);
                 dx = 2.0f * u24(w.x) - 1.0f; dy = 2.0f * u24(w.y) - 1.0f;
                 if (dx * dx + dy * dy >= 1.0f) continue;
                 break;
             }
         } else {
-            uint4 w = philox4x32<ROUNDS>(c.pixel, sample, 0u, RT_TAG_LENS << 24, P.key0, P.key1);
+            uint2 w = philox2x32<ROUNDS>(c.pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.key);
             float r = fast_sqrt(u24(w.x)), s, cs;
             fast_sincos_2pi(u24(w.y), s, cs);
             dx = r * cs; dy = r * s;
@@ -148,9 +148,9 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
         vec3f rv;
         if (SAMPLER == 1) rv = reject_in_unit_sphere<ROUNDS>(R, bounce);
         else {
-            uint32_t a = rnd.x, b = rnd.y;
-            float u3 = u21(((a & 0x7FFu) << 10) | (b & 0x3FFu));
-            rv = cbrtf(u3) * sphere_direct(u21(a >> 11), u21(b >> 11));
+            float u1, u2, u3;
+            u21x3(rnd, u1, u2, u3);
+            rv = cbrtf(u3) * sphere_direct(u1, u2);
         }
         vec3f refl = reflect(unit_vector(r.d), h.n);
         nd = refl + pb.y * rv;
@@ -182,18 +182,6 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
     return true;
 }
 
-// The 64 random bits of bounce b (1-based): block (b+1)>>1, words (x,y) for
-// odd b and (z,w) for even b.  `cache` carries the second half between calls.
-template <int ROUNDS>
-RT_D uint2 bounce_bits(const RngCtx& R, uint32_t bounce, uint2& cache) {
-    if (bounce & 1u) {
-        uint4 w = philox4x32<ROUNDS>(R.pixel, R.sample, (bounce + 1u) >> 1, RT_TAG_BOUNCE << 24, R.key0, R.key1);
-        cache = make_uint2(w.z, w.w);
-        return make_uint2(w.x, w.y);
-    }
-    return cache;
-}
-
 // ---------------------------------------------------------------------------
 // Megakernel.  Block = 128 threads = one 16x8 pixel tile; each warp owns an
 // 8x4 sub-tile so its lanes trace neighbouring pixels.  A lane runs all the
@@ -217,7 +205,7 @@ megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) 
     const bool valid = px < P.width && py < P.height;
 
     PixelCtx pc = pixel_setup<ROUNDS>(P, valid ? px : 0, valid ? py : 0);
-    RngCtx R; R.key0 = P.key0; R.key1 = P.key1; R.pixel = pc.pixel; R.sample = 0;
+    RngCtx R; R.key = P.key; R.pixel = pc.pixel; R.sample = 0;
 
     vec3f sum = mk3(0.0f, 0.0f, 0.0f);
     vec3f o = mk3(0.0f, 0.0f, 0.0f), d = o, T = o, Lr = o;
@@ -225,35 +213,23 @@ megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) 
     bool alive = false;
     int depth_left = 0, last_prim = -1;
     uint32_t bounce = 0;
-    uint2 cache = make_uint2(0u, 0u);
-    uint4 vj = make_uint4(0u, 0u, 0u, 0u);
-    int vj_block = -1;
     unsigned nseg = 0;
 
 #pragma unroll 1
     while (true) {
         if (!alive && s < P.s_end) {
             // ---- regenerate: next sample of this pixel ----
-            float vjit = 0.5f;
-            if (!P.fixed_jitter) {
-                if ((s >> 2) != vj_block) {
-                    vj_block = s >> 2;
-                    vj = philox4x32<ROUNDS>(pc.pixel, (uint32_t)vj_block, 0u, RT_TAG_VJIT << 24, P.key0, P.key1);
-                }
-                vjit = pick_word(vj, s & 3);
-            }
             R.sample = (uint32_t)s;
+            float vjit = 0.5f;
+            if (!P.fixed_jitter) vjit = u24(philox2x32<ROUNDS>(pc.pixel, rt_ctr1(R.sample, 0u, RT_TAG_PATH), P.key).x);
             camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d);
             T = mk3(1.0f, 1.0f, 1.0f);
             Lr = mk3(0.0f, 0.0f, 0.0f);
             depth_left = P.max_depth;
             bounce = 0; last_prim = -1;
-            alive = true;
+            alive = depth_left > 0;
             ++s;
-            if (depth_left == 0) {  // renderer.rs:48-56
-                sum = sum + mk3(1.0f, 1.0f, 1.0f);
-                alive = false;
-            }
+            if (!alive) sum = sum + mk3(1.0f, 1.0f, 1.0f);  // renderer.rs:48-56
         }
         if (!__any_sync(0xffffffffu, alive)) {
             if (!__any_sync(0xffffffffu, s < P.s_end)) break;
@@ -271,7 +247,7 @@ megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) 
                 alive = false;
             } else {
                 ++bounce;
-                uint2 rnd = bounce_bits<ROUNDS>(R, bounce, cache);
+                uint2 rnd = philox2x32<ROUNDS>(pc.pixel, rt_ctr1(R.sample, bounce, RT_TAG_PATH), P.key);
                 vec3f emit;
                 bool cont;
                 if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); cont = shade_hit<SAMPLER, ROUNDS>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, emit); }

@@ -43,46 +43,41 @@ template <typename T> RT_D Vec3T<T> unit_vector(Vec3T<T> a) { return a * rt_rsqr
 template <typename T> RT_D Vec3T<T> reflect(Vec3T<T> v, Vec3T<T> n) { return v - (T(2) * dot(v, n)) * n; }
 
 // ---------------------------------------------------------------------------
-// Philox4x32-R (Salmon et al., SC'11).  One call = four 32-bit words.
+// Philox2x32-R (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3",
+// SC'11): 64-bit counter, 32-bit key, 64 random bits per call.  One call costs
+// R x (IMAD.WIDE.U32 + LOP3) with the key schedule in uniform registers, and
+// 64 bits is exactly what one path event consumes, so nothing has to be cached
+// between bounces.
 // ---------------------------------------------------------------------------
-#define PHILOX_M0 0xD2511F53u
-#define PHILOX_M1 0xCD9E8D57u
-#define PHILOX_W0 0x9E3779B9u
-#define PHILOX_W1 0xBB67AE85u
+#define PHILOX2_M 0xD256D193u
+#define PHILOX2_W 0x9E3779B9u
 
 template <int ROUNDS>
-RT_HD uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+RT_HD uint2 philox2x32(uint32_t c0, uint32_t c1, uint32_t key) {
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
-        if (r > 0) { k0 += PHILOX_W0; k1 += PHILOX_W1; }
-        uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;  // IMAD.WIDE.U32
-        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
-        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        const uint64_t p = (uint64_t)PHILOX2_M * c0;   // IMAD.WIDE.U32
+        c0 = (uint32_t)(p >> 32) ^ (key + (uint32_t)r * PHILOX2_W) ^ c1;
+        c1 = (uint32_t)p;
     }
-    return make_uint4(c0, c1, c2, c3);
+    return make_uint2(c0, c1);
 }
 
-RT_HD uint4 philox_rounds(int rounds, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-    if (rounds == 10) return philox4x32<10>(c0, c1, c2, c3, k0, k1);
-    if (rounds == 7) return philox4x32<7>(c0, c1, c2, c3, k0, k1);
-    for (int r = 0; r < rounds; ++r) {
-        if (r > 0) { k0 += PHILOX_W0; k1 += PHILOX_W1; }
-        uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
+// Counter layout (DESIGN.md "RNG streams"):
+//   c0 = pixel index (24 bits) | iteration j of a rejection loop << 24
+//   c1 = sample index (24 bits) | bounce (6 bits) << 24 | stream tag << 30
+//   key = low 32 bits of the seed XOR its high 32 bits
+#define RT_TAG_PATH   0u   // bounce 0: x -> v jitter, y -> ray time; bounce b >= 1: the event's 64 bits
+#define RT_TAG_PIXEL  1u   // sample = bounce = 0: x -> per-pixel u jitter (cpu.rs:35-36)
+#define RT_TAG_LENS   2u   // j = 0: (x, y) -> direct lens sample; j >= 1: rejection iteration j
+#define RT_TAG_REJECT 3u   // (bounce b, iteration j): three 21-bit uniforms of a rejection iteration
 
-// stream tags (counter word 3, bits 24..31); see DESIGN.md "RNG streams"
-#define RT_TAG_PIXEL  1u   // (pixel, 0, 0, tag): x -> per-pixel u jitter
-#define RT_TAG_VJIT   3u   // (pixel, sample>>2, 0, tag): word sample&3 -> v jitter
-#define RT_TAG_LENS   4u   // (pixel, sample, 0, tag|j): x,y -> lens disk; z -> time
-#define RT_TAG_BOUNCE 5u   // (pixel, sample, (b+1)>>1, tag): b odd -> (x,y), b even -> (z,w)
-#define RT_TAG_REJECT 6u   // (pixel, sample, b, tag|j): x,y,z of rejection iteration j
+RT_HD uint32_t rt_ctr1(uint32_t sample, uint32_t bounce, uint32_t tag) { return sample | (bounce << 24) | (tag << 30); }
 
 // 24-bit and 21-bit uniforms in [0,1): exactly representable in fp32 and f64
 RT_HD float u24(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
 RT_HD float u21(uint32_t w) { return (float)w * (1.0f / 2097152.0f); }  // w < 2^21
+// three 21-bit uniforms out of 64 bits
+RT_HD void u21x3(uint2 w, float& a, float& b, float& c) {
+    a = u21(w.x >> 11); b = u21(w.y >> 11); c = u21(((w.x & 0x7FFu) << 10) | (w.y & 0x3FFu));
+}

@@ -31,6 +31,7 @@
 #define RT_TEX_NOISE 3
 
 #define RT_MAX_CONST_PRIMS 40   // primitives kept in the kernel-parameter constant bank
+#define RT_MAX_CONST_RECTS 8    // per axis group, fully unrolled with constant-bank operands
 #define RT_MAX_IMAGES 8
 #define RT_T_MIN 0.001          // src/renderer.rs:58
 
@@ -75,10 +76,11 @@ struct KParams {
     DevCamera<float> cam;
     float4 bg_a, bg_b;          // background colours; bg_a.w = bits(bg type)
     int width, height;
+    float inv_wm1, inv_hm1;     // 1/(W-1), 1/(H-1) (cpu.rs:35-40 divide by W-1 and H-1)
     int s_begin, s_end;         // sample range traced by this launch
     int max_depth;
     int fixed_jitter;
-    uint32_t key0, key1;        // Philox key = seed
+    uint32_t key;               // Philox2x32 key = seed_lo ^ seed_hi
     int tile_first, tile_stride, n_tiles;   // interleaved tile partition
     int tiles_x, tile_w, tile_h;
     int n_prims, n_nodes;
@@ -96,6 +98,11 @@ struct KParams {
     int image_w[RT_MAX_IMAGES], image_h[RT_MAX_IMAGES];
     unsigned long long* segment_counter;
     DevPrim cprims[RT_MAX_CONST_PRIMS];   // type-sorted copy for the linear constant-bank path
+    // rectangles of the constant-bank path once more, split by plane axis so that the
+    // unrolled tests address them with compile-time offsets (operands straight from the
+    // constant bank, no load instructions): group 0 = xy, 1 = xz, 2 = yz
+    float4 crect_bounds[3][RT_MAX_CONST_RECTS];
+    float crect_k[3][RT_MAX_CONST_RECTS];
 };
 
 // ---------------------------------------------------------------------------
@@ -270,11 +277,37 @@ RT_D void rect_group(const Scene& S, int begin, int end, const RayT<float>& r, i
     }
 }
 
-template <class Scene>
-RT_D int closest_hit_linear(const Scene& S, const int* lin_end, const RayT<float>& r, int last_prim, float& best_t) {
+// The same test with the rectangle constants addressed at compile-time offsets
+// of the kernel parameters (fully unrolled, one uniform branch per rectangle).
+template <int AXIS_N>
+RT_D void rect_group_const(const KParams& P, const RayT<float>& r, int last_prim, float& best_t, int& best) {
+    constexpr int G = AXIS_N == 2 ? 0 : (AXIS_N == 1 ? 1 : 2);
+    const int base = P.lin_end[G];
+    const int n = P.lin_end[G + 1] - base;
+    if (n <= 0) return;
+    const float on = AXIS_N == 2 ? r.o.z : (AXIS_N == 1 ? r.o.y : r.o.x);
+    const float in = AXIS_N == 2 ? r.inv_d.z : (AXIS_N == 1 ? r.inv_d.y : r.inv_d.x);
+    const float oa = AXIS_N == 0 ? r.o.y : r.o.x, da = AXIS_N == 0 ? r.d.y : r.d.x;
+    const float ob = AXIS_N == 2 ? r.o.y : r.o.z, db = AXIS_N == 2 ? r.d.y : r.d.z;
+    const float shift = -on * in;
+#pragma unroll
+    for (int j = 0; j < RT_MAX_CONST_RECTS; ++j) {
+        if (j >= n) break;  // uniform
+        const float4 a = P.crect_bounds[G][j];
+        const float t = fmaf(P.crect_k[G][j], in, shift);
+        const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
+        const bool hit = (t >= (float)RT_T_MIN) & (t <= best_t) & (pa >= a.x) & (pa <= a.y) & (pb >= a.z) & (pb <= a.w) &
+                         (base + j != last_prim);
+        best_t = hit ? t : best_t;
+        best = hit ? base + j : best;
+    }
+}
+
+template <bool CONST_RECTS, class Scene>
+RT_D int closest_hit_linear(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& best_t) {
     int best = -1;
     best_t = __int_as_float(0x7f800000);
-    const int n_sph = lin_end[0];
+    const int n_sph = P.lin_end[0];
     if (n_sph > 0) {
         const float a = dot(r.d, r.d), inv_a = fast_rcp(a);
 #pragma unroll 1
@@ -287,9 +320,15 @@ RT_D int closest_hit_linear(const Scene& S, const int* lin_end, const RayT<float
             best = hit ? i : best;
         }
     }
-    rect_group<2>(S, lin_end[0], lin_end[1], r, last_prim, best_t, best);
-    rect_group<1>(S, lin_end[1], lin_end[2], r, last_prim, best_t, best);
-    rect_group<0>(S, lin_end[2], lin_end[3], r, last_prim, best_t, best);
+    if (CONST_RECTS) {
+        rect_group_const<2>(P, r, last_prim, best_t, best);
+        rect_group_const<1>(P, r, last_prim, best_t, best);
+        rect_group_const<0>(P, r, last_prim, best_t, best);
+    } else {
+        rect_group<2>(S, P.lin_end[0], P.lin_end[1], r, last_prim, best_t, best);
+        rect_group<1>(S, P.lin_end[1], P.lin_end[2], r, last_prim, best_t, best);
+        rect_group<0>(S, P.lin_end[2], P.lin_end[3], r, last_prim, best_t, best);
+    }
     return best;
 }
 
@@ -475,7 +514,7 @@ RT_D vec3f background_color(const KParams& P, vec3f d) {
 // block per iteration (src/vec3.rs:424-444, src/util.rs:25-39).
 // ---------------------------------------------------------------------------
 struct RngCtx {
-    uint32_t key0, key1, pixel, sample;
+    uint32_t key, pixel, sample;
 };
 
 // (cos, sin) of 2*pi*u for u in [0,1): the SFU sine/cosine are evaluated at
@@ -497,8 +536,10 @@ RT_D vec3f sphere_direct(float u1, float u2) {
 template <int ROUNDS>
 RT_D vec3f reject_in_unit_sphere(const RngCtx& R, uint32_t bounce) {  // vec3.rs:424-430
     for (uint32_t j = 0;; ++j) {
-        uint4 w = philox4x32<ROUNDS>(R.pixel, R.sample, bounce, (RT_TAG_REJECT << 24) | j, R.key0, R.key1);
-        vec3f v = mk3(2.0f * u24(w.x) - 1.0f, 2.0f * u24(w.y) - 1.0f, 2.0f * u24(w.z) - 1.0f);
+        uint2 w = philox2x32<ROUNDS>(R.pixel | (j << 24), rt_ctr1(R.sample, bounce, RT_TAG_REJECT), R.key);
+        float a, b, c;
+        u21x3(w, a, b, c);
+        vec3f v = mk3(2.0f * a - 1.0f, 2.0f * b - 1.0f, 2.0f * c - 1.0f);   // random_range(-1, 1)
         if (length_squared(v) >= 1.0f) continue;
         return v;
     }

@@ -72,6 +72,20 @@ def test_philox_known_answers(oracle, ctr, key, want):
     assert harness.philox4x32(ctr, key, 10) == want   # the host's copy (Perlin tables) agrees
 
 
+PHILOX2_KAT = [   # Random123 kat_vectors, philox2x32 10
+    ((0, 0), 0, (0xff1dae59, 0x6cd10df2)),
+    ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+    ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12)),
+]
+
+
+@pytest.mark.parametrize("ctr,key,want", PHILOX2_KAT)
+def test_philox2x32_known_answers(oracle, ctr, key, want):
+    out = (C.c_uint32 * 2)()
+    oracle.lib().oracle_philox2x32((C.c_uint32 * 2)(*ctr), key, 10, out)
+    assert tuple(out) == want
+
+
 # ---------------------------------------------------------------------------
 # Geometry
 # ---------------------------------------------------------------------------
