@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libracer_cuda.so")
+# RC_CUDA_LIB points at an alternative build of the same library (tuning experiments)
+LIB_PATH = os.environ.get("RC_CUDA_LIB", os.path.join(HERE, "libracer_cuda.so"))
 
 RC_OK = 0
 RC_ERR_INVALID, RC_ERR_NO_DEVICE, RC_ERR_CUDA, RC_ERR_STATE, RC_ERR_CANCELLED, RC_ERR_NCCL = -1, -2, -3, -4, -5, -6

@@ -90,6 +90,7 @@ struct rc_ctx {
     int mode = RT_MODE_CONST_LINEAR;
     size_t smem_bytes = 0;
     bool has_scene = false, has_camera = false;
+    bool has_textures = false;   // any primitive whose texture is not a solid colour
     rc_camera camera;
     rc_stats stats;
     MultiState multi;
@@ -202,13 +203,13 @@ int set_smem(K kernel, size_t bytes) {
     return RC_OK;
 }
 
-template <int MODE>
+template <int MODE, bool TEX>
 int launch_mega_mode(const KParams& kp, float* accum, int sampler, int rounds, int blocks, size_t smem, cudaStream_t st) {
 #define RC_LAUNCH(S, R)                                                                         \
     do {                                                                                        \
-        int rc__ = set_smem(megakernel_render<MODE, S, R>, smem);                               \
+        int rc__ = set_smem(megakernel_render<MODE, S, R, TEX>, smem);                          \
         if (rc__ != RC_OK) return rc__;                                                         \
-        megakernel_render<MODE, S, R><<<blocks, RT_BLOCK, smem, st>>>(kp, accum);               \
+        megakernel_render<MODE, S, R, TEX><<<blocks, RT_BLOCK, smem, st>>>(kp, accum);          \
     } while (0)
     if (rounds == 7) { if (sampler == RC_SAMPLER_REJECTION) RC_LAUNCH(1, 7); else RC_LAUNCH(0, 7); }
     else { if (sampler == RC_SAMPLER_REJECTION) RC_LAUNCH(1, 10); else RC_LAUNCH(0, 10); }
@@ -217,13 +218,16 @@ int launch_mega_mode(const KParams& kp, float* accum, int sampler, int rounds, i
     return RC_OK;
 }
 
-int launch_mega(int mode, const KParams& kp, float* accum, int sampler, int rounds, int blocks, size_t smem, cudaStream_t st) {
+int launch_mega(int mode, bool tex, const KParams& kp, float* accum, int sampler, int rounds, int blocks, size_t smem, cudaStream_t st) {
+#define RC_MODE(M) (tex ? launch_mega_mode<M, true>(kp, accum, sampler, rounds, blocks, smem, st) \
+                        : launch_mega_mode<M, false>(kp, accum, sampler, rounds, blocks, smem, st))
     switch (mode) {
-    case RT_MODE_CONST_LINEAR: return launch_mega_mode<RT_MODE_CONST_LINEAR>(kp, accum, sampler, rounds, blocks, smem, st);
-    case RT_MODE_SMEM_BVH: return launch_mega_mode<RT_MODE_SMEM_BVH>(kp, accum, sampler, rounds, blocks, smem, st);
-    case RT_MODE_GLOBAL_BVH: return launch_mega_mode<RT_MODE_GLOBAL_BVH>(kp, accum, sampler, rounds, blocks, smem, st);
-    default: return launch_mega_mode<RT_MODE_SMEM_LINEAR>(kp, accum, sampler, rounds, blocks, smem, st);
+    case RT_MODE_CONST_LINEAR: return RC_MODE(RT_MODE_CONST_LINEAR);
+    case RT_MODE_SMEM_BVH: return RC_MODE(RT_MODE_SMEM_BVH);
+    case RT_MODE_GLOBAL_BVH: return RC_MODE(RT_MODE_GLOBAL_BVH);
+    default: return RC_MODE(RT_MODE_SMEM_LINEAR);
     }
+#undef RC_MODE
 }
 
 int check_params(const rc_params* p) {
@@ -248,6 +252,7 @@ void partition(KParams& kp, const rc_params* p, int part, int parts) {
     kp.max_depth = p->max_depth;
     kp.fixed_jitter = p->fixed_jitter;
     kp.key = (uint32_t)p->seed ^ (uint32_t)(p->seed >> 32);
+    for (int r = 0; r < 10; ++r) kp.ks[r] = kp.key + (uint32_t)r * PHILOX2_W;
     kp.inv_wm1 = 1.0f / (float)(p->width - 1); kp.inv_hm1 = 1.0f / (float)(p->height - 1);
     kp.tile_w = RT_TILE_W; kp.tile_h = RT_TILE_H;
     kp.tiles_x = (p->width + RT_TILE_W - 1) / RT_TILE_W;
@@ -307,7 +312,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         const int step = cancel ? 32 : (s1 - s0);
         for (int s = s0; s < s1; s += step) {
             kp.s_begin = s; kp.s_end = s + step < s1 ? s + step : s1;
-            int rc = launch_mega(ctx->mode, kp, accum, p->sampler, rounds, kp.n_tiles, ctx->smem_bytes, d.stream);
+            int rc = launch_mega(ctx->mode, ctx->has_textures, kp, accum, p->sampler, rounds, kp.n_tiles, ctx->smem_bytes, d.stream);
             if (rc != RC_OK) return rc;
             ++launches;
             if (cancel && n_dev == 1) {
@@ -448,6 +453,7 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     std::vector<int> kinds(s->n_prims);
     std::vector<uint32_t> ids(s->n_prims);
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    bool any_textured = false;
     for (int i = 0; i < s->n_prims; ++i) {
         const double* d = s->prim_data + 5 * (size_t)i;
         const rc_material& m = s->materials[s->prim_material[i]];
@@ -475,6 +481,7 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
             if (t.type == RC_TEX_SOLID) { col[0] = t.color[0]; col[1] = t.color[1]; col[2] = t.color[2]; tex_index = -1; }
         }
         int inst = (s->prim_instance && s->n_instances > 0) ? s->prim_instance[i] : -1;
+        if (tex_type != RT_TEX_SOLID) any_textured = true;
         int packed = type | (m.type << 4) | (tex_type << 8) | ((inst + 1) << 12);
         p.b.z = bits(packed);
         p.b.w = bits(tex_index);
@@ -553,6 +560,7 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
         kp.image_h[i] = i < s->n_images ? s->images[i].height : 0;
     }
     ctx->mode = pick_mode(s, rects_fit, ctx->smem_bytes);
+    ctx->has_textures = any_textured;
     ctx->aov.n_prims = s->n_prims; ctx->aov.n_nodes = s->n_nodes;
 
     for (auto& d : ctx->devs) {

@@ -83,7 +83,7 @@ RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
     c.px = px; c.py = py;
     c.pixel = (uint32_t)(py * P.width + px);
     float ujit = 0.5f;
-    if (!P.fixed_jitter) ujit = u24(philox2x32<ROUNDS>(c.pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.key).x);
+    if (!P.fixed_jitter) ujit = u24(philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.ks).x);
     float u = ((float)px + ujit) / (float)(P.width - 1);  // once per pixel, cpu.rs:35-36
     // cam.upper_left_corner holds (upper_left_corner - origin), formed in f64 on the host
     c.dir0 = P.cam.upper_left_corner + u * P.cam.horizontal;
@@ -100,13 +100,13 @@ RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float
         float dx, dy;
         if (SAMPLER == 1) {  // random_in_unit_disk, util.rs:25-39
             for (uint32_t j = 1;; ++j) {
-                uint2 w = philox2x32<ROUNDS>(c.pixel | (j << 24), rt_ctr1(sample, 0u, RT_TAG_LENS), P.key);
+                uint2 w = philox2x32_ks<ROUNDS>(c.pixel | (j << 24), rt_ctr1(sample, 0u, RT_TAG_LENS), P.ks);
                 dx = 2.0f * u24(w.x) - 1.0f; dy = 2.0f * u24(w.y) - 1.0f;
                 if (dx * dx + dy * dy >= 1.0f) continue;
                 break;
             }
         } else {
-            uint2 w = philox2x32<ROUNDS>(c.pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.key);
+            uint2 w = philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.ks);
             float r = fast_sqrt(u24(w.x)), s, cs;
             fast_sincos_2pi(u24(w.y), s, cs);
             dx = r * cs; dy = r * s;
@@ -122,7 +122,7 @@ RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float
 // Returns true if the path continues with (o, d) and throughput T updated;
 // `emit` receives the emitted radiance.
 // ---------------------------------------------------------------------------
-template <int SAMPLER, int ROUNDS, class Scene>
+template <int SAMPLER, int ROUNDS, bool TEX, class Scene>
 RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const RngCtx& R, int prim,
                     const RayT<float>& r, float t, uint32_t bounce, uint2 rnd, vec3f& o, vec3f& d,
                     vec3f& T, vec3f& emit) {
@@ -130,7 +130,9 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
     float4 pb = S.pb(prim), pc = S.pc(prim);
     int mat = kinds_mat(pb.z);
     vec3f col = mk3(pc.x, pc.y, pc.z);
-    if (kinds_tex(pb.z) != RT_TEX_SOLID) col = texture_value(P, X, S, __float_as_int(pb.w), prim, h);
+    if (TEX) {  // compiled out for scenes whose textures are all solid colours
+        if (kinds_tex(pb.z) != RT_TEX_SOLID) col = texture_value(P, X, S, __float_as_int(pb.w), prim, h);
+    }
     emit = mk3(0.0f, 0.0f, 0.0f);
     if (mat == RT_MAT_LIGHT) {  // diffuse_light.rs:25-36
         emit = col;
@@ -190,8 +192,11 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
 // only at the very end of the tile.  Radiance sums stay in registers and are
 // added to the accumulation buffer once.
 // ---------------------------------------------------------------------------
-template <int MODE, int SAMPLER, int ROUNDS>
-__global__ void __launch_bounds__(RT_BLOCK)
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 6
+#endif
+template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
+__global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)
 megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) {
     extern __shared__ __align__(16) unsigned char smem[];
     SmemLayout L = stage_scene<MODE>(P, smem);
@@ -205,10 +210,13 @@ megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) 
     const bool valid = px < P.width && py < P.height;
 
     PixelCtx pc = pixel_setup<ROUNDS>(P, valid ? px : 0, valid ? py : 0);
-    RngCtx R; R.key = P.key; R.pixel = pc.pixel; R.sample = 0;
+    RngCtx R; R.ks = P.ks; R.pixel = pc.pixel; R.sample = 0;
 
+    // Path state.  Radiance is only ever picked up where a path ENDS (escape, light, depth
+    // exhaustion): lights do not scatter and nothing else emits (src/material/*.rs), so
+    // ray_color's `emitted + attenuation * recurse` collapses to throughput x terminal radiance.
     vec3f sum = mk3(0.0f, 0.0f, 0.0f);
-    vec3f o = mk3(0.0f, 0.0f, 0.0f), d = o, T = o, Lr = o;
+    vec3f o = mk3(0.0f, 0.0f, 0.0f), d = o, T = o;
     int s = valid ? P.s_begin : P.s_end;
     bool alive = false;
     int depth_left = 0, last_prim = -1;
@@ -221,15 +229,14 @@ megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) 
             // ---- regenerate: next sample of this pixel ----
             R.sample = (uint32_t)s;
             float vjit = 0.5f;
-            if (!P.fixed_jitter) vjit = u24(philox2x32<ROUNDS>(pc.pixel, rt_ctr1(R.sample, 0u, RT_TAG_PATH), P.key).x);
+            if (!P.fixed_jitter) vjit = u24(philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, 0u, RT_TAG_PATH), P.ks).x);
             camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d);
             T = mk3(1.0f, 1.0f, 1.0f);
-            Lr = mk3(0.0f, 0.0f, 0.0f);
             depth_left = P.max_depth;
             bounce = 0; last_prim = -1;
             alive = depth_left > 0;
             ++s;
-            if (!alive) sum = sum + mk3(1.0f, 1.0f, 1.0f);  // renderer.rs:48-56
+            if (!alive) sum = sum + T;  // renderer.rs:48-56: depth 0 is white
         }
         if (!__any_sync(0xffffffffu, alive)) {
             if (!__any_sync(0xffffffffu, s < P.s_end)) break;
@@ -242,25 +249,23 @@ megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) 
             if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
             else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; prim = closest_hit<MODE>(P, S, r, last_prim, t); }
             ++nseg;
+            vec3f X_end;   // radiance that ends the path
             if (prim < 0) {  // renderer.rs:78-88
-                Lr = Lr + T * background_color(P, d);
+                X_end = background_color(P, d);
                 alive = false;
             } else {
                 ++bounce;
-                uint2 rnd = philox2x32<ROUNDS>(pc.pixel, rt_ctr1(R.sample, bounce, RT_TAG_PATH), P.key);
-                vec3f emit;
+                uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, bounce, RT_TAG_PATH), P.ks);
                 bool cont;
-                if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); cont = shade_hit<SAMPLER, ROUNDS>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, emit); }
-                else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; cont = shade_hit<SAMPLER, ROUNDS>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, emit); }
-                // emitted + attenuation * ray_color(...), renderer.rs:60-69 (emit is zero unless the
-                // material is a light, which never scatters)
-                if (!cont) { Lr = Lr + T * emit; alive = false; }
+                if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, X_end); }
+                else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, X_end); }
+                if (!cont) alive = false;                 // absorbed (X_end = 0) or a light (X_end = emission)
                 else {
                     last_prim = prim;
-                    if (--depth_left == 0) { Lr = Lr + T; alive = false; }  // white at depth 0
+                    if (--depth_left == 0) { X_end = mk3(1.0f, 1.0f, 1.0f); alive = false; }  // white at depth 0
                 }
             }
-            if (!alive) sum = sum + Lr;
+            if (!alive) sum = sum + T * X_end;
         }
     }
     if (valid) {

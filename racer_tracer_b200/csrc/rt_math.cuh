@@ -63,6 +63,19 @@ RT_HD uint2 philox2x32(uint32_t c0, uint32_t c1, uint32_t key) {
     return make_uint2(c0, c1);
 }
 
+// Device form with the key schedule (key + r*W, r = 0..9) precomputed by the host into the
+// kernel parameters: every round is IMAD.WIDE.U32 + one LOP3 with a constant-bank operand.
+template <int ROUNDS>
+RT_D uint2 philox2x32_ks(uint32_t c0, uint32_t c1, const uint32_t* ks) {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint64_t p = (uint64_t)PHILOX2_M * c0;
+        c0 = (uint32_t)(p >> 32) ^ ks[r] ^ c1;
+        c1 = (uint32_t)p;
+    }
+    return make_uint2(c0, c1);
+}
+
 // Counter layout (DESIGN.md "RNG streams"):
 //   c0 = pixel index (24 bits) | iteration j of a rejection loop << 24
 //   c1 = sample index (24 bits) | bounce (6 bits) << 24 | stream tag << 30

@@ -81,6 +81,7 @@ struct KParams {
     int max_depth;
     int fixed_jitter;
     uint32_t key;               // Philox2x32 key = seed_lo ^ seed_hi
+    uint32_t ks[10];            // its key schedule: key + r * 0x9E3779B9
     int tile_first, tile_stride, n_tiles;   // interleaved tile partition
     int tiles_x, tile_w, tile_h;
     int n_prims, n_nodes;
@@ -144,8 +145,9 @@ RT_D int kinds_inst(float packed) { return (int)((unsigned)__float_as_int(packed
 // which t_min = 0.001 rejects (src/renderer.rs:58).  In fp32 the origin sits
 // up to ~1e-4 off the surface, so that root can exceed t_min at grazing
 // angles.  We therefore give the departed primitive the limit the f64 code
-// converges to: a rectangle cannot be re-hit, and a sphere is solved with
-// c = |oc|^2 - r^2 = 0 exactly (roots 0 and -2b/a).
+// converges to: a sphere is solved with c = |oc|^2 - r^2 = 0 exactly (roots 0
+// and -2b/a), and a rectangle's hit point is snapped onto its plane so that
+// the re-test yields t = (k - o_n)/d_n = 0 exactly, below t_min.
 // ---------------------------------------------------------------------------
 
 // src/geometry/sphere.rs:39-58.  Returns the accepted root or -1.
@@ -245,8 +247,30 @@ RT_D float prim_test(const Scene& S, int i, const RayT<float>& r, int last_prim,
         const float aa = dot(r.d, r.d);
         return sphere_hit<float>(r.o, r.d, aa, fast_rcp(aa), mk3(a.x, a.y, a.z), a.w, b.x, self, (float)RT_T_MIN, t_max);
     }
-    if (self) return -1.0f;
     return rect_hit<float>(type, r.o, r.d, r.inv_d, a.x, a.y, a.z, a.w, b.x, (float)RT_T_MIN, t_max);
+}
+
+#define RT_NO_HIT 3.0e38f   /* closest-hit distances start here; +inf marks "no candidate" */
+
+// Candidate distance of one axis-aligned rectangle: t when a0 <= pa <= a1, b0 <= pb <= b1
+// and t >= t_min; +inf otherwise.  Written with explicit predicate logic (two independent
+// setp chains, one selp) because the compiler otherwise lowers the conjunction to a chain of
+// six dependent FSELs.
+//
+// No "is this the rectangle the ray leaves" test is needed: make_hit() snaps the hit point
+// onto the plane, so for that rectangle k - o_n is exactly 0 and t = (k - o_n) * (1/d_n) is 0
+// (or NaN when d_n = 0) — rejected by t >= t_min exactly as the reference's 1e-13 is.
+RT_D float rect_candidate(float t, float pa, float pb, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.ge.f32 p, %1, %3;\n\t"
+        "setp.le.and.f32 p, %1, %4, p;\n\t"
+        "setp.ge.f32 q, %2, %5;\n\t"
+        "setp.le.and.f32 q, %2, %6, q;\n\t"
+        "setp.ge.and.f32 p, %0, 0f3A83126F, p;\n\t"   /* t >= 0.001f */
+        "and.pred p, p, q;\n\t"
+        "selp.f32 %0, %0, 0f7F800000, p;\n\t}"
+        : "+f"(t), "+f"(pa), "+f"(pb) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+    return t;
 }
 
 // Linear closest hit over the TYPE-SORTED table (spheres, xy, xz, yz rects):
@@ -263,22 +287,28 @@ RT_D void rect_group(const Scene& S, int begin, int end, const RayT<float>& r, i
     const float in = AXIS_N == 2 ? r.inv_d.z : (AXIS_N == 1 ? r.inv_d.y : r.inv_d.x);
     const float oa = AXIS_N == 0 ? r.o.y : r.o.x, da = AXIS_N == 0 ? r.d.y : r.d.x;
     const float ob = AXIS_N == 2 ? r.o.y : r.o.z, db = AXIS_N == 2 ? r.d.y : r.d.z;
-    const float shift = -on * in;
+    (void)last_prim;
 #pragma unroll 2
     for (int i = begin; i < end; ++i) {
         const float4 a = S.pa(i);
         const float k = S.pb(i).x;
-        const float t = fmaf(k, in, shift);              // (k - o_n) / d_n
+        const float t = (k - on) * in;                   // (k - o_n) / d_n; exactly 0 on the plane the ray leaves
         const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
-        const bool hit = (t >= (float)RT_T_MIN) & (t <= best_t) & (pa >= a.x) & (pa <= a.y) & (pb >= a.z) & (pb <= a.w) &
-                         (i != last_prim);
-        best_t = hit ? t : best_t;
+        const float tc = rect_candidate(t, pa, pb, a.x, a.y, a.z, a.w);
+        const bool hit = tc <= best_t;
+        best_t = hit ? tc : best_t;
         best = hit ? i : best;
     }
 }
 
 // The same test with the rectangle constants addressed at compile-time offsets
 // of the kernel parameters (fully unrolled, one uniform branch per rectangle).
+// Two passes so the rectangles do not serialise on `best_t`: first every
+// rectangle's own candidate distance (t if the plane hit is inside the bounds
+// and beyond t_min, +inf otherwise) — independent chains the scheduler can
+// interleave — then a short ordered min-reduction (`<=`: a later rectangle
+// wins an exact tie).
+
 template <int AXIS_N>
 RT_D void rect_group_const(const KParams& P, const RayT<float>& r, int last_prim, float& best_t, int& best) {
     constexpr int G = AXIS_N == 2 ? 0 : (AXIS_N == 1 ? 1 : 2);
@@ -289,16 +319,21 @@ RT_D void rect_group_const(const KParams& P, const RayT<float>& r, int last_prim
     const float in = AXIS_N == 2 ? r.inv_d.z : (AXIS_N == 1 ? r.inv_d.y : r.inv_d.x);
     const float oa = AXIS_N == 0 ? r.o.y : r.o.x, da = AXIS_N == 0 ? r.d.y : r.d.x;
     const float ob = AXIS_N == 2 ? r.o.y : r.o.z, db = AXIS_N == 2 ? r.d.y : r.d.z;
-    const float shift = -on * in;
+    (void)last_prim;
+    float tc[RT_MAX_CONST_RECTS];
 #pragma unroll
     for (int j = 0; j < RT_MAX_CONST_RECTS; ++j) {
         if (j >= n) break;  // uniform
         const float4 a = P.crect_bounds[G][j];
-        const float t = fmaf(P.crect_k[G][j], in, shift);
+        const float t = (P.crect_k[G][j] - on) * in;  // (k - o_n) / d_n; exactly 0 on the plane the ray leaves
         const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
-        const bool hit = (t >= (float)RT_T_MIN) & (t <= best_t) & (pa >= a.x) & (pa <= a.y) & (pb >= a.z) & (pb <= a.w) &
-                         (base + j != last_prim);
-        best_t = hit ? t : best_t;
+        tc[j] = rect_candidate(t, pa, pb, a.x, a.y, a.z, a.w);
+    }
+#pragma unroll
+    for (int j = 0; j < RT_MAX_CONST_RECTS; ++j) {
+        if (j >= n) break;  // uniform
+        const bool hit = tc[j] <= best_t;
+        best_t = hit ? tc[j] : best_t;
         best = hit ? base + j : best;
     }
 }
@@ -306,7 +341,7 @@ RT_D void rect_group_const(const KParams& P, const RayT<float>& r, int last_prim
 template <bool CONST_RECTS, class Scene>
 RT_D int closest_hit_linear(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& best_t) {
     int best = -1;
-    best_t = __int_as_float(0x7f800000);
+    best_t = RT_NO_HIT;
     const int n_sph = P.lin_end[0];
     if (n_sph > 0) {
         const float a = dot(r.d, r.d), inv_a = fast_rcp(a);
@@ -350,7 +385,7 @@ RT_D bool aabb_hit(float4 lo, float4 hi, const RayT<float>& r, float t_max) {
 template <class Scene>
 RT_D int closest_hit_bvh(const Scene& S, int n_nodes, const RayT<float>& r, int last_prim, float& best_t) {
     int best = -1;
-    best_t = __int_as_float(0x7f800000);
+    best_t = RT_NO_HIT;
     int i = 0;
 #pragma unroll 1
     while (i < n_nodes) {
@@ -394,14 +429,19 @@ RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t) {
         const float aa = dot(r.d, r.d);
         h.outward = sphere_normal(r.o, r.d, aa, fast_rcp(aa), ctr, a.w, t);  // sphere.rs:61
         h.p = ctr + a.w * h.outward;   // the point on the surface that normal belongs to
+        h.front_face = dot(r.d, h.outward) < 0.0f;  // geometry.rs:49-56
+        h.n = h.front_face ? h.outward : -h.outward;
     } else {
-        h.outward = mk3(type == RT_PRIM_YZ ? 1.0f : 0.0f, type == RT_PRIM_XZ ? 1.0f : 0.0f,
-                        type == RT_PRIM_XY ? 1.0f : 0.0f);
-        // keep the point on the plane (the reference's f64 ray.at(t) lands on it to 1e-13)
-        if (type == RT_PRIM_XY) h.p.z = b.x; else if (type == RT_PRIM_XZ) h.p.y = b.x; else h.p.x = b.x;
+        // rectangles, branch-free: +axis normal (xy_rect.rs:45 etc.), point kept on the plane
+        // (the reference's f64 ray.at(t) lands on it to 1e-13)
+        const bool xy = type == RT_PRIM_XY, xz = type == RT_PRIM_XZ, yz = type == RT_PRIM_YZ;
+        h.outward = mk3(yz ? 1.0f : 0.0f, xz ? 1.0f : 0.0f, xy ? 1.0f : 0.0f);
+        h.p.x = yz ? b.x : h.p.x; h.p.y = xz ? b.x : h.p.y; h.p.z = xy ? b.x : h.p.z;
+        const float dn = xy ? r.d.z : (xz ? r.d.y : r.d.x);
+        h.front_face = dn < 0.0f;   // dot(d, axis) < 0, geometry.rs:49-56
+        const float sgn = h.front_face ? 1.0f : -1.0f;
+        h.n = mk3(sgn * h.outward.x, sgn * h.outward.y, sgn * h.outward.z);
     }
-    h.front_face = dot(r.d, h.outward) < 0.0f;  // geometry.rs:49-56
-    h.n = h.front_face ? h.outward : -h.outward;
     return h;
 }
 
@@ -514,7 +554,8 @@ RT_D vec3f background_color(const KParams& P, vec3f d) {
 // block per iteration (src/vec3.rs:424-444, src/util.rs:25-39).
 // ---------------------------------------------------------------------------
 struct RngCtx {
-    uint32_t key, pixel, sample;
+    const uint32_t* ks;   // Philox key schedule (kernel parameters)
+    uint32_t pixel, sample;
 };
 
 // (cos, sin) of 2*pi*u for u in [0,1): the SFU sine/cosine are evaluated at
@@ -536,7 +577,7 @@ RT_D vec3f sphere_direct(float u1, float u2) {
 template <int ROUNDS>
 RT_D vec3f reject_in_unit_sphere(const RngCtx& R, uint32_t bounce) {  // vec3.rs:424-430
     for (uint32_t j = 0;; ++j) {
-        uint2 w = philox2x32<ROUNDS>(R.pixel | (j << 24), rt_ctr1(R.sample, bounce, RT_TAG_REJECT), R.key);
+        uint2 w = philox2x32_ks<ROUNDS>(R.pixel | (j << 24), rt_ctr1(R.sample, bounce, RT_TAG_REJECT), R.ks);
         float a, b, c;
         u21x3(w, a, b, c);
         vec3f v = mk3(2.0f * a - 1.0f, 2.0f * b - 1.0f, 2.0f * c - 1.0f);   // random_range(-1, 1)
