@@ -297,6 +297,15 @@ int rc_primary_aov(rc_ctx* ctx, const rc_params* params, int32_t precision,
 
 int rc_get_stats(rc_ctx* ctx, rc_stats* out);
 
+/* The share of participant `part` of `parts` under params->split, as the
+ * kernels will trace it (pure host arithmetic, no device needed): interleaved
+ * 16x8-pixel tiles `tile_first + k * tile_stride`, k < n_tiles, of a
+ * tiles_x-wide tile grid, and the sample range [s_begin, s_end).  The tile
+ * grid plays the role of CpuRenderer::prepare_threads (src/renderer/cpu.rs:
+ * 73-115); out = {tile_first, tile_stride, n_tiles, tiles_x, tile_w, tile_h,
+ * s_begin, s_end}. */
+int rc_partition(const rc_params* params, int32_t part, int32_t parts, int32_t out[8]);
+
 /* FP32 (non-tensor) FMA micro-benchmark on device 0: the roofline denominator
  * of SURVEY §8(d).  Returns achieved TFLOP/s (FMA = 2 flop) of a register-only
  * FFMA loop filling every SM, and the SM clock implied by it. */

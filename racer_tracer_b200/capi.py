@@ -107,7 +107,7 @@ class rc_stats(C.Structure):
 ABI_SYMBOLS = [
     "rc_create", "rc_destroy", "rc_set_stream", "rc_upload_scene", "rc_set_camera", "rc_render",
     "rc_render_accumulate", "rc_finalize", "rc_postprocess", "rc_primary_aov", "rc_get_stats",
-    "rc_last_error", "rc_abi_version", "rc_fp32_peak",
+    "rc_last_error", "rc_abi_version", "rc_fp32_peak", "rc_partition",
 ]
 
 
@@ -146,6 +146,7 @@ def load(path: str | None = None) -> C.CDLL:
                                    C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.rc_get_stats.argtypes = [vp, C.POINTER(rc_stats)]
     lib.rc_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.rc_partition.argtypes = [C.POINTER(rc_params), C.c_int32, C.c_int32, C.c_int32 * 8]
     lib.rc_last_error.restype = C.c_char_p
     lib.rc_last_error.argtypes = []
     lib.rc_abi_version.argtypes = []

@@ -786,6 +786,18 @@ int rc_primary_aov(rc_ctx* ctx, const rc_params* p, int32_t precision, uint32_t*
     return RC_OK;
 }
 
+int rc_partition(const rc_params* p, int32_t part, int32_t parts, int32_t out[8]) {
+    int rc = check_params(p);
+    if (rc != RC_OK) return rc;
+    if (!out || parts < 1 || part < 0 || part >= parts) return fail(RC_ERR_INVALID, "bad partition arguments");
+    KParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    partition(kp, p, part, parts);
+    out[0] = kp.tile_first; out[1] = kp.tile_stride; out[2] = kp.n_tiles; out[3] = kp.tiles_x;
+    out[4] = kp.tile_w; out[5] = kp.tile_h; out[6] = kp.s_begin; out[7] = kp.s_end;
+    return RC_OK;
+}
+
 int rc_fp32_peak(rc_ctx* ctx, double* tflops, double* lane_ginstr_per_s) {
     if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
     DeviceState& d = ctx->devs[0];

@@ -614,6 +614,26 @@ def make_params(width, height, samples, max_depth, seed=0, variant=capi.RC_VARIA
     return p
 
 
+def partition(params: rc_params, part: int, parts: int) -> dict:
+    """rc_partition: the share of participant `part` of `parts` (host arithmetic only)."""
+    lib = capi.load()
+    out = (C.c_int32 * 8)()
+    capi.check(lib, lib.rc_partition(C.byref(params), part, parts, out))
+    keys = ("tile_first", "tile_stride", "n_tiles", "tiles_x", "tile_w", "tile_h", "s_begin", "s_end")
+    return dict(zip(keys, [int(v) for v in out]))
+
+
+def share_mask(params: rc_params, part: int, parts: int) -> np.ndarray:
+    """Boolean (H, W) mask of the pixels participant `part` traces."""
+    sh = partition(params, part, parts)
+    mask = np.zeros((params.height, params.width), dtype=bool)
+    for k in range(sh["n_tiles"]):
+        tile = sh["tile_first"] + k * sh["tile_stride"]
+        tx, ty = tile % sh["tiles_x"], tile // sh["tiles_x"]
+        mask[ty * sh["tile_h"]:(ty + 1) * sh["tile_h"], tx * sh["tile_w"]:(tx + 1) * sh["tile_w"]] = True
+    return mask
+
+
 @dataclass
 class Job:
     """Everything one Renderer::render call needs (RenderData, renderer.rs:92-99)."""

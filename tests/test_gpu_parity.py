@@ -151,6 +151,40 @@ def test_converged_image_psnr_independent_streams(renderer, oracle, cfg, name, s
     assert got >= noise_floor - 1.0, "the GPU image is further from the oracle than Monte-Carlo noise explains"
 
 
+@pytest.mark.parametrize("name", SCENES)
+def test_wavefront_traces_the_same_paths_as_the_megakernel(renderer, oracle, cfg, name):
+    """Both variants share ray-gen, RNG streams, intersection and shading code; only the
+    fp32 summation order of the per-pixel sum differs (chunks of 32 samples + atomics)."""
+    w, h, spp = 150, 90, 40      # ragged tiles, spp not a multiple of the 32-sample chunk
+    job = job_for(name, cfg, w, h)
+    renderer.upload(job)
+    a = renderer.render(harness.make_params(w, h, spp, 20, seed=5, variant=capi.RC_VARIANT_MEGAKERNEL))
+    b = renderer.render(harness.make_params(w, h, spp, 20, seed=5, variant=capi.RC_VARIANT_WAVEFRONT))
+    assert np.isfinite(b).all()
+    # same functions, but compiled into different kernels: FMA contraction differs by an ulp here and
+    # there, and a path that sits on a checker edge or a reflect/refract threshold may flip
+    err = np.abs(a - b).max(axis=2)
+    assert np.median(err) < 1e-6 and np.quantile(err, 0.99) < 2e-4, f"max diff {err.max():.3e}"
+    assert float((err > 2e-3).mean()) < 0.005
+    ref = oracle.render(job, harness.make_params(w, h, spp, 20, seed=5))
+    assert float((np.abs(b - ref).max(axis=2) > 2e-3).mean()) < 0.03
+
+
+def test_wavefront_partitions_and_depth_edge_cases(renderer, cfg):
+    import torch
+    w, h, spp = 100, 75, 33
+    job = job_for("emissive", cfg, w, h)
+    renderer.upload(job)
+    wf = capi.RC_VARIANT_WAVEFRONT
+    whole = _accumulate(renderer, harness.make_params(w, h, spp, 20, seed=2, variant=wf))
+    for split in (capi.RC_SPLIT_TILES, capi.RC_SPLIT_SAMPLES):
+        parts = [_accumulate(renderer, harness.make_params(w, h, spp, 20, seed=2, variant=wf, rank=r, world=3, split=split))
+                 for r in range(3)]
+        assert torch.allclose(torch.stack(parts).sum(dim=0), whole, rtol=1e-5, atol=1e-5)
+    img0 = renderer.render(harness.make_params(w, h, 3, 0, seed=1, variant=wf))
+    assert np.array_equal(img0, np.ones_like(img0))
+
+
 def test_postprocess_matches_oracle_bytes(renderer, oracle, cfg):
     rng = np.random.default_rng(5)
     img = rng.random((37, 53, 3)) * 1.6
@@ -267,3 +301,27 @@ def test_full_size_properties_cornell(renderer, cfg):
     assert float(img[:, :300].abs().max()) == 0.0 and float(img[:, -300:].abs().max()) == 0.0
     st = renderer.stats()
     assert st.segments > st.samples  # more than one segment per sample inside the box
+
+
+def test_two_devices_in_one_context(renderer, cfg):
+    """rc_create over two devices (the single-process form the Rust host uses): tile split
+    gathers disjoint tiles peer-to-peer, sample split sums partial buffers with ncclReduce."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h, spp = 333, 201, 24
+    job = job_for("three_balls", cfg, w, h)
+    renderer.upload(job)
+    one = renderer.render(harness.make_params(w, h, spp, 20, seed=4))
+    r2 = harness.CudaRenderer([0, 1])
+    try:
+        r2.upload(job)
+        two = r2.render(harness.make_params(w, h, spp, 20, seed=4, split=capi.RC_SPLIT_TILES))
+        assert np.array_equal(one, two)               # x + 0 = x: the gather is exact
+        assert r2.stats().n_devices == 2
+        two_s = r2.render(harness.make_params(w, h, spp, 20, seed=4, split=capi.RC_SPLIT_SAMPLES))
+        assert np.allclose(one, two_s, rtol=1e-5, atol=1e-6)
+        wf = r2.render(harness.make_params(w, h, spp, 20, seed=4, variant=capi.RC_VARIANT_WAVEFRONT))
+        assert np.allclose(one, wf, rtol=1e-4, atol=1e-5)
+    finally:
+        r2.close()
