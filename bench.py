@@ -135,9 +135,9 @@ def run_reference(args, wl_name):
     job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".yml"), cfg, w, h)
     params = harness.make_params(w, h, spp, depth, seed=0, sampler=capi.RC_SAMPLER_REJECTION)
     cores = os.cpu_count() or 1
-    # bounded sample per step: ~4 s of CPU work
-    probe, _, _ = oracle_slice(job, harness.make_params(w // 8, h // 8, spp, depth, sampler=capi.RC_SAMPLER_REJECTION), 4)
-    slice_spp = max(1, min(spp, int(probe * 4.0 / (w * h))))
+    # bounded sample per step: ~4 s of CPU work, sized from a 2-spp probe of the same frame
+    probe, _, _ = oracle_slice(job, params, 2)
+    slice_spp = max(2, min(spp, int(round(probe * 4.0 / (w * h)))))
     for _ in range(args.warmup):
         oracle_slice(job, params, 1)
     t = []
@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--sampler", default="direct", choices=["direct", "rejection"])
     ap.add_argument("--rng-rounds", type=int, default=10)
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling runs only)")
+    ap.add_argument("--specialize", type=int, default=int(os.environ.get("RC_SPECIALIZE", "1")), choices=[0, 1, 2],
+                    help="1: scene compiled into the megakernel with NVRTC (default); 0: precompiled kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -203,8 +205,9 @@ def main():
     job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".yml"), cfg, w, h)
     variant = capi.RC_VARIANT_MEGAKERNEL if args.variant == "megakernel" else capi.RC_VARIANT_WAVEFRONT
     sampler = capi.RC_SAMPLER_DIRECT if args.sampler == "direct" else capi.RC_SAMPLER_REJECTION
+    spec = args.specialize if (args.variant == "megakernel" and args.sampler == "direct" and args.rng_rounds == 10) else 0
     params = harness.make_params(w, h, spp, depth, seed=0, variant=variant, sampler=sampler, split=split,
-                                 rank=rank, world=world, rng_rounds=args.rng_rounds)
+                                 rank=rank, world=world, rng_rounds=args.rng_rounds, specialize=spec)
 
     r = harness.CudaRenderer([local_rank])
     stream = torch.cuda.current_stream()
@@ -274,7 +277,7 @@ def main():
                    job.scene.c.n_textures * 48 + job.scene.c.n_nodes * 56 + job.scene.c.n_perlin * C.sizeof(capi.rc_perlin) +
                    sum(im[0] * im[1] * 4 for im in job.scene.images) + C.sizeof(capi.rc_camera) + C.sizeof(capi.rc_params))
     e2e_params = harness.make_params(w, h, spp, depth, seed=0, variant=variant, sampler=sampler, split=split,
-                                     rank=rank, world=world, rng_rounds=args.rng_rounds)
+                                     rank=rank, world=world, rng_rounds=args.rng_rounds, specialize=spec)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -308,7 +311,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "scene": scene + ".yml", "width": w, "height": h, "spp": spp,
                        "max_depth": depth, "variant": args.variant, "sampler": args.sampler,
-                       "rng": f"philox4x32-{args.rng_rounds}", "split": split_name,
+                       "rng": f"philox2x32-{args.rng_rounds}", "split": split_name,
+                       "kernel": "scene-specialised (NVRTC)" if spec else "precompiled",
                        "l2": "256 MiB buffer written between timed iterations (flush)",
                        "parallelism": f"tiles{world}" if split_name == "tiles" else f"samples{world}"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(scene_bytes),
@@ -325,9 +329,8 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import oracle as O  # noqa: F401  (checker / baseline only)
             pr = harness.make_params(w, h, spp, depth, seed=0, sampler=capi.RC_SAMPLER_REJECTION)
-            probe, _, _ = oracle_slice(job, harness.make_params(max(2, w // 8), max(2, h // 8), spp, depth,
-                                                                sampler=capi.RC_SAMPLER_REJECTION), 4)
-            slice_spp = max(1, min(spp, int(probe * 15.0 / (w * h))))
+            probe, _, _ = oracle_slice(job, pr, 2)
+            slice_spp = max(2, min(spp, int(round(probe * 15.0 / (w * h)))))
             sps, dt, cnt = oracle_slice(job, pr, slice_spp)
             types = job.scene.np["prim_type"]
             n_sph = int((types == capi.RC_PRIM_SPHERE).sum())

@@ -200,7 +200,11 @@ typedef struct rc_params {
     int32_t  fixed_jitter;    /* 1: pixel-centre, lens-centre rays
                                  (primary-hit parity)         */
     int32_t  rng_rounds;      /* Philox rounds; 0 = 10                      */
-    int32_t  reserved;
+    int32_t  specialize;      /* 0: precompiled kernels.  1: compile the scene
+                                 into the megakernel at run time (NVRTC, cached
+                                 per scene; small scenes only) and fail if that
+                                 is impossible.  2: the same, but fall back to
+                                 the precompiled kernel                     */
 } rc_params;
 
 typedef struct rc_tone_map {
@@ -296,6 +300,11 @@ int rc_primary_aov(rc_ctx* ctx, const rc_params* params, int32_t precision,
                    uint32_t* id, double* t, double* normal, double* point);
 
 int rc_get_stats(rc_ctx* ctx, rc_stats* out);
+
+/* The CUDA source rc_params.specialize compiles for this scene (host only; for
+ * inspection and tests).  Returns its length, writes at most capacity-1 bytes
+ * and a terminator to `out` (may be NULL). */
+int64_t rc_spec_source(const rc_scene* scene, char* out, int64_t capacity);
 
 /* The share of participant `part` of `parts` under params->split, as the
  * kernels will trace it (pure host arithmetic, no device needed): interleaved

@@ -87,7 +87,7 @@ class rc_params(C.Structure):
                 ("max_depth", C.c_int32), ("seed", C.c_uint64), ("variant", C.c_int32),
                 ("sampler", C.c_int32), ("split", C.c_int32), ("tile_w", C.c_int32),
                 ("tile_h", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("fixed_jitter", C.c_int32), ("rng_rounds", C.c_int32), ("reserved", C.c_int32)]
+                ("fixed_jitter", C.c_int32), ("rng_rounds", C.c_int32), ("specialize", C.c_int32)]
 
 
 class rc_tone_map(C.Structure):
@@ -107,7 +107,7 @@ class rc_stats(C.Structure):
 ABI_SYMBOLS = [
     "rc_create", "rc_destroy", "rc_set_stream", "rc_upload_scene", "rc_set_camera", "rc_render",
     "rc_render_accumulate", "rc_finalize", "rc_postprocess", "rc_primary_aov", "rc_get_stats",
-    "rc_last_error", "rc_abi_version", "rc_fp32_peak", "rc_partition",
+    "rc_last_error", "rc_abi_version", "rc_fp32_peak", "rc_partition", "rc_spec_source",
 ]
 
 
@@ -147,12 +147,14 @@ def load(path: str | None = None) -> C.CDLL:
     lib.rc_get_stats.argtypes = [vp, C.POINTER(rc_stats)]
     lib.rc_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.rc_partition.argtypes = [C.POINTER(rc_params), C.c_int32, C.c_int32, C.c_int32 * 8]
+    lib.rc_spec_source.argtypes = [C.POINTER(rc_scene), C.c_char_p, C.c_int64]
     lib.rc_last_error.restype = C.c_char_p
     lib.rc_last_error.argtypes = []
     lib.rc_abi_version.argtypes = []
     for name in ABI_SYMBOLS:
         if name != "rc_last_error":
             getattr(lib, name).restype = C.c_int
+    lib.rc_spec_source.restype = C.c_int64
     if path is None:
         _lib = lib
     return lib

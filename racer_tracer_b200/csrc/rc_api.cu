@@ -7,12 +7,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
 #include "rt_kernels.cuh"
 #include "rt_wavefront.cuh"
 #include "rc_multi.cuh"
+#include "rc_spec.cuh"
 
 namespace {
 
@@ -78,6 +80,7 @@ struct DeviceState {
     DevBuf<double> out64;
     DevBuf<unsigned long long> counter;
     WavefrontState wf;
+    std::map<std::string, SpecKernel> spec_cache;   // scene-specialised kernels loaded on this device
     int sm_count = 0, clock_khz = 0;
 };
 
@@ -91,6 +94,8 @@ struct rc_ctx {
     size_t smem_bytes = 0;
     bool has_scene = false, has_camera = false;
     bool has_textures = false;   // any primitive whose texture is not a solid colour
+    int mats_mask = 0xF;         // material kinds the scene uses
+    std::string spec_source;     // generated source of the scene-specialised kernel ("" = not generated yet)
     rc_camera camera;
     rc_stats stats;
     MultiState multi;
@@ -243,6 +248,7 @@ int check_params(const rc_params* p) {
     if (p->variant != RC_VARIANT_MEGAKERNEL && p->variant != RC_VARIANT_WAVEFRONT) return fail(RC_ERR_INVALID, "unknown variant");
     if (p->sampler != RC_SAMPLER_DIRECT && p->sampler != RC_SAMPLER_REJECTION) return fail(RC_ERR_INVALID, "unknown sampler");
     if (p->split != RC_SPLIT_TILES && p->split != RC_SPLIT_SAMPLES) return fail(RC_ERR_INVALID, "unknown split");
+    if (p->specialize < 0 || p->specialize > 2) return fail(RC_ERR_INVALID, "specialize must be 0, 1 or 2");
     return RC_OK;
 }
 
@@ -308,11 +314,31 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
             if (rc != RC_OK) return fail(rc, "wavefront launch failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
             continue;
         }
+        // scene-specialised kernel (NVRTC), cached per scene and device
+        SpecKernel* spec = nullptr;
+        if (p->specialize && ctx->mode == RT_MODE_CONST_LINEAR && p->sampler == RC_SAMPLER_DIRECT && rounds == 10) {
+            std::string err;
+            if (!spec_load_api((const void*)&rc_abi_version)) err = spec_api().err;
+            else {
+                if (ctx->spec_source.empty()) ctx->spec_source = spec_generate(ctx->kp, ctx->has_textures, ctx->mats_mask);
+                spec = spec_build(d.spec_cache, ctx->spec_source, err);
+            }
+            if (!spec && p->specialize == 1) return fail(RC_ERR_STATE, "scene specialisation failed: " + err);
+        } else if (p->specialize == 1) {
+            return fail(RC_ERR_INVALID, "specialize = 1 needs the megakernel, the direct sampler, 10 Philox rounds and a scene "
+                                        "that fits the constant-bank path");
+        }
         const int s0 = kp.s_begin, s1 = kp.s_end;
         const int step = cancel ? 32 : (s1 - s0);
         for (int s = s0; s < s1; s += step) {
             kp.s_begin = s; kp.s_end = s + step < s1 ? s + step : s1;
-            int rc = launch_mega(ctx->mode, ctx->has_textures, kp, accum, p->sampler, rounds, kp.n_tiles, ctx->smem_bytes, d.stream);
+            int rc;
+            if (spec) {
+                rc = spec_launch(spec, kp, accum, kp.n_tiles, ctx->smem_bytes, d.stream) == 0 ? RC_OK : RC_ERR_CUDA;
+                if (rc != RC_OK) return fail(rc, "launch of the scene-specialised kernel failed");
+            } else {
+                rc = launch_mega(ctx->mode, ctx->has_textures, kp, accum, p->sampler, rounds, kp.n_tiles, ctx->smem_bytes, d.stream);
+            }
             if (rc != RC_OK) return rc;
             ++launches;
             if (cancel && n_dev == 1) {
@@ -359,6 +385,146 @@ int finish_stats(rc_ctx* ctx, const rc_params* p) {
 }
 
 }  // namespace
+
+struct HostTables {   // everything rc_upload_scene derives from an rc_scene, before any device call
+    std::vector<DevPrim> prims, prims_lin;
+    std::vector<DevPrimD> prims_d;
+    std::vector<int> kinds;
+    std::vector<uint32_t> ids;
+    std::vector<DevNode> nodes;
+    std::vector<DevNodeD> nodes_d;
+    std::vector<DevTexture> textures;
+    std::vector<float4> perlin;
+    std::vector<uint8_t> perm;
+    KParams kp;
+    int mode = RT_MODE_CONST_LINEAR;
+    size_t smem_bytes = 0;
+    bool has_textures = false;
+    int mats_mask = 0xF;
+};
+
+// f64 host scene -> fp32 device tables (pure host arithmetic)
+static void build_tables(const rc_scene* s, HostTables& t) {
+    std::memset(&t.kp, 0, sizeof(t.kp));
+    // ---- fp32 + f64 primitive tables ----
+    std::vector<DevPrim>& prims = t.prims; prims.assign(s->n_prims, DevPrim());
+    std::vector<DevPrimD>& prims_d = t.prims_d; prims_d.assign(s->n_prims, DevPrimD());
+    std::vector<int>& kinds = t.kinds; kinds.assign(s->n_prims, 0);
+    std::vector<uint32_t>& ids = t.ids; ids.assign(s->n_prims, 0u);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    bool any_textured = false;
+    for (int i = 0; i < s->n_prims; ++i) {
+        const double* d = s->prim_data + 5 * (size_t)i;
+        const rc_material& m = s->materials[s->prim_material[i]];
+        int type = s->prim_type[i];
+        DevPrim& p = prims[i];
+        DevPrimD& q = prims_d[i];
+        for (int k = 0; k < 4; ++k) q.a[k] = d[k];
+        if (type == RC_PRIM_SPHERE) {
+            double cc = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] - d[3] * d[3];
+            p.a = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
+            p.b.x = (float)cc;
+            q.k_or_cc = cc;
+        } else {
+            p.a = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
+            p.b.x = (float)d[4];
+            q.k_or_cc = d[4];
+        }
+        p.b.y = (float)m.param;
+        int tex_type = RT_TEX_SOLID, tex_index = -1;
+        double col[3] = {1.0, 1.0, 1.0};
+        if (m.type != RC_MAT_DIELECTRIC) {
+            const rc_texture& t = s->textures[m.texture];
+            tex_type = t.type;
+            tex_index = m.texture;
+            if (t.type == RC_TEX_SOLID) { col[0] = t.color[0]; col[1] = t.color[1]; col[2] = t.color[2]; tex_index = -1; }
+        }
+        int inst = (s->prim_instance && s->n_instances > 0) ? s->prim_instance[i] : -1;
+        if (tex_type != RT_TEX_SOLID) any_textured = true;
+        int packed = type | (m.type << 4) | (tex_type << 8) | ((inst + 1) << 12);
+        p.b.z = bits(packed);
+        p.b.w = bits(tex_index);
+        p.c = f4(col[0], col[1], col[2], ubits(s->prim_id[i]));
+        kinds[i] = type;
+        ids[i] = s->prim_id[i];
+        if (s->prim_aabb)
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = std::fmin(lo[a], s->prim_aabb[6 * i + a]);
+                hi[a] = std::fmax(hi[a], s->prim_aabb[6 * i + 3 + a]);
+            }
+    }
+    // ---- threaded BVH ----
+    std::vector<DevNode>& nodes = t.nodes; nodes.assign(s->n_nodes, DevNode());
+    std::vector<DevNodeD>& nodes_d = t.nodes_d; nodes_d.assign(s->n_nodes, DevNodeD());
+    if (s->n_nodes > 0) {
+        std::vector<int> skip(s->n_nodes, s->n_nodes);
+        set_skip(s, 0, s->n_nodes, skip);
+        for (int i = 0; i < s->n_nodes; ++i) {
+            const rc_bvh_node& n = s->nodes[i];
+            int leaf = n.left < 0 ? ((~n.left) | (n.right << 24)) : -1;
+            double ext = 0;
+            for (int a = 0; a < 3; ++a) ext = std::fmax(ext, n.bmax[a] - n.bmin[a]);
+            nodes[i].lo = make_float4(pad_lo(n.bmin[0], ext), pad_lo(n.bmin[1], ext), pad_lo(n.bmin[2], ext), bits(skip[i]));
+            nodes[i].hi = make_float4(pad_hi(n.bmax[0], ext), pad_hi(n.bmax[1], ext), pad_hi(n.bmax[2], ext), bits(leaf));
+            for (int a = 0; a < 3; ++a) { nodes_d[i].lo[a] = n.bmin[a]; nodes_d[i].hi[a] = n.bmax[a]; }
+            nodes_d[i].skip = skip[i];
+            nodes_d[i].leaf = leaf;
+        }
+    }
+    std::vector<DevTexture>& textures = t.textures; textures.assign(s->n_textures, DevTexture());
+    for (int i = 0; i < s->n_textures; ++i) {
+        const rc_texture& t = s->textures[i];
+        textures[i].type = t.type; textures[i].a = t.a; textures[i].b = t.b;
+        textures[i].scale = (float)t.scale;
+        textures[i].color = f4(t.color[0], t.color[1], t.color[2], 0.f);
+    }
+    std::vector<float4>& perlin = t.perlin; perlin.assign((size_t)s->n_perlin * 256, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<uint8_t>& perm = t.perm; perm.assign((size_t)s->n_perlin * 768, 0);
+    for (int k = 0; k < s->n_perlin; ++k)
+        for (int i = 0; i < 256; ++i) {
+            const rc_perlin& pl = s->perlin[k];
+            perlin[(size_t)k * 256 + i] = f4(pl.ran_vec[i][0], pl.ran_vec[i][1], pl.ran_vec[i][2], 0.f);
+            perm[(size_t)k * 768 + i] = (uint8_t)(pl.perm_x[i] & 255);
+            perm[(size_t)k * 768 + 256 + i] = (uint8_t)(pl.perm_y[i] & 255);
+            perm[(size_t)k * 768 + 512 + i] = (uint8_t)(pl.perm_z[i] & 255);
+        }
+
+    KParams& kp = t.kp;
+    kp.n_prims = s->n_prims; kp.n_nodes = s->n_nodes; kp.n_perlin = s->n_perlin;
+    kp.bg_a = f4(s->bg_a[0], s->bg_a[1], s->bg_a[2], bits(s->bg_type));
+    kp.bg_b = f4(s->bg_b[0], s->bg_b[1], s->bg_b[2], 0.f);
+    // type-sorted table for the linear modes (stable: canonical order within a kind)
+    std::vector<DevPrim>& prims_lin = t.prims_lin;
+    prims_lin.clear();
+    prims_lin.reserve(s->n_prims);
+    for (int type = 0; type < 4; ++type) {
+        for (int i = 0; i < s->n_prims; ++i)
+            if (kinds[i] == type) prims_lin.push_back(prims[i]);
+        kp.lin_end[type] = (int)prims_lin.size();
+    }
+    for (int i = 0; i < RT_MAX_CONST_PRIMS; ++i)
+        if (i < s->n_prims) kp.cprims[i] = prims_lin[i]; else std::memset(&kp.cprims[i], 0, sizeof(DevPrim));
+    std::memset(kp.crect_bounds, 0, sizeof(kp.crect_bounds));
+    std::memset(kp.crect_k, 0, sizeof(kp.crect_k));
+    bool rects_fit = true;
+    for (int g = 0; g < 3; ++g) {
+        int begin = kp.lin_end[g], n = kp.lin_end[g + 1] - begin;
+        if (n > RT_MAX_CONST_RECTS) { rects_fit = false; continue; }
+        for (int j = 0; j < n; ++j) {
+            kp.crect_bounds[g][j] = prims_lin[begin + j].a;
+            kp.crect_k[g][j] = prims_lin[begin + j].b.x;
+        }
+    }
+    for (int i = 0; i < RT_MAX_IMAGES; ++i) {
+        kp.image_w[i] = i < s->n_images ? s->images[i].width : 0;
+        kp.image_h[i] = i < s->n_images ? s->images[i].height : 0;
+    }
+    t.mode = pick_mode(s, rects_fit, t.smem_bytes);
+    t.has_textures = any_textured;
+    t.mats_mask = 0;
+    for (int i = 0; i < s->n_prims; ++i) t.mats_mask |= 1 << s->materials[s->prim_material[i]].type;
+
+}
 
 // ===========================================================================
 #pragma GCC visibility push(default)
@@ -424,6 +590,7 @@ int rc_destroy(rc_ctx* ctx) {
         free_scene(d);
         d.accum.release(); d.out64.release(); d.counter.release();
         wavefront_release(d.wf);
+        spec_release(d.spec_cache);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
@@ -446,122 +613,25 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
     int rc = validate_scene(s);
     if (rc != RC_OK) return rc;
-
-    // ---- fp32 + f64 primitive tables ----
-    std::vector<DevPrim> prims(s->n_prims);
-    std::vector<DevPrimD> prims_d(s->n_prims);
-    std::vector<int> kinds(s->n_prims);
-    std::vector<uint32_t> ids(s->n_prims);
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    bool any_textured = false;
-    for (int i = 0; i < s->n_prims; ++i) {
-        const double* d = s->prim_data + 5 * (size_t)i;
-        const rc_material& m = s->materials[s->prim_material[i]];
-        int type = s->prim_type[i];
-        DevPrim& p = prims[i];
-        DevPrimD& q = prims_d[i];
-        for (int k = 0; k < 4; ++k) q.a[k] = d[k];
-        if (type == RC_PRIM_SPHERE) {
-            double cc = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] - d[3] * d[3];
-            p.a = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
-            p.b.x = (float)cc;
-            q.k_or_cc = cc;
-        } else {
-            p.a = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
-            p.b.x = (float)d[4];
-            q.k_or_cc = d[4];
-        }
-        p.b.y = (float)m.param;
-        int tex_type = RT_TEX_SOLID, tex_index = -1;
-        double col[3] = {1.0, 1.0, 1.0};
-        if (m.type != RC_MAT_DIELECTRIC) {
-            const rc_texture& t = s->textures[m.texture];
-            tex_type = t.type;
-            tex_index = m.texture;
-            if (t.type == RC_TEX_SOLID) { col[0] = t.color[0]; col[1] = t.color[1]; col[2] = t.color[2]; tex_index = -1; }
-        }
-        int inst = (s->prim_instance && s->n_instances > 0) ? s->prim_instance[i] : -1;
-        if (tex_type != RT_TEX_SOLID) any_textured = true;
-        int packed = type | (m.type << 4) | (tex_type << 8) | ((inst + 1) << 12);
-        p.b.z = bits(packed);
-        p.b.w = bits(tex_index);
-        p.c = f4(col[0], col[1], col[2], ubits(s->prim_id[i]));
-        kinds[i] = type;
-        ids[i] = s->prim_id[i];
-        if (s->prim_aabb)
-            for (int a = 0; a < 3; ++a) {
-                lo[a] = std::fmin(lo[a], s->prim_aabb[6 * i + a]);
-                hi[a] = std::fmax(hi[a], s->prim_aabb[6 * i + 3 + a]);
-            }
+    HostTables t;
+    build_tables(s, t);
+    {   // keep the camera / launch fields already stored in ctx->kp
+        DevCamera<float> cam = ctx->kp.cam;
+        int lens = ctx->kp.lens_enabled;
+        ctx->kp = t.kp;
+        ctx->kp.cam = cam;
+        ctx->kp.lens_enabled = lens;
     }
-    // ---- threaded BVH ----
-    std::vector<DevNode> nodes(s->n_nodes);
-    std::vector<DevNodeD> nodes_d(s->n_nodes);
-    if (s->n_nodes > 0) {
-        std::vector<int> skip(s->n_nodes, s->n_nodes);
-        set_skip(s, 0, s->n_nodes, skip);
-        for (int i = 0; i < s->n_nodes; ++i) {
-            const rc_bvh_node& n = s->nodes[i];
-            int leaf = n.left < 0 ? ((~n.left) | (n.right << 24)) : -1;
-            double ext = 0;
-            for (int a = 0; a < 3; ++a) ext = std::fmax(ext, n.bmax[a] - n.bmin[a]);
-            nodes[i].lo = make_float4(pad_lo(n.bmin[0], ext), pad_lo(n.bmin[1], ext), pad_lo(n.bmin[2], ext), bits(skip[i]));
-            nodes[i].hi = make_float4(pad_hi(n.bmax[0], ext), pad_hi(n.bmax[1], ext), pad_hi(n.bmax[2], ext), bits(leaf));
-            for (int a = 0; a < 3; ++a) { nodes_d[i].lo[a] = n.bmin[a]; nodes_d[i].hi[a] = n.bmax[a]; }
-            nodes_d[i].skip = skip[i];
-            nodes_d[i].leaf = leaf;
-        }
-    }
-    std::vector<DevTexture> textures(s->n_textures);
-    for (int i = 0; i < s->n_textures; ++i) {
-        const rc_texture& t = s->textures[i];
-        textures[i].type = t.type; textures[i].a = t.a; textures[i].b = t.b;
-        textures[i].scale = (float)t.scale;
-        textures[i].color = f4(t.color[0], t.color[1], t.color[2], 0.f);
-    }
-    std::vector<float4> perlin((size_t)s->n_perlin * 256);
-    std::vector<uint8_t> perm((size_t)s->n_perlin * 768);
-    for (int k = 0; k < s->n_perlin; ++k)
-        for (int i = 0; i < 256; ++i) {
-            const rc_perlin& pl = s->perlin[k];
-            perlin[(size_t)k * 256 + i] = f4(pl.ran_vec[i][0], pl.ran_vec[i][1], pl.ran_vec[i][2], 0.f);
-            perm[(size_t)k * 768 + i] = (uint8_t)(pl.perm_x[i] & 255);
-            perm[(size_t)k * 768 + 256 + i] = (uint8_t)(pl.perm_y[i] & 255);
-            perm[(size_t)k * 768 + 512 + i] = (uint8_t)(pl.perm_z[i] & 255);
-        }
-
-    KParams& kp = ctx->kp;
-    kp.n_prims = s->n_prims; kp.n_nodes = s->n_nodes; kp.n_perlin = s->n_perlin;
-    kp.bg_a = f4(s->bg_a[0], s->bg_a[1], s->bg_a[2], bits(s->bg_type));
-    kp.bg_b = f4(s->bg_b[0], s->bg_b[1], s->bg_b[2], 0.f);
-    // type-sorted table for the linear modes (stable: canonical order within a kind)
-    std::vector<DevPrim> prims_lin;
-    prims_lin.reserve(s->n_prims);
-    for (int type = 0; type < 4; ++type) {
-        for (int i = 0; i < s->n_prims; ++i)
-            if (kinds[i] == type) prims_lin.push_back(prims[i]);
-        kp.lin_end[type] = (int)prims_lin.size();
-    }
-    for (int i = 0; i < RT_MAX_CONST_PRIMS; ++i)
-        if (i < s->n_prims) kp.cprims[i] = prims_lin[i]; else std::memset(&kp.cprims[i], 0, sizeof(DevPrim));
-    std::memset(kp.crect_bounds, 0, sizeof(kp.crect_bounds));
-    std::memset(kp.crect_k, 0, sizeof(kp.crect_k));
-    bool rects_fit = true;
-    for (int g = 0; g < 3; ++g) {
-        int begin = kp.lin_end[g], n = kp.lin_end[g + 1] - begin;
-        if (n > RT_MAX_CONST_RECTS) { rects_fit = false; continue; }
-        for (int j = 0; j < n; ++j) {
-            kp.crect_bounds[g][j] = prims_lin[begin + j].a;
-            kp.crect_k[g][j] = prims_lin[begin + j].b.x;
-        }
-    }
-    for (int i = 0; i < RT_MAX_IMAGES; ++i) {
-        kp.image_w[i] = i < s->n_images ? s->images[i].width : 0;
-        kp.image_h[i] = i < s->n_images ? s->images[i].height : 0;
-    }
-    ctx->mode = pick_mode(s, rects_fit, ctx->smem_bytes);
-    ctx->has_textures = any_textured;
+    ctx->mode = t.mode;
+    ctx->smem_bytes = t.smem_bytes;
+    ctx->has_textures = t.has_textures;
+    ctx->mats_mask = t.mats_mask;
+    ctx->spec_source.clear();
     ctx->aov.n_prims = s->n_prims; ctx->aov.n_nodes = s->n_nodes;
+    std::vector<DevPrim>& prims = t.prims; std::vector<DevPrim>& prims_lin = t.prims_lin;
+    std::vector<DevPrimD>& prims_d = t.prims_d; std::vector<int>& kinds = t.kinds; std::vector<uint32_t>& ids = t.ids;
+    std::vector<DevNode>& nodes = t.nodes; std::vector<DevNodeD>& nodes_d = t.nodes_d;
+    std::vector<DevTexture>& textures = t.textures; std::vector<float4>& perlin = t.perlin; std::vector<uint8_t>& perm = t.perm;
 
     for (auto& d : ctx->devs) {
         free_scene(d);
@@ -820,6 +890,20 @@ int rc_fp32_peak(rc_ctx* ctx, double* tflops, double* lane_ginstr_per_s) {
     if (lane_ginstr_per_s) *lane_ginstr_per_s = fmas / (best_ms * 1e-3) / 1e9;
     if (tflops) *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
     return RC_OK;
+}
+
+int64_t rc_spec_source(const rc_scene* scene, char* out, int64_t capacity) {
+    if (validate_scene(scene) != RC_OK) return -1;
+    HostTables t;
+    build_tables(scene, t);
+    if (t.mode != RT_MODE_CONST_LINEAR) return fail(RC_ERR_INVALID, "scene does not fit the constant-bank path");
+    std::string src = spec_generate(t.kp, t.has_textures, t.mats_mask);
+    if (out && capacity > 0) {
+        size_t n = src.size() < (size_t)capacity - 1 ? src.size() : (size_t)capacity - 1;
+        std::memcpy(out, src.data(), n);
+        out[n] = '\0';
+    }
+    return (int64_t)src.size();
 }
 
 int rc_get_stats(rc_ctx* ctx, rc_stats* out) {

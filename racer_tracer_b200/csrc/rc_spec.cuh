@@ -1,0 +1,211 @@
+// rc_spec.cuh — scene-specialised megakernel, compiled at run time with NVRTC.
+//
+// The precompiled megakernel reads the primitive tables from the constant bank with uniform
+// loads and loops whose trip counts it learns at run time.  For a final render of one scene it
+// pays to compile the scene INTO the kernel: every rectangle / sphere constant becomes an
+// immediate operand, the loops unroll exactly, and material kinds / background / lens that the
+// scene does not use disappear from the code.  The source is generated here (a closest-hit
+// function with the constants spelled out + a few #defines), compiled for sm_100a against the
+// same rt_*.cuh headers the precompiled kernels use (read from csrc/ next to the library), loaded
+// with the driver API and cached per scene.  libnvrtc and libcuda are dlopen'ed, so the library
+// has no link-time dependency on either; when rc_params.specialize == 1 and anything here fails
+// the render call fails loudly (rc_params.specialize == 2 falls back to the precompiled CUDA
+// kernel instead).
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "rt_kernels.cuh"
+
+struct SpecKernel {
+    void* module = nullptr;     // CUmodule
+    void* function = nullptr;   // CUfunction
+    std::string source;
+};
+
+struct SpecApi {
+    bool tried = false, ok = false;
+    std::string err;
+    void* nvrtc = nullptr;
+    void* cuda = nullptr;
+    int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+    int (*GetCUBINSize)(void*, size_t*) = nullptr;
+    int (*GetCUBIN)(void*, char*) = nullptr;
+    int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+    int (*GetProgramLog)(void*, char*) = nullptr;
+    int (*DestroyProgram)(void**) = nullptr;
+    int (*cuModuleLoadData)(void**, const void*) = nullptr;
+    int (*cuModuleGetFunction)(void**, void*, const char*) = nullptr;
+    int (*cuModuleUnload)(void*) = nullptr;
+    int (*cuLaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**) = nullptr;
+    std::string header_dir;
+};
+
+inline SpecApi& spec_api() {
+    static SpecApi api;
+    return api;
+}
+
+inline bool spec_load_api(const void* anchor_symbol) {
+    SpecApi& a = spec_api();
+    if (a.tried) return a.ok;
+    a.tried = true;
+    const char* nvrtc_names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+    for (const char* n : nvrtc_names) { a.nvrtc = dlopen(n, RTLD_NOW); if (a.nvrtc) break; }
+    if (!a.nvrtc) { a.err = "libnvrtc.so.12 not found"; return false; }
+    a.cuda = dlopen("libcuda.so.1", RTLD_NOW);
+    if (!a.cuda) { a.err = "libcuda.so.1 not found"; return false; }
+#define RC_SYM(lib, field, name)                                                        \
+    *(void**)(&a.field) = dlsym(a.lib, name);                                           \
+    if (!a.field) { a.err = std::string("missing symbol ") + name; return false; }
+    RC_SYM(nvrtc, CreateProgram, "nvrtcCreateProgram");
+    RC_SYM(nvrtc, CompileProgram, "nvrtcCompileProgram");
+    RC_SYM(nvrtc, GetCUBINSize, "nvrtcGetCUBINSize");
+    RC_SYM(nvrtc, GetCUBIN, "nvrtcGetCUBIN");
+    RC_SYM(nvrtc, GetProgramLogSize, "nvrtcGetProgramLogSize");
+    RC_SYM(nvrtc, GetProgramLog, "nvrtcGetProgramLog");
+    RC_SYM(nvrtc, DestroyProgram, "nvrtcDestroyProgram");
+    RC_SYM(cuda, cuModuleLoadData, "cuModuleLoadData");
+    RC_SYM(cuda, cuModuleGetFunction, "cuModuleGetFunction");
+    RC_SYM(cuda, cuModuleUnload, "cuModuleUnload");
+    RC_SYM(cuda, cuLaunchKernel, "cuLaunchKernel");
+#undef RC_SYM
+    Dl_info info;
+    if (!dladdr(anchor_symbol, &info) || !info.dli_fname) { a.err = "cannot locate the library on disk"; return false; }
+    std::string path(info.dli_fname);
+    size_t slash = path.find_last_of('/');
+    a.header_dir = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/csrc/";
+    a.ok = true;
+    return true;
+}
+
+inline std::string spec_float(float v) {
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "%.9g", (double)v);
+    std::string s(buf);
+    if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
+    return s + "f";
+}
+
+// Source of the specialised translation unit for a scene already laid out in KParams
+// (type-sorted constant-bank table).
+inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
+    std::ostringstream o;
+    o << "#include \"rt_scene.cuh\"\n";
+    o << "RT_D int spec_closest_hit(const RayT<float>& r, int last_prim, float& best_t) {\n";
+    o << "    int best = -1;\n    best_t = RT_NO_HIT;\n    (void)last_prim;\n";
+    const int n_sph = kp.lin_end[0];
+    if (n_sph > 0) {
+        o << "    {\n        const float a = dot(r.d, r.d), inv_a = fast_rcp(a);\n        float t;\n";
+        for (int i = 0; i < n_sph; ++i) {
+            const DevPrim& p = kp.cprims[i];
+            o << "        t = sphere_hit<float>(r.o, r.d, a, inv_a, mk3(" << spec_float(p.a.x) << ", " << spec_float(p.a.y) << ", "
+              << spec_float(p.a.z) << "), " << spec_float(p.a.w) << ", " << spec_float(p.b.x) << ", last_prim == " << i
+              << ", (float)RT_T_MIN, best_t);\n";
+            o << "        if (t >= 0.0f) { best_t = t; best = " << i << "; }\n";
+        }
+        o << "    }\n";
+    }
+    // rectangles: per axis group, all candidates first (independent), then the ordered min-reduction
+    const char* on[3] = {"r.o.z", "r.o.y", "r.o.x"};
+    const char* in[3] = {"r.inv_d.z", "r.inv_d.y", "r.inv_d.x"};
+    const char* oa[3] = {"r.o.x", "r.o.x", "r.o.y"};
+    const char* da[3] = {"r.d.x", "r.d.x", "r.d.y"};
+    const char* ob[3] = {"r.o.y", "r.o.z", "r.o.z"};
+    const char* db[3] = {"r.d.y", "r.d.z", "r.d.z"};
+    for (int g = 0; g < 3; ++g) {
+        const int begin = kp.lin_end[g], end = kp.lin_end[g + 1];
+        if (end <= begin) continue;
+        o << "    {\n";
+        for (int i = begin; i < end; ++i) {
+            const DevPrim& p = kp.cprims[i];
+            o << "        const float t" << i << " = (" << spec_float(p.b.x) << " - " << on[g] << ") * " << in[g] << ";\n";
+            o << "        const float c" << i << " = rect_candidate(t" << i << ", fmaf(t" << i << ", " << da[g] << ", " << oa[g]
+              << "), fmaf(t" << i << ", " << db[g] << ", " << ob[g] << "), " << spec_float(p.a.x) << ", " << spec_float(p.a.y)
+              << ", " << spec_float(p.a.z) << ", " << spec_float(p.a.w) << ");\n";
+        }
+        for (int i = begin; i < end; ++i)
+            o << "        { const bool hit = c" << i << " <= best_t; best_t = hit ? c" << i << " : best_t; best = hit ? " << i
+              << " : best; }\n";
+        o << "    }\n";
+    }
+    o << "    return best;\n}\n";
+    o << "#define RT_SPECIALIZED 1\n";
+    o << "#define RT_SPEC_MATS " << mats_mask << "\n";
+    o << "#include \"rt_kernels.cuh\"\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)\n"
+         "spec_megakernel(const __grid_constant__ KParams P, float* __restrict__ accum) {\n"
+         "    extern __shared__ __align__(16) unsigned char smem[];\n"
+         "    megakernel_body<RT_MODE_CONST_LINEAR, 0, 10, " << (tex ? "true" : "false") << ">(P, accum, smem);\n}\n";
+    return o.str();
+}
+
+inline bool spec_read(const std::string& path, std::string& out) {
+    std::ifstream f(path.c_str());
+    if (!f) return false;
+    std::stringstream ss;
+    ss << f.rdbuf();
+    out = ss.str();
+    return true;
+}
+
+// Compile + load; returns nullptr and sets err on failure.
+inline SpecKernel* spec_build(std::map<std::string, SpecKernel>& cache, const std::string& source, std::string& err) {
+    auto it = cache.find(source);
+    if (it != cache.end()) return &it->second;
+    SpecApi& a = spec_api();
+    std::string h_math, h_scene, h_kernels;
+    if (!spec_read(a.header_dir + "rt_math.cuh", h_math) || !spec_read(a.header_dir + "rt_scene.cuh", h_scene) ||
+        !spec_read(a.header_dir + "rt_kernels.cuh", h_kernels)) {
+        err = "kernel headers not found in " + a.header_dir;
+        return nullptr;
+    }
+    const char* headers[3] = {h_math.c_str(), h_scene.c_str(), h_kernels.c_str()};
+    const char* names[3] = {"rt_math.cuh", "rt_scene.cuh", "rt_kernels.cuh"};
+    void* prog = nullptr;
+    if (a.CreateProgram(&prog, source.c_str(), "spec_scene.cu", 3, headers, names) != 0) { err = "nvrtcCreateProgram failed"; return nullptr; }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    int rc = a.CompileProgram(prog, 4, opts);
+    if (rc != 0) {
+        size_t n = 0;
+        a.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) a.GetProgramLog(prog, &log[0]);
+        err = "nvrtc compile failed: " + log.substr(0, 1500);
+        a.DestroyProgram(&prog);
+        return nullptr;
+    }
+    size_t n = 0;
+    a.GetCUBINSize(prog, &n);
+    std::vector<char> cubin(n);
+    a.GetCUBIN(prog, cubin.data());
+    a.DestroyProgram(&prog);
+    SpecKernel k;
+    k.source = source;
+    if (a.cuModuleLoadData(&k.module, cubin.data()) != 0) { err = "cuModuleLoadData failed"; return nullptr; }
+    if (a.cuModuleGetFunction(&k.function, k.module, "spec_megakernel") != 0) { err = "spec_megakernel not found in module"; return nullptr; }
+    auto res = cache.emplace(source, k);
+    return &res.first->second;
+}
+
+inline void spec_release(std::map<std::string, SpecKernel>& cache) {
+    SpecApi& a = spec_api();
+    for (auto& kv : cache)
+        if (kv.second.module && a.cuModuleUnload) a.cuModuleUnload(kv.second.module);
+    cache.clear();
+}
+
+inline int spec_launch(SpecKernel* k, const KParams& kp, float* accum, int blocks, size_t smem, cudaStream_t st) {
+    SpecApi& a = spec_api();
+    KParams p = kp;
+    void* args[2] = {&p, &accum};
+    return a.cuLaunchKernel(k->function, (unsigned)blocks, 1, 1, RT_BLOCK, 1, 1, (unsigned)smem, (void*)st, args, nullptr);
+}

@@ -61,9 +61,22 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
     return L;
 }
 
+// Compile-time knowledge about the scene.  The precompiled kernels know nothing (all material
+// kinds possible, background and lens decided at run time); a scene-specialised translation
+// unit (rc_spec.cuh, NVRTC) defines these before including this header, together with
+// spec_closest_hit(), the closest-hit with every primitive constant compiled in.
+#ifndef RT_SPEC_MATS
+#define RT_SPEC_MATS 0xF      /* bit m set: material kind m occurs in the scene */
+#endif
+#define RT_HAS_MAT(m) ((RT_SPEC_MATS >> (m)) & 1)
+
 template <int MODE, class Scene>
 RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& t) {
+#ifdef RT_SPECIALIZED
+    if constexpr (MODE == RT_MODE_CONST_LINEAR) return spec_closest_hit(r, last_prim, t);
+#else
     if constexpr (MODE == RT_MODE_CONST_LINEAR) return closest_hit_linear<true>(P, S, r, last_prim, t);
+#endif
     else if constexpr (MODE == RT_MODE_SMEM_LINEAR) return closest_hit_linear<false>(P, S, r, last_prim, t);
     else return closest_hit_bvh(S, P.n_nodes, r, last_prim, t);
 }
@@ -134,19 +147,19 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
         if (kinds_tex(pb.z) != RT_TEX_SOLID) col = texture_value(P, X, S, __float_as_int(pb.w), prim, h);
     }
     emit = mk3(0.0f, 0.0f, 0.0f);
-    if (mat == RT_MAT_LIGHT) {  // diffuse_light.rs:25-36
+    if (RT_HAS_MAT(RT_MAT_LIGHT) && mat == RT_MAT_LIGHT) {  // diffuse_light.rs:25-36
         emit = col;
         return false;
     }
     vec3f nd;
-    if (mat == RT_MAT_LAMBERTIAN) {  // lambertian.rs:25-39
+    if (RT_HAS_MAT(RT_MAT_LAMBERTIAN) && (mat == RT_MAT_LAMBERTIAN || !(RT_HAS_MAT(RT_MAT_METAL) || RT_HAS_MAT(RT_MAT_DIELECTRIC)))) {  // lambertian.rs:25-39
         vec3f rv;
         if (SAMPLER == 1) rv = unit_vector(reject_in_unit_sphere<ROUNDS>(R, bounce));
         else rv = sphere_direct(u24(rnd.x), u24(rnd.y));
         nd = h.n + rv;
         const float s = 1e-8f;  // near_zero, vec3.rs:127-130
         if (fabsf(nd.x) < s && fabsf(nd.y) < s && fabsf(nd.z) < s) nd = h.n;
-    } else if (mat == RT_MAT_METAL) {  // metal.rs:25-44
+    } else if (RT_HAS_MAT(RT_MAT_METAL) && (mat == RT_MAT_METAL || !RT_HAS_MAT(RT_MAT_DIELECTRIC))) {  // metal.rs:25-44
         vec3f rv;
         if (SAMPLER == 1) rv = reject_in_unit_sphere<ROUNDS>(R, bounce);
         else {
@@ -196,9 +209,7 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
 #define RT_MIN_BLOCKS 6
 #endif
 template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
-__global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)
-megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) {
-    extern __shared__ __align__(16) unsigned char smem[];
+RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned char* smem) {
     SmemLayout L = stage_scene<MODE>(P, smem);
     TexCtx X; X.perlin = L.perlin; X.perm = L.perm;
 
@@ -276,6 +287,15 @@ megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) 
     for (int off = 16; off > 0; off >>= 1) nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
     if (lane == 0 && P.segment_counter) atomicAdd(P.segment_counter, (unsigned long long)nseg);
 }
+
+#ifndef RT_SPECIALIZED
+template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
+__global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)
+megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    megakernel_body<MODE, SAMPLER, ROUNDS, TEX>(P, accum, smem);
+}
+
 
 // ---------------------------------------------------------------------------
 // Primary-visibility AOV (RayImageData, src/renderer.rs:33-39): fixed jitter,
@@ -544,3 +564,4 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ out, 
     for (int k = 0; k < 16; ++k) s += x[k];
     if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+#endif  // !RT_SPECIALIZED (a scene-specialised translation unit only needs megakernel_body)

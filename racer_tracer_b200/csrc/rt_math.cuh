@@ -2,8 +2,16 @@
 // renderer, double for the f64 instantiation of the primary-visibility AOV),
 // Philox4x32 and the uniform conversions of DESIGN.md "RNG streams".
 #pragma once
+#ifdef __CUDACC_RTC__
+// NVRTC (scene-specialised kernels, rc_spec.cuh): no host headers
+typedef unsigned char uint8_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #define RT_HD __host__ __device__ __forceinline__
 #define RT_D __device__ __forceinline__

@@ -606,11 +606,12 @@ def make_tone_map(node) -> rc_tone_map:
 
 def make_params(width, height, samples, max_depth, seed=0, variant=capi.RC_VARIANT_MEGAKERNEL,
                 sampler=capi.RC_SAMPLER_DIRECT, split=capi.RC_SPLIT_TILES, rank=0, world=1,
-                fixed_jitter=0, tile_w=0, tile_h=0, rng_rounds=0) -> rc_params:
+                fixed_jitter=0, tile_w=0, tile_h=0, rng_rounds=0, specialize=0) -> rc_params:
     p = rc_params()
     p.width, p.height, p.samples, p.max_depth, p.seed = width, height, samples, max_depth, seed
     p.variant, p.sampler, p.split, p.rank, p.world = variant, sampler, split, rank, world
     p.fixed_jitter, p.tile_w, p.tile_h, p.rng_rounds = fixed_jitter, tile_w, tile_h, rng_rounds
+    p.specialize = specialize
     return p
 
 

@@ -82,7 +82,7 @@ pub struct rc_camera {
 pub struct rc_params {
     pub width: i32, pub height: i32, pub samples: i32, pub max_depth: i32, pub seed: u64,
     pub variant: i32, pub sampler: i32, pub split: i32, pub tile_w: i32, pub tile_h: i32,
-    pub rank: i32, pub world: i32, pub fixed_jitter: i32, pub rng_rounds: i32, pub reserved: i32,
+    pub rank: i32, pub world: i32, pub fixed_jitter: i32, pub rng_rounds: i32, pub specialize: i32,
 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -106,6 +106,7 @@ extern "C" {
                           normal: *mut f64, point: *mut f64) -> c_int;
     pub fn rc_partition(params: *const rc_params, part: i32, parts: i32, out: *mut i32) -> c_int;
     pub fn rc_get_stats(ctx: *mut rc_ctx, out: *mut rc_stats) -> c_int;
+    pub fn rc_spec_source(scene: *const rc_scene, out: *mut c_char, capacity: i64) -> i64;
     pub fn rc_fp32_peak(ctx: *mut rc_ctx, tflops: *mut f64, lane_ginstr_per_s: *mut f64) -> c_int;
     pub fn rc_last_error() -> *const c_char;
     pub fn rc_abi_version() -> c_int;

@@ -89,3 +89,22 @@ def test_product_never_touches_the_oracle():
                 assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f
     out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_specialised_source_compiles_for_sm_100a(cuda_lib, cfg, tmp_path):
+    """The CUDA source rc_params.specialize hands to NVRTC, compiled here with nvcc against the
+    same headers (no GPU needed): scene constants appear as literals."""
+    from conftest import scene_path
+    job = harness.prepare_job(scene_path("cornell_box"), cfg, 64, 64)
+    n = cuda_lib.rc_spec_source(job.scene.ptr, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    assert cuda_lib.rc_spec_source(job.scene.ptr, buf, n + 1) == n
+    src = buf.value.decode()
+    assert "spec_closest_hit" in src and "554.0f" in src and "#define RT_SPEC_MATS 9" in src   # lambertian + light
+    cu = tmp_path / "spec.cu"
+    cu.write_text(src)
+    subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I",
+                    os.path.join(ROOT, "racer_tracer_b200", "csrc"), "-cubin", "-o", str(tmp_path / "spec.cubin"), str(cu)],
+                   check=True)
+    big = harness.prepare_job(scene_path("clown"), cfg, 64, 64)
+    assert cuda_lib.rc_spec_source(big.scene.ptr, None, 0) > 0          # 23 spheres still fit the constant bank

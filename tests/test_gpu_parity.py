@@ -325,3 +325,23 @@ def test_two_devices_in_one_context(renderer, cfg):
         assert np.allclose(one, wf, rtol=1e-4, atol=1e-5)
     finally:
         r2.close()
+
+
+def test_scene_specialised_kernel_matches_the_generic_one(renderer, cfg):
+    """rc_params.specialize = 1: the scene compiled into the megakernel with NVRTC (constants as
+    immediates, unused material code removed) traces the same paths as the precompiled kernel."""
+    w, h, spp = 200, 120, 24
+    for name in ("cornell_box", "three_balls", "emissive"):
+        job = job_for(name, cfg, w, h)
+        renderer.upload(job)
+        a = renderer.render(harness.make_params(w, h, spp, 20, seed=6))
+        b = renderer.render(harness.make_params(w, h, spp, 20, seed=6, specialize=1))
+        err = np.abs(a - b).max(axis=2)
+        assert np.median(err) < 1e-6 and np.quantile(err, 0.99) < 2e-4, f"{name}: max diff {err.max():.3e}"
+        assert float((err > 2e-3).mean()) < 0.005
+    # a second upload of the same scene hits the per-scene cache (no recompilation)
+    import time
+    renderer.upload(job)
+    t0 = time.perf_counter()
+    renderer.render(harness.make_params(w, h, 1, 20, seed=6, specialize=1))
+    assert time.perf_counter() - t0 < 0.5
