@@ -511,7 +511,9 @@ static void build_tables(const rc_scene* s, HostTables& t) {
         int begin = kp.lin_end[g], n = kp.lin_end[g + 1] - begin;
         if (n > RT_MAX_CONST_RECTS) { rects_fit = false; continue; }
         for (int j = 0; j < n; ++j) {
-            kp.crect_bounds[g][j] = prims_lin[begin + j].a;
+            const float4 r4 = prims_lin[begin + j].a;   // (a0, a1, b0, b1) -> (ca, ha, cb, hb), formed in f64
+            kp.crect_bounds[g][j] = make_float4((float)(0.5 * ((double)r4.x + r4.y)), (float)(0.5 * ((double)r4.y - r4.x)),
+                                                (float)(0.5 * ((double)r4.z + r4.w)), (float)(0.5 * ((double)r4.w - r4.z)));
             kp.crect_k[g][j] = prims_lin[begin + j].b.x;
         }
     }

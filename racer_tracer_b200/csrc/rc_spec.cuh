@@ -114,23 +114,40 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
         }
         o << "    }\n";
     }
-    // rectangles: per axis group, all candidates first (independent), then the ordered min-reduction
+    // rectangles: per axis group, all candidates first (independent), then the ordered min-reduction.
+    // Origins relative to each distinct rectangle centre are formed once per ray and shared.
     const char* on[3] = {"r.o.z", "r.o.y", "r.o.x"};
     const char* in[3] = {"r.inv_d.z", "r.inv_d.y", "r.inv_d.x"};
     const char* oa[3] = {"r.o.x", "r.o.x", "r.o.y"};
     const char* da[3] = {"r.d.x", "r.d.x", "r.d.y"};
     const char* ob[3] = {"r.o.y", "r.o.z", "r.o.z"};
     const char* db[3] = {"r.d.y", "r.d.z", "r.d.z"};
+    std::map<std::string, std::string> rel;   // "r.o.x - 277.5f" -> variable name
+    auto rel_origin = [&](const char* axis, float centre) {
+        std::string key = std::string(axis) + " - " + spec_float(centre);
+        auto it = rel.find(key);
+        if (it != rel.end()) return it->second;
+        std::string name = "oc" + std::to_string(rel.size());
+        o << "    const float " << name << " = " << key << ";\n";
+        rel[key] = name;
+        return name;
+    };
     for (int g = 0; g < 3; ++g) {
         const int begin = kp.lin_end[g], end = kp.lin_end[g + 1];
         if (end <= begin) continue;
+        std::vector<std::string> va(end - begin), vb(end - begin);
+        for (int i = begin; i < end; ++i) {
+            const float4 c = kp.crect_bounds[g][i - begin];
+            va[i - begin] = rel_origin(oa[g], c.x);
+            vb[i - begin] = rel_origin(ob[g], c.z);
+        }
         o << "    {\n";
         for (int i = begin; i < end; ++i) {
             const DevPrim& p = kp.cprims[i];
+            const float4 c = kp.crect_bounds[g][i - begin];
             o << "        const float t" << i << " = (" << spec_float(p.b.x) << " - " << on[g] << ") * " << in[g] << ";\n";
-            o << "        const float c" << i << " = rect_candidate(t" << i << ", fmaf(t" << i << ", " << da[g] << ", " << oa[g]
-              << "), fmaf(t" << i << ", " << db[g] << ", " << ob[g] << "), " << spec_float(p.a.x) << ", " << spec_float(p.a.y)
-              << ", " << spec_float(p.a.z) << ", " << spec_float(p.a.w) << ");\n";
+            o << "        const float c" << i << " = rect_candidate(t" << i << ", fmaf(t" << i << ", " << da[g] << ", " << va[i - begin]
+              << "), fmaf(t" << i << ", " << db[g] << ", " << vb[i - begin] << "), " << spec_float(c.y) << ", " << spec_float(c.w) << ");\n";
         }
         for (int i = begin; i < end; ++i)
             o << "        { const bool hit = c" << i << " <= best_t; best_t = hit ? c" << i << " : best_t; best = hit ? " << i

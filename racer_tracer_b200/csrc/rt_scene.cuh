@@ -102,7 +102,7 @@ struct KParams {
     // rectangles of the constant-bank path once more, split by plane axis so that the
     // unrolled tests address them with compile-time offsets (operands straight from the
     // constant bank, no load instructions): group 0 = xy, 1 = xz, 2 = yz
-    float4 crect_bounds[3][RT_MAX_CONST_RECTS];
+    float4 crect_bounds[3][RT_MAX_CONST_RECTS];   // (centre a, half extent a, centre b, half extent b)
     float crect_k[3][RT_MAX_CONST_RECTS];
 };
 
@@ -252,24 +252,23 @@ RT_D float prim_test(const Scene& S, int i, const RayT<float>& r, int last_prim,
 
 #define RT_NO_HIT 3.0e38f   /* closest-hit distances start here; +inf marks "no candidate" */
 
-// Candidate distance of one axis-aligned rectangle: t when a0 <= pa <= a1, b0 <= pb <= b1
-// and t >= t_min; +inf otherwise.  Written with explicit predicate logic (two independent
-// setp chains, one selp) because the compiler otherwise lowers the conjunction to a chain of
-// six dependent FSELs.
+// Candidate distance of one axis-aligned rectangle: t when the in-plane hit point lies inside
+// the rectangle and t >= t_min; +inf otherwise.  The bounds test a0 <= pa <= a1 (xy_rect.rs:36-38)
+// is evaluated as |pa - ca| <= ha with ca = (a0 + a1)/2, ha = (a1 - a0)/2 formed in f64 on the
+// host: one FADD (FMA pipe) + one compare with |.| per axis instead of two compares — the ALU
+// pipe (compares, selects, logic) is the saturated one in this kernel (profiles/).  `xa`, `xb`
+// are the hit coordinates already relative to the centre.  Three chained setp + one selp.
 //
 // No "is this the rectangle the ray leaves" test is needed: make_hit() snaps the hit point
 // onto the plane, so for that rectangle k - o_n is exactly 0 and t = (k - o_n) * (1/d_n) is 0
 // (or NaN when d_n = 0) — rejected by t >= t_min exactly as the reference's 1e-13 is.
-RT_D float rect_candidate(float t, float pa, float pb, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .pred p, q;\n\t"
-        "setp.ge.f32 p, %1, %3;\n\t"
-        "setp.le.and.f32 p, %1, %4, p;\n\t"
-        "setp.ge.f32 q, %2, %5;\n\t"
-        "setp.le.and.f32 q, %2, %6, q;\n\t"
+RT_D float rect_candidate(float t, float xa, float xb, float ha, float hb) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.f32 p, %1, %3;\n\t"
+        "setp.le.and.f32 p, %2, %4, p;\n\t"
         "setp.ge.and.f32 p, %0, 0f3A83126F, p;\n\t"   /* t >= 0.001f */
-        "and.pred p, p, q;\n\t"
         "selp.f32 %0, %0, 0f7F800000, p;\n\t}"
-        : "+f"(t), "+f"(pa), "+f"(pb) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+        : "+f"(t) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb));
     return t;
 }
 
@@ -294,7 +293,7 @@ RT_D void rect_group(const Scene& S, int begin, int end, const RayT<float>& r, i
         const float k = S.pb(i).x;
         const float t = (k - on) * in;                   // (k - o_n) / d_n; exactly 0 on the plane the ray leaves
         const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
-        const float tc = rect_candidate(t, pa, pb, a.x, a.y, a.z, a.w);
+        const float tc = rect_candidate(t, pa - 0.5f * (a.x + a.y), pb - 0.5f * (a.z + a.w), 0.5f * (a.y - a.x), 0.5f * (a.w - a.z));
         const bool hit = tc <= best_t;
         best_t = hit ? tc : best_t;
         best = hit ? i : best;
@@ -324,10 +323,10 @@ RT_D void rect_group_const(const KParams& P, const RayT<float>& r, int last_prim
 #pragma unroll
     for (int j = 0; j < RT_MAX_CONST_RECTS; ++j) {
         if (j >= n) break;  // uniform
-        const float4 a = P.crect_bounds[G][j];
+        const float4 a = P.crect_bounds[G][j];   // (ca, ha, cb, hb)
         const float t = (P.crect_k[G][j] - on) * in;  // (k - o_n) / d_n; exactly 0 on the plane the ray leaves
-        const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
-        tc[j] = rect_candidate(t, pa, pb, a.x, a.y, a.z, a.w);
+        const float xa = fmaf(t, da, oa - a.x), xb = fmaf(t, db, ob - a.z);
+        tc[j] = rect_candidate(t, xa, xb, a.y, a.w);
     }
 #pragma unroll
     for (int j = 0; j < RT_MAX_CONST_RECTS; ++j) {
