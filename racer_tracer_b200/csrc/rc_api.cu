@@ -74,6 +74,8 @@ struct DeviceState {
     DevBuf<int> prim_kind;
     DevBuf<uint32_t> prim_id;
     DevBuf<DevNodeD> nodes_d;
+    DevBuf<int> prim_inst;
+    DevBuf<DevInstanceD> instances_d;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> tex;
     DevBuf<float> accum;
@@ -111,7 +113,7 @@ void free_scene(DeviceState& d) {
     d.arrays.clear();
     d.prims.release(); d.prims_lin.release(); d.nodes.release(); d.textures.release(); d.instances.release();
     d.perlin.release(); d.perm.release(); d.prims_d.release(); d.prim_kind.release();
-    d.prim_id.release(); d.nodes_d.release();
+    d.prim_id.release(); d.nodes_d.release(); d.prim_inst.release(); d.instances_d.release();
 }
 
 int validate_scene(const rc_scene* s) {
@@ -155,10 +157,12 @@ int validate_scene(const rc_scene* s) {
                 return fail(RC_ERR_INVALID, "BVH leaf range out of bounds");
         }
     }
-    if (s->n_instances > 0 && s->prim_instance)
+    if (s->n_instances > 0 && s->prim_instance) {
+        if (!s->instances) return fail(RC_ERR_INVALID, "instance table missing");
         for (int i = 0; i < s->n_prims; ++i)
-            if (s->prim_instance[i] >= 0)
-                return fail(RC_ERR_INVALID, "instanced primitives (Box/RotateY/Translate) are not supported by this build");
+            if (s->prim_instance[i] >= 0 && s->n_nodes == 0)
+                return fail(RC_ERR_INVALID, "scenes with RotateY / Translate instances need the BVH (n_nodes > 0)");
+    }
     return RC_OK;
 }
 
@@ -180,16 +184,17 @@ void set_skip(const rc_scene* s, int i, int skip, std::vector<int>& out) {
     }
 }
 
-int pick_mode(const rc_scene* s, bool rects_fit, size_t& smem_bytes) {
+int pick_mode(const rc_scene* s, bool rects_fit, bool instanced, size_t& smem_bytes) {
     const char* force = std::getenv("RC_SCENE_MODE");  // experiments: const | smem | global | smemlin
     size_t perlin_bytes = (size_t)s->n_perlin * (256 * 16 + 768);
     size_t bvh_bytes = (size_t)s->n_nodes * sizeof(DevNode) + (size_t)s->n_prims * sizeof(DevPrim);
     int mode;
-    if (s->n_prims <= RT_MAX_CONST_PRIMS && rects_fit) mode = RT_MODE_CONST_LINEAR;
+    // instanced scenes always traverse the BVH: its (possibly non-bounding, Q14) boxes are part of the semantics
+    if (!instanced && s->n_prims <= RT_MAX_CONST_PRIMS && rects_fit) mode = RT_MODE_CONST_LINEAR;
     else if (s->n_nodes > 0 && bvh_bytes + perlin_bytes <= 200 * 1024) mode = RT_MODE_SMEM_BVH;
     else if (s->n_nodes > 0) mode = RT_MODE_GLOBAL_BVH;
     else mode = RT_MODE_SMEM_LINEAR;
-    if (force) {
+    if (force && !instanced) {
         std::string f(force);
         if (f == "const" && s->n_prims <= RT_MAX_CONST_PRIMS && rects_fit) mode = RT_MODE_CONST_LINEAR;
         else if (f == "smem" && s->n_nodes > 0) mode = RT_MODE_SMEM_BVH;
@@ -396,6 +401,9 @@ struct HostTables {   // everything rc_upload_scene derives from an rc_scene, be
     std::vector<DevTexture> textures;
     std::vector<float4> perlin;
     std::vector<uint8_t> perm;
+    std::vector<DevInstance> instances;
+    std::vector<DevInstanceD> instances_d;
+    std::vector<int> prim_inst;
     KParams kp;
     int mode = RT_MODE_CONST_LINEAR;
     size_t smem_bytes = 0;
@@ -489,7 +497,28 @@ static void build_tables(const rc_scene* s, HostTables& t) {
             perm[(size_t)k * 768 + 512 + i] = (uint8_t)(pl.perm_z[i] & 255);
         }
 
+    t.instances.assign(s->n_instances, DevInstance());
+    t.instances_d.assign(s->n_instances, DevInstanceD());
+    bool any_rotate = false, any_instance = false;
+    for (int i = 0; i < s->n_instances; ++i) {
+        const rc_instance& in = s->instances[i];
+        DevInstance& d = t.instances[i];
+        d.sin_theta = (float)in.sin_theta; d.cos_theta = (float)in.cos_theta;
+        d.ox = (float)in.offset[0]; d.oy = (float)in.offset[1]; d.oz = (float)in.offset[2];
+        d.flags = in.flags;
+        DevInstanceD& q = t.instances_d[i];
+        q.sin_theta = in.sin_theta; q.cos_theta = in.cos_theta;
+        q.offset[0] = in.offset[0]; q.offset[1] = in.offset[1]; q.offset[2] = in.offset[2];
+        q.flags = in.flags;
+    }
+    t.prim_inst.assign(s->n_prims, -1);
+    for (int i = 0; i < s->n_prims; ++i) {
+        int inst = (s->prim_instance && s->n_instances > 0) ? s->prim_instance[i] : -1;
+        t.prim_inst[i] = inst;
+        if (inst >= 0) { any_instance = true; if (s->instances[inst].flags & 1) any_rotate = true; }
+    }
     KParams& kp = t.kp;
+    kp.ref_aabb = any_rotate ? 1 : 0;
     kp.n_prims = s->n_prims; kp.n_nodes = s->n_nodes; kp.n_perlin = s->n_perlin;
     kp.bg_a = f4(s->bg_a[0], s->bg_a[1], s->bg_a[2], bits(s->bg_type));
     kp.bg_b = f4(s->bg_b[0], s->bg_b[1], s->bg_b[2], 0.f);
@@ -521,7 +550,7 @@ static void build_tables(const rc_scene* s, HostTables& t) {
         kp.image_w[i] = i < s->n_images ? s->images[i].width : 0;
         kp.image_h[i] = i < s->n_images ? s->images[i].height : 0;
     }
-    t.mode = pick_mode(s, rects_fit, t.smem_bytes);
+    t.mode = pick_mode(s, rects_fit && !any_instance, any_instance, t.smem_bytes);
     t.has_textures = any_textured;
     t.mats_mask = 0;
     for (int i = 0; i < s->n_prims; ++i) t.mats_mask |= 1 << s->materials[s->prim_material[i]].type;
@@ -648,6 +677,9 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
         CUDA_TRY(d.prim_kind.assign(kinds));
         CUDA_TRY(d.prim_id.assign(ids));
         CUDA_TRY(d.nodes_d.assign(nodes_d));
+        CUDA_TRY(d.instances.assign(t.instances));
+        CUDA_TRY(d.instances_d.assign(t.instances_d));
+        CUDA_TRY(d.prim_inst.assign(t.prim_inst));
         for (int i = 0; i < s->n_images; ++i) {
             // image textures as CUDA texture objects: point filter, clamp, u8 -> float/255
             // (src/texture/image.rs:28-51, Q21)
@@ -844,6 +876,7 @@ int rc_primary_aov(rc_ctx* ctx, const rc_params* p, int32_t precision, uint32_t*
         AovParamsD ap = ctx->aov;
         ap.width = p->width; ap.height = p->height;
         ap.prims = d.prims_d.p; ap.prim_kind = d.prim_kind.p; ap.prim_id = d.prim_id.p; ap.nodes = d.nodes_d.p;
+        ap.prim_inst = d.prim_inst.p; ap.instances = d.instances_d.p;
         dim3 block(16, 8), grid((p->width + 15) / 16, (p->height + 7) / 8);
         primary_aov_kernel_f64<<<grid, block, 0, d.stream>>>(ap, d_id.p, d_t.p, d_n.p, d_p.p);
     }

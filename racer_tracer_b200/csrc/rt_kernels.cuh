@@ -258,7 +258,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             float t;
             int prim;
             if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
-            else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; prim = closest_hit<MODE>(P, S, r, last_prim, t); }
+            else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t); }
             ++nseg;
             vec3f X_end;   // radiance that ends the path
             if (prim < 0) {  // renderer.rs:78-88
@@ -269,7 +269,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                 uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, bounce, RT_TAG_PATH), P.ks);
                 bool cont;
                 if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, X_end); }
-                else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, X_end); }
+                else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, X_end); }
                 if (!cont) alive = false;                 // absorbed (X_end = 0) or a light (X_end = emission)
                 else {
                     last_prim = prim;
@@ -326,7 +326,7 @@ primary_aov_kernel(const __grid_constant__ KParams P, uint32_t* __restrict__ id,
         prim = closest_hit<MODE>(P, S, r, -1, t);
         if (prim >= 0) { h = make_hit(S, prim, r, t); oid = (uint32_t)__float_as_int(S.pc(prim).w); }
     } else {
-        PtrScene S; S.prims = L.prims; S.nodes = L.nodes;
+        PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb;
         prim = closest_hit<MODE>(P, S, r, -1, t);
         if (prim >= 0) { h = make_hit(S, prim, r, t); oid = (uint32_t)__float_as_int(S.pc(prim).w); }
     }
@@ -357,6 +357,8 @@ struct AovParamsD {
     const int* prim_kind;    // RT_PRIM_*
     const uint32_t* prim_id;
     const DevNodeD* nodes;
+    const int* prim_inst;             // -1 or index into instances
+    const DevInstanceD* instances;
 };
 
 RT_D double sd_add(double a, double b) { return __dadd_rn(a, b); }
@@ -368,10 +370,23 @@ RT_D Vec3T<double> sd_sub3(Vec3T<double> a, Vec3T<double> b) { return mk3(sd_sub
 RT_D Vec3T<double> sd_add3(Vec3T<double> a, Vec3T<double> b) { return mk3(sd_add(a.x, b.x), sd_add(a.y, b.y), sd_add(a.z, b.z)); }
 RT_D Vec3T<double> sd_scale(double s, Vec3T<double> a) { return mk3(sd_mul(s, a.x), sd_mul(s, a.y), sd_mul(s, a.z)); }
 
+// ray into an instance's space, reference order: translate.rs:32, rotate_y.rs:38-47
+RT_D void to_local_d(const DevInstanceD& in, Vec3T<double>& o, Vec3T<double>& d) {
+    if (in.flags & 2) o = sd_sub3(o, mk3(in.offset[0], in.offset[1], in.offset[2]));
+    if (in.flags & 1) {
+        const double s = in.sin_theta, c = in.cos_theta;
+        const double ox = sd_sub(sd_mul(c, o.x), sd_mul(s, o.z)), oz = sd_add(sd_mul(s, o.x), sd_mul(c, o.z));
+        const double dx = sd_sub(sd_mul(c, d.x), sd_mul(s, d.z)), dz = sd_add(sd_mul(s, d.x), sd_mul(c, d.z));
+        o.x = ox; o.z = oz; d.x = dx; d.z = dz;
+    }
+}
+
 // obj_hit in reference order; returns t or -1
 RT_D double prim_test_d(const AovParamsD& P, int i, Vec3T<double> o, Vec3T<double> d, double t_min, double t_max) {
     const DevPrimD& p = P.prims[i];
     int type = P.prim_kind[i];
+    const int inst = P.prim_inst[i];
+    if (inst >= 0) to_local_d(P.instances[inst], o, d);
     if (type == RT_PRIM_SPHERE) {  // sphere.rs:39-58
         Vec3T<double> oc = sd_sub3(o, mk3(p.a[0], p.a[1], p.a[2]));
         double a = sd_dot(d, d), half_b = sd_dot(oc, d);
@@ -456,13 +471,31 @@ __global__ void primary_aov_kernel_f64(const __grid_constant__ AovParamsD P, uin
     }
     const DevPrimD& p = P.prims[best];
     int type = P.prim_kind[best];
-    Vec3T<double> hp = sd_add3(o, sd_scale(best_t, d)), on;   // Ray::at
+    const int inst = P.prim_inst[best];
+    Vec3T<double> lo = o, ld = d;           // ray in the primitive's space
+    if (inst >= 0) to_local_d(P.instances[inst], lo, ld);
+    Vec3T<double> hp = sd_add3(lo, sd_scale(best_t, ld)), on;   // Ray::at
     if (type == RT_PRIM_SPHERE) {
         Vec3T<double> pc = sd_sub3(hp, mk3(p.a[0], p.a[1], p.a[2]));
         on = mk3(sd_div(pc.x, p.a[3]), sd_div(pc.y, p.a[3]), sd_div(pc.z, p.a[3]));  // sphere.rs:61
     } else on = mk3(type == RT_PRIM_YZ ? 1.0 : 0.0, type == RT_PRIM_XZ ? 1.0 : 0.0, type == RT_PRIM_XY ? 1.0 : 0.0);
-    bool front = sd_dot(d, on) < 0.0;
+    bool front = sd_dot(ld, on) < 0.0;
     Vec3T<double> n = front ? on : -on;
+    if (inst >= 0) {
+        const DevInstanceD& in = P.instances[inst];
+        if (in.flags & 1) {  // rotate_y.rs:51-63
+            const double s = in.sin_theta, c = in.cos_theta;
+            Vec3T<double> q = hp, m = n;
+            q.x = sd_add(sd_mul(c, hp.x), sd_mul(s, hp.z)); q.z = sd_add(sd_mul(-s, hp.x), sd_mul(c, hp.z));
+            m.x = sd_add(sd_mul(c, n.x), sd_mul(s, n.z)); m.z = sd_add(sd_mul(-s, n.x), sd_mul(c, n.z));
+            hp = q;
+            n = sd_dot(ld, m) < 0.0 ? m : -m;
+        }
+        if (in.flags & 2) {  // translate.rs:34-37
+            hp = sd_add3(hp, mk3(in.offset[0], in.offset[1], in.offset[2]));
+            n = sd_dot(d, n) < 0.0 ? n : -n;
+        }
+    }
     if (id) id[i] = P.prim_id[best];
     if (t_out) t_out[i] = best_t;
     if (normal) { normal[3 * i] = n.x; normal[3 * i + 1] = n.y; normal[3 * i + 2] = n.z; }

@@ -62,7 +62,12 @@ struct DevTexture {   // 32 B
 
 struct DevInstance {  // src/geometry/rotate_y.rs, translate.rs
     float sin_theta, cos_theta, ox, oy, oz;
-    int flags;
+    int flags;        // bit 0 rotate, bit 1 translate
+};
+
+struct DevInstanceD {
+    double sin_theta, cos_theta, offset[3];
+    int flags, pad;
 };
 
 template <typename T>
@@ -88,6 +93,7 @@ struct KParams {
     int lin_end[4];             // type-sorted linear table: [0,lin_end[0]) spheres, then xy, xz, yz rects
     int n_perlin;
     int lens_enabled;
+    int ref_aabb;               // scenes with RotateY: BVH culling uses the reference's per-axis Aabb::hit
     const DevPrim* prims;       // all primitives, BVH depth-first order (global memory)
     const DevPrim* prims_lin;   // the same primitives sorted by type (linear modes)
     const DevNode* nodes;       // threaded BVH (global memory)
@@ -120,11 +126,17 @@ struct ConstScene {
     RT_D float4 pc(int i) const { return P.cprims[i].c; }
     RT_D float4 nlo(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }  // no BVH in the constant bank
     RT_D float4 nhi(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    RT_D const DevInstance* instances() const { return nullptr; }            // instanced scenes never take this path
+    RT_D bool reference_aabb() const { return false; }
 };
 
 struct PtrScene {  // shared or global, decided by where the pointers point
     const DevPrim* prims;
     const DevNode* nodes;
+    const DevInstance* inst;   // RotateY / Translate table (global memory), may be null
+    int ref_aabb;              // 1: cull with the reference's per-axis Aabb::hit (scenes with RotateY, Q11/Q14)
+    RT_D const DevInstance* instances() const { return inst; }
+    RT_D bool reference_aabb() const { return ref_aabb != 0; }
     RT_D float4 pa(int i) const { return prims[i].a; }
     RT_D float4 pb(int i) const { return prims[i].b; }
     RT_D float4 pc(int i) const { return prims[i].c; }
@@ -237,17 +249,44 @@ RT_D RayT<T> make_ray(Vec3T<T> o, Vec3T<T> d) {
     return r;
 }
 
-// One primitive of the fp32 tables against a ray; returns t or -1.
+// Ray into the space of an instanced object: Translate is the outer wrapper (the ray moves by
+// -offset, translate.rs:32), RotateY the inner one (rotate_y.rs:38-47).  t is preserved.
+RT_D RayT<float> to_local(const DevInstance& in, const RayT<float>& r) {
+    vec3f o = r.o, d = r.d;
+    if (in.flags & 2) o = mk3(o.x - in.ox, o.y - in.oy, o.z - in.oz);
+    if (in.flags & 1) {
+        const float s = in.sin_theta, c = in.cos_theta;
+        o = mk3(c * o.x - s * o.z, o.y, s * o.x + c * o.z);
+        d = mk3(c * d.x - s * d.z, d.y, s * d.x + c * d.z);
+    }
+    return make_ray(o, d);
+}
+
+// One primitive of the fp32 tables against a ray already in the primitive's space; returns t or -1.
 template <class Scene>
-RT_D float prim_test(const Scene& S, int i, const RayT<float>& r, int last_prim, float t_max) {
-    float4 a = S.pa(i), b = S.pb(i);
+RT_D float prim_test_local(const Scene& S, int i, float4 a, float4 b, const RayT<float>& r, bool self, bool instanced, float t_max) {
+    (void)S; (void)i;
     int type = kinds_prim(b.z);
-    bool self = (i == last_prim);
     if (type == RT_PRIM_SPHERE) {
         const float aa = dot(r.d, r.d);
         return sphere_hit<float>(r.o, r.d, aa, fast_rcp(aa), mk3(a.x, a.y, a.z), a.w, b.x, self, (float)RT_T_MIN, t_max);
     }
+    // an instanced rectangle's hit point goes through a rotation before it becomes the next
+    // origin, so it is not exactly on the plane any more: the rectangle a ray leaves is skipped
+    if (self && instanced) return -1.0f;
     return rect_hit<float>(type, r.o, r.d, r.inv_d, a.x, a.y, a.z, a.w, b.x, (float)RT_T_MIN, t_max);
+}
+
+// One primitive against a world-space ray (SceneObject::hit, src/scene.rs:98-101).
+template <class Scene>
+RT_D float prim_test(const Scene& S, int i, const RayT<float>& r, int last_prim, float t_max) {
+    float4 a = S.pa(i), b = S.pb(i);
+    const int inst = kinds_inst(b.z);
+    if (inst >= 0) {
+        const RayT<float> lr = to_local(S.instances()[inst], r);
+        return prim_test_local(S, i, a, b, lr, i == last_prim, true, t_max);
+    }
+    return prim_test_local(S, i, a, b, r, i == last_prim, false, t_max);
 }
 
 #define RT_NO_HIT 3.0e38f   /* closest-hit distances start here; +inf marks "no candidate" */
@@ -378,24 +417,55 @@ RT_D bool aabb_hit(float4 lo, float4 hi, const RayT<float>& r, float t_max) {
     return tn <= tf;
 }
 
+// Aabb::hit exactly as the reference evaluates it (src/aabb.rs:42-59): every axis is clipped
+// against the ORIGINAL [t_min, t_max] (Q12).  Needed when stored boxes are not bounding boxes —
+// RotateY's (Q14) — because the box then decides which rays may see the object at all (Q11).
+RT_D bool aabb_hit_reference(float4 lo, float4 hi, const RayT<float>& r, float t_max) {
+    const float t_min = (float)RT_T_MIN;
+    float t0 = (lo.x - r.o.x) * r.inv_d.x, t1 = (hi.x - r.o.x) * r.inv_d.x;
+    if (r.inv_d.x < 0.0f) { float q = t0; t0 = t1; t1 = q; }
+    if ((t1 < t_max ? t1 : t_max) <= (t0 > t_min ? t0 : t_min)) return false;
+    t0 = (lo.y - r.o.y) * r.inv_d.y; t1 = (hi.y - r.o.y) * r.inv_d.y;
+    if (r.inv_d.y < 0.0f) { float q = t0; t0 = t1; t1 = q; }
+    if ((t1 < t_max ? t1 : t_max) <= (t0 > t_min ? t0 : t_min)) return false;
+    t0 = (lo.z - r.o.z) * r.inv_d.z; t1 = (hi.z - r.o.z) * r.inv_d.z;
+    if (r.inv_d.z < 0.0f) { float q = t0; t0 = t1; t1 = q; }
+    if ((t1 < t_max ? t1 : t_max) <= (t0 > t_min ? t0 : t_min)) return false;
+    return true;
+}
+
 // Threaded pre-order BVH: left child = i + 1, `skip` = next node when this
 // subtree is done.  Visits left before right with a shrinking t_max, exactly
-// the order of Node::hit (src/bvh_node.rs:112-132).
+// the order of Node::hit (src/bvh_node.rs:112-132).  A leaf is one top-level
+// object: one primitive, or the six sides of a Box tested in order
+// (src/geometry/box.rs:82-101); all of them share the object's instance
+// transform, which is applied to the ray once per leaf.
 template <class Scene>
 RT_D int closest_hit_bvh(const Scene& S, int n_nodes, const RayT<float>& r, int last_prim, float& best_t) {
     int best = -1;
     best_t = RT_NO_HIT;
+    const bool ref_box = S.reference_aabb();
     int i = 0;
 #pragma unroll 1
     while (i < n_nodes) {
         float4 lo = S.nlo(i), hi = S.nhi(i);
         int leaf = __float_as_int(hi.w);
-        if (aabb_hit(lo, hi, r, best_t)) {
+        const bool box_hit = ref_box ? aabb_hit_reference(lo, hi, r, best_t) : aabb_hit(lo, hi, r, best_t);
+        if (box_hit) {
             if (leaf >= 0) {
                 int first = leaf & 0xffffff, count = leaf >> 24;
-                for (int p = first; p < first + count; ++p) {
-                    float t = prim_test(S, p, r, last_prim, best_t);
-                    if (t >= 0.0f) { best_t = t; best = p; }
+                const int inst = kinds_inst(S.pb(first).z);
+                if (inst >= 0) {
+                    const RayT<float> lr = to_local(S.instances()[inst], r);
+                    for (int p = first; p < first + count; ++p) {
+                        float t = prim_test_local(S, p, S.pa(p), S.pb(p), lr, p == last_prim, true, best_t);
+                        if (t >= 0.0f) { best_t = t; best = p; }
+                    }
+                } else {
+                    for (int p = first; p < first + count; ++p) {
+                        float t = prim_test_local(S, p, S.pa(p), S.pb(p), r, p == last_prim, false, best_t);
+                        if (t >= 0.0f) { best_t = t; best = p; }
+                    }
                 }
                 i = __float_as_int(lo.w);
             } else {
@@ -412,15 +482,16 @@ RT_D int closest_hit_bvh(const Scene& S, int n_nodes, const RayT<float>& r, int 
 // Hit record (src/geometry.rs:17-57) rebuilt from (ray, t, primitive).
 // ---------------------------------------------------------------------------
 struct Hit {
-    vec3f p, n;        // point, face normal
-    vec3f outward;     // outward normal (sphere uv, sphere.rs:61-63)
+    vec3f p, n;        // point, face normal (world space)
+    vec3f outward;     // outward normal in the primitive's own space (sphere uv, sphere.rs:61-63)
+    vec3f lp;          // hit point in the primitive's own space (rectangle uv)
     bool front_face;
 };
 
 template <class Scene>
-RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t) {
+RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT<float>& r, float t) {
+    (void)S; (void)prim;
     Hit h;
-    float4 a = S.pa(prim), b = S.pb(prim);
     int type = kinds_prim(b.z);
     h.p = r.o + t * r.d;  // Ray::at
     if (type == RT_PRIM_SPHERE) {
@@ -441,6 +512,34 @@ RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t) {
         const float sgn = h.front_face ? 1.0f : -1.0f;
         h.n = mk3(sgn * h.outward.x, sgn * h.outward.y, sgn * h.outward.z);
     }
+    h.lp = h.p;
+    return h;
+}
+
+// Hit record of (world ray, t, primitive), through the instance wrappers when there are any:
+// RotateY turns point and normal back and re-derives the face from the ROTATED ray and the
+// WORLD normal (rotate_y.rs:51-63, Q15); Translate adds the offset and runs set_face_normal
+// again on the already-flipped normal (translate.rs:34-37, Q15).
+template <class Scene>
+RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t) {
+    float4 a = S.pa(prim), b = S.pb(prim);
+    const int inst = kinds_inst(b.z);
+    if (inst < 0) return make_hit_local(S, prim, a, b, r, t);
+    const DevInstance in = S.instances()[inst];
+    const RayT<float> lr = to_local(in, r);
+    Hit h = make_hit_local(S, prim, a, b, lr, t);
+    if (in.flags & 1) {
+        const float s = in.sin_theta, c = in.cos_theta;
+        h.p = mk3(c * h.p.x + s * h.p.z, h.p.y, -s * h.p.x + c * h.p.z);
+        const vec3f n = mk3(c * h.n.x + s * h.n.z, h.n.y, -s * h.n.x + c * h.n.z);
+        h.front_face = dot(lr.d, n) < 0.0f;
+        h.n = h.front_face ? n : -n;
+    }
+    if (in.flags & 2) {
+        h.p = mk3(h.p.x + in.ox, h.p.y + in.oy, h.p.z + in.oz);
+        h.front_face = dot(r.d, h.n) < 0.0f;   // the moved ray has the original direction
+        h.n = h.front_face ? h.n : -h.n;
+    }
     return h;
 }
 
@@ -456,8 +555,8 @@ RT_D void hit_uv(const Scene& S, int prim, const Hit& h, float& u, float& v) {
         u = phi / (2.0f * PI_F);
         v = theta / PI_F;
     } else {
-        float pa = type == RT_PRIM_YZ ? h.p.y : h.p.x;
-        float pb = type == RT_PRIM_XY ? h.p.y : h.p.z;
+        float pa = type == RT_PRIM_YZ ? h.lp.y : h.lp.x;
+        float pb = type == RT_PRIM_XY ? h.lp.y : h.lp.z;
         u = (pa - a.x) / (a.y - a.x);
         v = (pb - a.z) / (a.w - a.z);
     }

@@ -202,7 +202,7 @@ wf_intersect(const __grid_constant__ KParams P, WfPool W) {
         int prim;
         float packed;
         if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); prim = closest_hit<MODE>(P, S, r, last_prim, t); packed = prim >= 0 ? S.pb(prim).z : 0.f; }
-        else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; prim = closest_hit<MODE>(P, S, r, last_prim, t); packed = prim >= 0 ? S.pb(prim).z : 0.f; }
+        else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t); packed = prim >= 0 ? S.pb(prim).z : 0.f; }
         if (prim < 0) {  // renderer.rs:78-88
             vec3f bg = background_color(P, r.d);
             float4 a = W.acc[i];
@@ -279,7 +279,7 @@ wf_shade(const __grid_constant__ KParams P, WfPool W) {
         ConstScene S(P);
         if (cls == 2) wf_shade_one<SAMPLER, ROUNDS, true>(P, W, X, S, i); else wf_shade_one<SAMPLER, ROUNDS, false>(P, W, X, S, i);
     } else {
-        PtrScene S; S.prims = L.prims; S.nodes = L.nodes;
+        PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb;
         if (cls == 2) wf_shade_one<SAMPLER, ROUNDS, true>(P, W, X, S, i); else wf_shade_one<SAMPLER, ROUNDS, false>(P, W, X, S, i);
     }
 }

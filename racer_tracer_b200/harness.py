@@ -690,8 +690,11 @@ class CudaRenderer:
         capi.check(self.lib, self.lib.rc_upload_scene(self.ctx, job.scene.ptr))
         capi.check(self.lib, self.lib.rc_set_camera(self.ctx, C.byref(job.camera)))
 
-    def render(self, params: rc_params, cancel=None) -> np.ndarray:
-        out = np.empty((params.height, params.width, 3), dtype=np.float64)
+    def render(self, params: rc_params, cancel=None, out: np.ndarray | None = None) -> np.ndarray:
+        """rc_render into `out` ((H, W, 3) float64, C-contiguous; e.g. a pinned buffer) or a new array."""
+        if out is None:
+            out = np.empty((params.height, params.width, 3), dtype=np.float64)
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == params.height * params.width * 3
         cptr = C.cast(C.pointer(cancel), C.POINTER(C.c_int32)) if cancel is not None else None
         capi.check(self.lib, self.lib.rc_render(self.ctx, C.byref(params),
                                                 out.ctypes.data_as(C.POINTER(C.c_double)), cptr))

@@ -8,7 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-SCENES = ["three_balls", "emissive", "noise_and_textures", "cornell_box", "clown"]
+SCENES = ["three_balls", "emissive", "noise_and_textures", "cornell_box", "clown"]   # the BASELINE configs
+# + the reference's Sandbox scene (Box / RotateY / Translate instances) in YAML form
+SCENES_X = SCENES + ["sandbox_boxes"]
 
 
 def pytest_configure(config):

@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES, scene_path
+from conftest import SCENES, SCENES_X, scene_path
 from racer_tracer_b200 import capi, harness
 
 pytestmark = pytest.mark.gpu
@@ -61,7 +61,7 @@ def ambiguous_mask(oracle, job, p):
     return mask
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", SCENES_X)
 def test_primary_aov_f64_is_bit_exact(renderer, oracle, cfg, name):
     """precision=64: the reference's f64 operation order on the GPU.  ids, t and
     normals equal the CPU restatement bit for bit, ties included."""
@@ -78,7 +78,7 @@ def test_primary_aov_f64_is_bit_exact(renderer, oracle, cfg, name):
     assert np.array_equal(pt, opt)
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", SCENES_X)
 def test_primary_aov_fp32_matches_oracle(renderer, oracle, cfg, name):
     """precision=32: the renderer's own fp32 ray-gen + closest hit.  ids are
     bit-exact wherever the f64 answer is stable under an fp32-sized shift of the
@@ -108,7 +108,7 @@ def test_primary_aov_fp32_matches_oracle(renderer, oracle, cfg, name):
     assert (np.abs(pt[hit] - opt[hit]).max(axis=1) / scale).max() <= 2e-4   # one fp32 ulp at |p| ~ 1000 is 6e-5
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", SCENES_X)
 @pytest.mark.parametrize("sampler", [capi.RC_SAMPLER_DIRECT, capi.RC_SAMPLER_REJECTION])
 def test_same_stream_image_matches_oracle(renderer, oracle, cfg, name, sampler):
     """GPU fp32 and oracle f64 consume identical Philox streams: images agree
@@ -151,7 +151,7 @@ def test_converged_image_psnr_independent_streams(renderer, oracle, cfg, name, s
     assert got >= noise_floor - 1.0, "the GPU image is further from the oracle than Monte-Carlo noise explains"
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", SCENES_X)
 def test_wavefront_traces_the_same_paths_as_the_megakernel(renderer, oracle, cfg, name):
     """Both variants share ray-gen, RNG streams, intersection and shading code; only the
     fp32 summation order of the per-pixel sum differs (chunks of 32 samples + atomics)."""
