@@ -79,6 +79,7 @@ struct DeviceState {
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> tex;
     DevBuf<float> accum;
+    DevBuf<float> slice_buf;
     DevBuf<double> out64;
     DevBuf<unsigned long long> counter;
     WavefrontState wf;
@@ -266,6 +267,7 @@ void partition(KParams& kp, const rc_params* p, int part, int parts) {
     for (int r = 0; r < 10; ++r) kp.ks[r] = kp.key + (uint32_t)r * PHILOX2_W;
     kp.inv_wm1 = 1.0f / (float)(p->width - 1); kp.inv_hm1 = 1.0f / (float)(p->height - 1);
     kp.tile_w = RT_TILE_W; kp.tile_h = RT_TILE_H;
+    kp.slices = 1; kp.slice_buf = nullptr;
     kp.tiles_x = (p->width + RT_TILE_W - 1) / RT_TILE_W;
     int tiles_y = (p->height + RT_TILE_H - 1) / RT_TILE_H;
     int total = kp.tiles_x * tiles_y;
@@ -335,17 +337,37 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         }
         const int s0 = kp.s_begin, s1 = kp.s_end;
         const int step = cancel ? 32 : (s1 - s0);
+        // few tiles on this device (its share of a multi-GPU render): cut every tile's sample range
+        // into slices so that the grid is still >= 8 full machine loads of CTAs
+        kp.slices = 1;
+        kp.slice_buf = nullptr;
+        if (!cancel) {
+            const long long want = 8LL * d.sm_count * 10;
+            long long sl = (want + kp.n_tiles - 1) / kp.n_tiles;
+            if (sl > (s1 - s0) / 16) sl = (s1 - s0) / 16;
+            if (const char* e = std::getenv("RC_SLICES")) sl = std::atoll(e);
+            if (sl > 1) {
+                CUDA_TRY(d.slice_buf.resize((size_t)sl * kp.n_tiles * RT_BLOCK * 3));
+                kp.slices = (int)sl;
+                kp.slice_buf = d.slice_buf.p;
+            }
+        }
         for (int s = s0; s < s1; s += step) {
             kp.s_begin = s; kp.s_end = s + step < s1 ? s + step : s1;
             int rc;
             if (spec) {
-                rc = spec_launch(spec, kp, accum, kp.n_tiles, ctx->smem_bytes, d.stream) == 0 ? RC_OK : RC_ERR_CUDA;
+                rc = spec_launch(spec, kp, accum, kp.n_tiles * kp.slices, ctx->smem_bytes, d.stream) == 0 ? RC_OK : RC_ERR_CUDA;
                 if (rc != RC_OK) return fail(rc, "launch of the scene-specialised kernel failed");
             } else {
-                rc = launch_mega(ctx->mode, ctx->has_textures, kp, accum, p->sampler, rounds, kp.n_tiles, ctx->smem_bytes, d.stream);
+                rc = launch_mega(ctx->mode, ctx->has_textures, kp, accum, p->sampler, rounds, kp.n_tiles * kp.slices, ctx->smem_bytes, d.stream);
             }
             if (rc != RC_OK) return rc;
             ++launches;
+            if (kp.slices > 1) {
+                reduce_slices_kernel<<<(kp.n_tiles * RT_BLOCK + 255) / 256, 256, 0, d.stream>>>(kp, accum);
+                CUDA_TRY(cudaGetLastError());
+                ++launches;
+            }
             if (cancel && n_dev == 1) {
                 CUDA_TRY(cudaStreamSynchronize(d.stream));
                 if (cancelled(cancel)) { was_cancelled = true; return RC_OK; }
@@ -619,7 +641,7 @@ int rc_destroy(rc_ctx* ctx) {
         cudaSetDevice(d.device);
         cudaDeviceSynchronize();
         free_scene(d);
-        d.accum.release(); d.out64.release(); d.counter.release();
+        d.accum.release(); d.slice_buf.release(); d.out64.release(); d.counter.release();
         wavefront_release(d.wf);
         spec_release(d.spec_cache);
         if (d.ev0) cudaEventDestroy(d.ev0);

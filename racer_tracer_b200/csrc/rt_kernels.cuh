@@ -213,12 +213,23 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     SmemLayout L = stage_scene<MODE>(P, smem);
     TexCtx X; X.perlin = L.perlin; X.perm = L.perm;
 
-    const int tile = P.tile_first + blockIdx.x * P.tile_stride;
+    // CTA -> (tile, slice of the sample range).  With one GPU there are thousands of tiles and
+    // slices == 1; when the tiles are shared out over several GPUs each tile's samples are cut
+    // into `slices` CTAs so the grid still fills the machine many times over (no long tail).
+    const int tile_k = P.slices > 1 ? (int)blockIdx.x / P.slices : (int)blockIdx.x;
+    const int slice = P.slices > 1 ? (int)blockIdx.x - tile_k * P.slices : 0;
+    const int tile = P.tile_first + tile_k * P.tile_stride;
     const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int px = tx * RT_TILE_W + (warp & 1) * 8 + (lane & 7);
     const int py = ty * RT_TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool valid = px < P.width && py < P.height;
+    int s_first = P.s_begin, s_last = P.s_end;
+    if (P.slices > 1) {
+        const int n = P.s_end - P.s_begin;
+        s_first = P.s_begin + (int)(((long long)n * slice) / P.slices);
+        s_last = P.s_begin + (int)(((long long)n * (slice + 1)) / P.slices);
+    }
 
     PixelCtx pc = pixel_setup<ROUNDS>(P, valid ? px : 0, valid ? py : 0);
     RngCtx R; R.ks = P.ks; R.pixel = pc.pixel; R.sample = 0;
@@ -228,7 +239,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     // ray_color's `emitted + attenuation * recurse` collapses to throughput x terminal radiance.
     vec3f sum = mk3(0.0f, 0.0f, 0.0f);
     vec3f o = mk3(0.0f, 0.0f, 0.0f), d = o, T = o;
-    int s = valid ? P.s_begin : P.s_end;
+    int s = valid ? s_first : s_last;
     bool alive = false;
     int depth_left = 0, last_prim = -1;
     uint32_t bounce = 0;
@@ -236,7 +247,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
 
 #pragma unroll 1
     while (true) {
-        if (!alive && s < P.s_end) {
+        if (!alive && s < s_last) {
             // ---- regenerate: next sample of this pixel ----
             R.sample = (uint32_t)s;
             float vjit = 0.5f;
@@ -250,7 +261,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             if (!alive) sum = sum + T;  // renderer.rs:48-56: depth 0 is white
         }
         if (!__any_sync(0xffffffffu, alive)) {
-            if (!__any_sync(0xffffffffu, s < P.s_end)) break;
+            if (!__any_sync(0xffffffffu, s < s_last)) break;
             continue;
         }
         if (alive) {
@@ -279,7 +290,11 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             if (!alive) sum = sum + T * X_end;
         }
     }
-    if (valid) {
+    if (P.slices > 1) {
+        // partial sum of this slice; reduce_slices_kernel adds the slices in order (deterministic)
+        float* a = P.slice_buf + 3 * ((size_t)slice * ((size_t)P.n_tiles * RT_BLOCK) + (size_t)tile_k * RT_BLOCK + threadIdx.x);
+        a[0] = sum.x; a[1] = sum.y; a[2] = sum.z;
+    } else if (valid) {
         float* a = accum + 3 * (size_t)pc.pixel;
         a[0] += sum.x; a[1] += sum.y; a[2] += sum.z;
     }
@@ -289,6 +304,26 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
 }
 
 #ifndef RT_SPECIALIZED
+// accum[pixel] += sum over slices (in slice order) of the partial sums the sliced megakernel left
+__global__ void reduce_slices_kernel(const __grid_constant__ KParams P, float* __restrict__ accum) {
+    const int rank = blockIdx.x * blockDim.x + threadIdx.x;     // tile_k * 128 + thread
+    if (rank >= P.n_tiles * RT_BLOCK) return;
+    const int tile_k = rank / RT_BLOCK, within = rank % RT_BLOCK;
+    const int tile = P.tile_first + tile_k * P.tile_stride;
+    const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+    const int warp = within >> 5, lane = within & 31;
+    const int px = tx * RT_TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int py = ty * RT_TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    if (px >= P.width || py >= P.height) return;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int j = 0; j < P.slices; ++j) {
+        const float* a = P.slice_buf + 3 * ((size_t)j * ((size_t)P.n_tiles * RT_BLOCK) + rank);
+        sx += a[0]; sy += a[1]; sz += a[2];
+    }
+    float* dst = accum + 3 * ((size_t)py * P.width + px);
+    dst[0] += sx; dst[1] += sy; dst[2] += sz;
+}
+
 template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
 __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)
 megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) {

@@ -88,6 +88,8 @@ struct KParams {
     uint32_t key;               // Philox2x32 key = seed_lo ^ seed_hi
     uint32_t ks[10];            // its key schedule: key + r * 0x9E3779B9
     int tile_first, tile_stride, n_tiles;   // interleaved tile partition
+    int slices;                 // > 1: every tile's sample range is cut into this many CTAs (few tiles per GPU)
+    float* slice_buf;           // [slices][n_tiles * 128][3] partial sums, reduced in slice order afterwards
     int tiles_x, tile_w, tile_h;
     int n_prims, n_nodes;
     int lin_end[4];             // type-sorted linear table: [0,lin_end[0]) spheres, then xy, xz, yz rects

@@ -234,6 +234,27 @@ def test_partitions_cover_the_image_exactly(renderer, cfg):
         assert torch.allclose(s, whole, rtol=1e-5, atol=1e-5)
 
 
+def test_sliced_tiles_equal_unsliced(renderer, cfg):
+    """Few tiles per device (a multi-GPU share, or a small image): each tile's sample range is cut
+    into several CTAs whose partial sums are added in slice order.  Same samples, deterministic,
+    equal to the unsliced render up to fp32 summation order."""
+    w, h, spp = 128, 96, 256          # 96 tiles -> sliced
+    job = job_for("cornell_box", cfg, w, h)
+    renderer.upload(job)
+    p = harness.make_params(w, h, spp, 20, seed=3)
+    a = renderer.render(p)
+    assert np.array_equal(a, renderer.render(p))
+    os.environ["RC_SLICES"] = "1"
+    try:
+        b = renderer.render(p)
+    finally:
+        del os.environ["RC_SLICES"]
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert renderer.stats().kernel_launches == 1
+    renderer.render(p)
+    assert renderer.stats().kernel_launches == 2     # sliced megakernel + reduce_slices_kernel
+
+
 def test_render_is_deterministic_and_seeded(renderer, cfg):
     w, h = 128, 96
     job = job_for("cornell_box", cfg, w, h)
