@@ -127,10 +127,13 @@ struct Xoshiro {
 //   c0 = pixel (24 bits) | rejection iteration j << 24
 //   c1 = sample (24 bits) | bounce (6 bits) << 24 | tag << 30
 //   key = seed_lo ^ seed_hi
-const uint32_t TAG_PATH = 0u;    // bounce 0: x -> v jitter, y -> ray time; bounce b >= 1: the event's 64 bits
+// One PATH block per path segment e (0 = primary ray): the upper 24 bits of each word feed the
+// scattering event at the end of that segment (hit number b = e + 1); the low byte of each word
+// is spare, and in block 0 the two spare bytes are the sample's 16-bit v jitter.
+const uint32_t TAG_PATH = 0u;    // segment e: scatter bits of hit e + 1; e = 0 also: low bytes -> v jitter
 const uint32_t TAG_PIXEL = 1u;   // x -> per-pixel u jitter
-const uint32_t TAG_LENS = 2u;    // j = 0: direct lens sample; j >= 1: rejection iteration j
-const uint32_t TAG_REJECT = 3u;  // (bounce b, iteration j): three 21-bit uniforms
+const uint32_t TAG_LENS = 2u;    // j = 0: direct lens sample, low bytes -> ray time; j >= 1: rejection iteration j
+const uint32_t TAG_REJECT = 3u;  // (hit number b, iteration j): three 21-bit uniforms
 
 inline double u21_from_bits(uint32_t x) { return (double)x * (1.0 / 2097152.0); }  // x < 2^21
 
@@ -157,11 +160,16 @@ struct Draws {
         words(0u, 0u, 0u, TAG_PIXEL, w);
         return u01_from_bits(w[0]);
     }
+    static double u16_low_bytes(const uint32_t w[2]) { return (double)(((w[0] & 0xFFu) << 8) | (w[1] & 0xFFu)) * (1.0 / 65536.0); }
+    static void split16(const uint32_t w[2], double u[3]) {   // three 16-bit uniforms from the upper 24 bits of each word
+        u[0] = (double)(w[0] >> 16) * (1.0 / 65536.0); u[1] = (double)(w[1] >> 16) * (1.0 / 65536.0);
+        u[2] = (double)((((w[0] >> 8) & 0xFFu) << 8) | ((w[1] >> 8) & 0xFFu)) * (1.0 / 65536.0);
+    }
     double v_jitter() const {  // cpu.rs:39-40
         if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
         uint32_t w[2];
         words(0u, sample, 0u, TAG_PATH, w);
-        return u01_from_bits(w[0]);
+        return u16_low_bytes(w);
     }
     // j = 0: the direct lens sample (u1, u2); j >= 1: the j-th iteration of random_in_unit_disk
     void lens(uint32_t j, double u[2]) const {
@@ -173,25 +181,25 @@ struct Draws {
     double time_u() const {  // camera.rs:335
         if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
         uint32_t w[2];
-        words(0u, sample, 0u, TAG_PATH, w);
-        return u01_from_bits(w[1]);
+        words(0u, sample, 0u, TAG_LENS, w);
+        return u16_low_bytes(w);
     }
     void two(uint32_t b, double u[2]) const {     // lambertian, direct
         if (backend != ORACLE_RNG_PHILOX) { u[0] = seq->uniform(); u[1] = seq->uniform(); return; }
         uint32_t w[2];
-        words(0u, sample, b, TAG_PATH, w);
+        words(0u, sample, b - 1u, TAG_PATH, w);   // hit number b closes segment b - 1
         u[0] = u01_from_bits(w[0]); u[1] = u01_from_bits(w[1]);
     }
-    void three(uint32_t b, double u[3]) const {   // metal, direct: three 21-bit uniforms
+    void three(uint32_t b, double u[3]) const {   // metal, direct: three 16-bit uniforms
         if (backend != ORACLE_RNG_PHILOX) { for (int i = 0; i < 3; ++i) u[i] = seq->uniform(); return; }
         uint32_t w[2];
-        words(0u, sample, b, TAG_PATH, w);
-        split21(w, u);
+        words(0u, sample, b - 1u, TAG_PATH, w);
+        split16(w, u);
     }
     double one(uint32_t b) const {                // dielectric
         if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
         uint32_t w[2];
-        words(0u, sample, b, TAG_PATH, w);
+        words(0u, sample, b - 1u, TAG_PATH, w);
         return u01_from_bits(w[0]);
     }
     void reject(uint32_t b, uint32_t j, double u[3]) const {  // iteration j of a rejection loop

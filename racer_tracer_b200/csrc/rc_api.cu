@@ -204,7 +204,9 @@ int pick_mode(const rc_scene* s, bool rects_fit, bool instanced, size_t& smem_by
     }
     smem_bytes = perlin_bytes;
     if (mode == RT_MODE_SMEM_BVH) smem_bytes += bvh_bytes;
-    if (mode == RT_MODE_SMEM_LINEAR) smem_bytes += (size_t)s->n_prims * sizeof(DevPrim);
+    // the linear modes stage the type-sorted table (the constant-bank mode too: its hit records
+    // and shading index it per lane)
+    if (mode == RT_MODE_SMEM_LINEAR || mode == RT_MODE_CONST_LINEAR) smem_bytes += (size_t)s->n_prims * sizeof(DevPrim);
     return mode;
 }
 
@@ -475,6 +477,8 @@ static void build_tables(const rc_scene* s, HostTables& t) {
         p.b.z = bits(packed);
         p.b.w = bits(tex_index);
         p.c = f4(col[0], col[1], col[2], ubits(s->prim_id[i]));
+        // +axis unit normal of a rectangle (xy_rect.rs:45, xz_rect.rs:46, yz_rect.rs:46); 0 for a sphere
+        p.n = make_float4(type == RC_PRIM_YZ_RECT ? 1.f : 0.f, type == RC_PRIM_XZ_RECT ? 1.f : 0.f, type == RC_PRIM_XY_RECT ? 1.f : 0.f, 0.f);
         kinds[i] = type;
         ids[i] = s->prim_id[i];
         if (s->prim_aabb)

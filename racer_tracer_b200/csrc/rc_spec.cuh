@@ -16,6 +16,8 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <map>
 #include <sstream>
@@ -87,6 +89,8 @@ inline bool spec_load_api(const void* anchor_symbol) {
     return true;
 }
 
+inline int __float_as_int_host(float f) { int i; std::memcpy(&i, &f, sizeof(i)); return i; }
+
 inline std::string spec_float(float v) {
     char buf[64];
     std::snprintf(buf, sizeof(buf), "%.9g", (double)v);
@@ -99,6 +103,15 @@ inline std::string spec_float(float v) {
 // (type-sorted constant-bank table).
 inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
     std::ostringstream o;
+    // primitive kinds present, background, regeneration batching: known before the headers are read
+    int prims_mask = 0;
+    if (kp.lin_end[0] > 0) prims_mask |= 1;
+    for (int g = 0; g < 3; ++g) if (kp.lin_end[g + 1] > kp.lin_end[g]) prims_mask |= 2 << g;
+    o << "#define RT_SPEC_PRIMS " << prims_mask << "\n";
+    const bool black = __float_as_int_host(kp.bg_a.w) != 0 && kp.bg_a.x == 0.f && kp.bg_a.y == 0.f && kp.bg_a.z == 0.f;
+    o << "#define RT_SPEC_BG_BLACK " << (black ? 1 : 0) << "\n";
+    if (const char* e = std::getenv("RC_REGEN_MIN")) o << "#define RT_REGEN_MIN " << std::atoi(e) << "\n";
+    if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
     o << "#include \"rt_scene.cuh\"\n";
     o << "RT_D int spec_closest_hit(const RayT<float>& r, int last_prim, float& best_t) {\n";
     o << "    int best = -1;\n    best_t = RT_NO_HIT;\n    (void)last_prim;\n";

@@ -42,11 +42,14 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
         L.nodes = reinterpret_cast<const DevNode*>(dst);
         dst += P.n_nodes * 2;
     }
-    if (MODE == RT_MODE_SMEM_BVH || MODE == RT_MODE_SMEM_LINEAR) {
-        const float4* src = reinterpret_cast<const float4*>(MODE == RT_MODE_SMEM_LINEAR ? P.prims_lin : P.prims);
-        for (int i = threadIdx.x; i < P.n_prims * 3; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (MODE != RT_MODE_GLOBAL_BVH) {
+        // the constant-bank mode stages the (type-sorted) table too: its intersection loops read
+        // the kernel parameters through uniform indices, the hit record and the shading read
+        // this copy through per-lane indices
+        const float4* src = reinterpret_cast<const float4*>(MODE == RT_MODE_SMEM_BVH ? P.prims : P.prims_lin);
+        for (int i = threadIdx.x; i < P.n_prims * 4; i += blockDim.x) dst[i] = __ldg(src + i);
         L.prims = reinterpret_cast<const DevPrim*>(dst);
-        dst += P.n_prims * 3;
+        dst += P.n_prims * 4;
     }
     if (P.n_perlin > 0) {
         for (int i = threadIdx.x; i < P.n_perlin * 256; i += blockDim.x) dst[i] = __ldg(P.perlin + i);
@@ -157,14 +160,14 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
         if (SAMPLER == 1) rv = unit_vector(reject_in_unit_sphere<ROUNDS>(R, bounce));
         else rv = sphere_direct(u24(rnd.x), u24(rnd.y));
         nd = h.n + rv;
-        const float s = 1e-8f;  // near_zero, vec3.rs:127-130
-        if (fabsf(nd.x) < s && fabsf(nd.y) < s && fabsf(nd.z) < s) nd = h.n;
+        // near_zero, vec3.rs:127-130: all three components below 1e-8 (rv = -n; one draw in 2^24)
+        if (fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z)) < 1e-8f) nd = h.n;
     } else if (RT_HAS_MAT(RT_MAT_METAL) && (mat == RT_MAT_METAL || !RT_HAS_MAT(RT_MAT_DIELECTRIC))) {  // metal.rs:25-44
         vec3f rv;
         if (SAMPLER == 1) rv = reject_in_unit_sphere<ROUNDS>(R, bounce);
         else {
             float u1, u2, u3;
-            u21x3(rnd, u1, u2, u3);
+            u16x3(rnd, u1, u2, u3);
             rv = cbrtf(u3) * sphere_direct(u1, u2);
         }
         vec3f refl = reflect(unit_vector(r.d), h.n);
@@ -208,6 +211,17 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 6
 #endif
+// Lanes whose path ended wait until at least this many lanes of the warp want a new sample
+// (or nobody is alive): regeneration is the one part of the loop that runs at low lane
+// occupancy, so it is batched.  1 = regenerate immediately.
+#ifndef RT_REGEN_MIN
+#define RT_REGEN_MIN 1
+#endif
+// Background known at compile time (scene-specialised kernels): 0 unknown, 1 solid black
+#ifndef RT_SPEC_BG_BLACK
+#define RT_SPEC_BG_BLACK 0
+#endif
+
 template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
 RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned char* smem) {
     SmemLayout L = stage_scene<MODE>(P, smem);
@@ -242,52 +256,62 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     int s = valid ? s_first : s_last;
     bool alive = false;
     int depth_left = 0, last_prim = -1;
-    uint32_t bounce = 0;
+    uint32_t seg = 0;          // index of the segment about to be traced (0 = primary ray)
     unsigned nseg = 0;
+    if (P.max_depth <= 0) {    // renderer.rs:48-56: depth 0 is white, for every sample
+        const float n = (float)(s_last - s);
+        sum = mk3(n, n, n);
+        s = s_last;
+    }
 
 #pragma unroll 1
     while (true) {
-        if (!alive && s < s_last) {
-            // ---- regenerate: next sample of this pixel ----
-            R.sample = (uint32_t)s;
-            float vjit = 0.5f;
-            if (!P.fixed_jitter) vjit = u24(philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, 0u, RT_TAG_PATH), P.ks).x);
-            camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d);
+        // ---- lanes whose path ended take the next sample of their pixel (bookkeeping only) ----
+        bool fresh = !alive && s < s_last;
+        if (RT_REGEN_MIN > 1) {
+            const unsigned want = __ballot_sync(0xffffffffu, fresh), live = __ballot_sync(0xffffffffu, alive);
+            if ((want | live) == 0u) break;
+            if (live != 0u && __popc(want) < RT_REGEN_MIN) fresh = false;
+        } else {
+            if (!__any_sync(0xffffffffu, fresh || alive)) break;
+        }
+        if (fresh) {
+            R.sample = (uint32_t)s++;
+            seg = 0; last_prim = -1;
             T = mk3(1.0f, 1.0f, 1.0f);
             depth_left = P.max_depth;
-            bounce = 0; last_prim = -1;
-            alive = depth_left > 0;
-            ++s;
-            if (!alive) sum = sum + T;  // renderer.rs:48-56: depth 0 is white
-        }
-        if (!__any_sync(0xffffffffu, alive)) {
-            if (!__any_sync(0xffffffffu, s < s_last)) break;
-            continue;
+            alive = true;
         }
         if (alive) {
+            // ---- the segment's random block: drawn here, by all lanes together ----
+            const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, seg, RT_TAG_PATH), P.ks);
+            if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337
+                const float vjit = P.fixed_jitter ? 0.5f : u16lo(rnd);
+                camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d);
+            }
             RayT<float> r = make_ray(o, d);
             float t;
             int prim;
-            if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
+            if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, L.prims); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
             else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t); }
             ++nseg;
-            vec3f X_end;   // radiance that ends the path
             if (prim < 0) {  // renderer.rs:78-88
-                X_end = background_color(P, d);
+                if (!RT_SPEC_BG_BLACK) sum = sum + T * background_color(P, d);
                 alive = false;
             } else {
-                ++bounce;
-                uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, bounce, RT_TAG_PATH), P.ks);
+                ++seg;   // hit number along the path (1 = primary hit)
+                vec3f X_end;   // radiance that ends the path
                 bool cont;
-                if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, X_end); }
-                else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, bounce, rnd, o, d, T, X_end); }
-                if (!cont) alive = false;                 // absorbed (X_end = 0) or a light (X_end = emission)
-                else {
+                if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, L.prims); cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
+                else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
+                if (!cont) {                 // absorbed (X_end = 0) or a light (X_end = emission)
+                    sum = sum + T * X_end;
+                    alive = false;
+                } else {
                     last_prim = prim;
-                    if (--depth_left == 0) { X_end = mk3(1.0f, 1.0f, 1.0f); alive = false; }  // white at depth 0
+                    if (--depth_left == 0) { sum = sum + T; alive = false; }  // white at depth 0
                 }
             }
-            if (!alive) sum = sum + T * X_end;
         }
     }
     if (P.slices > 1) {
@@ -357,7 +381,7 @@ primary_aov_kernel(const __grid_constant__ KParams P, uint32_t* __restrict__ id,
     Hit h;
     uint32_t oid = 0;
     if (MODE == RT_MODE_CONST_LINEAR) {
-        ConstScene S(P);
+        ConstScene S(P, L.prims);
         prim = closest_hit<MODE>(P, S, r, -1, t);
         if (prim >= 0) { h = make_hit(S, prim, r, t); oid = (uint32_t)__float_as_int(S.pc(prim).w); }
     } else {

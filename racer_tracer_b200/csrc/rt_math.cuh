@@ -86,19 +86,32 @@ RT_D uint2 philox2x32_ks(uint32_t c0, uint32_t c1, const uint32_t* ks) {
 
 // Counter layout (DESIGN.md "RNG streams"):
 //   c0 = pixel index (24 bits) | iteration j of a rejection loop << 24
-//   c1 = sample index (24 bits) | bounce (6 bits) << 24 | stream tag << 30
+//   c1 = sample index (24 bits) | segment or bounce (6 bits) << 24 | stream tag << 30
 //   key = low 32 bits of the seed XOR its high 32 bits
-#define RT_TAG_PATH   0u   // bounce 0: x -> v jitter, y -> ray time; bounce b >= 1: the event's 64 bits
-#define RT_TAG_PIXEL  1u   // sample = bounce = 0: x -> per-pixel u jitter (cpu.rs:35-36)
-#define RT_TAG_LENS   2u   // j = 0: (x, y) -> direct lens sample; j >= 1: rejection iteration j
-#define RT_TAG_REJECT 3u   // (bounce b, iteration j): three 21-bit uniforms of a rejection iteration
+// ONE PATH block per path segment: block e of a sample belongs to segment e (e = 0 is the primary
+// ray) and is drawn before the segment is intersected, by every lane of the warp together.  Its
+// upper 24 bits per word feed the scattering event at the END of that segment (hit number e + 1);
+// the low byte of each word is spare, and in block 0 the two spare bytes are the sample's v jitter.
+#define RT_TAG_PATH   0u   // segment e: scatter bits of hit e + 1; e = 0 also: low bytes -> 16-bit v jitter (cpu.rs:39-40)
+#define RT_TAG_PIXEL  1u   // sample = segment = 0: x -> per-pixel u jitter (cpu.rs:35-36)
+#define RT_TAG_LENS   2u   // j = 0: (x, y) -> direct lens sample, low bytes -> 16-bit ray time; j >= 1: rejection iteration j
+#define RT_TAG_REJECT 3u   // (hit number b, iteration j): three 21-bit uniforms of a rejection iteration
 
 RT_HD uint32_t rt_ctr1(uint32_t sample, uint32_t bounce, uint32_t tag) { return sample | (bounce << 24) | (tag << 30); }
 
 // 24-bit and 21-bit uniforms in [0,1): exactly representable in fp32 and f64
 RT_HD float u24(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
 RT_HD float u21(uint32_t w) { return (float)w * (1.0f / 2097152.0f); }  // w < 2^21
-// three 21-bit uniforms out of 64 bits
+// three 21-bit uniforms out of 64 bits (REJECT blocks: all 64 bits belong to the iteration)
 RT_HD void u21x3(uint2 w, float& a, float& b, float& c) {
     a = u21(w.x >> 11); b = u21(w.y >> 11); c = u21(((w.x & 0x7FFu) << 10) | (w.y & 0x3FFu));
+}
+// 16-bit uniform from the spare low byte of each word of a PATH / LENS block (v jitter, ray time).
+// fp32 cannot hold more of the jitter anyway: (float)py + jitter keeps 2^-13 at py >= 1024.
+RT_HD float u16lo(uint2 w) { return (float)(((w.x & 0xFFu) << 8) | (w.y & 0xFFu)) * (1.0f / 65536.0f); }
+// three 16-bit uniforms from the upper 24 bits of each word of a PATH block (metal fuzz, direct)
+RT_HD void u16x3(uint2 w, float& a, float& b, float& c) {
+    a = (float)(w.x >> 16) * (1.0f / 65536.0f);
+    b = (float)(w.y >> 16) * (1.0f / 65536.0f);
+    c = (float)(((w.x >> 8) & 0xFFu) << 8 | ((w.y >> 8) & 0xFFu)) * (1.0f / 65536.0f);
 }

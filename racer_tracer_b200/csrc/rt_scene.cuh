@@ -7,13 +7,15 @@
 #include "rt_math.cuh"
 
 // ---------------------------------------------------------------------------
-// Layout.  A primitive is three 16-byte words (float4 / double4-as-2x):
+// Layout.  A primitive is four 16-byte words (float4 / double4-as-2x):
 //   a: sphere (cx, cy, cz, r)            rect (a0, a1, b0, b1)
 //   b: sphere (|c|^2 - r^2, -, -, -)     rect (k, -, -, -);  b.y = material
 //      parameter (fuzz / refraction index), b.z = packed kinds, b.w = texture
 //      index (non-solid) or -1
 //   c: (r, g, b) of a solid-colour texture (albedo or emission), c.w = bits of
 //      the canonical object id
+//   n: rect: the +axis unit normal (xy_rect.rs:45 etc.), so that the hit record
+//      is formed with multiply-adds instead of per-type selects;  sphere: 0
 // packed kinds (b.z bits): [0:4) prim type, [4:8) material type, [8:12)
 // texture type, [12:32) instance index + 1 (0 = none)
 // ---------------------------------------------------------------------------
@@ -35,8 +37,8 @@
 #define RT_MAX_IMAGES 8
 #define RT_T_MIN 0.001          // src/renderer.rs:58
 
-struct DevPrim {      // fp32 primitive record, 48 B
-    float4 a, b, c;
+struct DevPrim {      // fp32 primitive record, 64 B
+    float4 a, b, c, n;
 };
 
 struct DevPrimD {     // f64 geometry of the same primitive (AOV f64 instantiation)
@@ -122,10 +124,17 @@ struct KParams {
 // ---------------------------------------------------------------------------
 struct ConstScene {
     const KParams& P;
-    RT_D ConstScene(const KParams& p) : P(p) {}
-    RT_D float4 pa(int i) const { return P.cprims[i].a; }
-    RT_D float4 pb(int i) const { return P.cprims[i].b; }
-    RT_D float4 pc(int i) const { return P.cprims[i].c; }
+    const DevPrim* sh;   // the same type-sorted table staged in shared memory: per-lane (divergent) indices
+    RT_D ConstScene(const KParams& p, const DevPrim* staged) : P(p), sh(staged) {}
+    // uniform index (the intersection loops): constant-bank operands
+    RT_D float4 ua(int i) const { return P.cprims[i].a; }
+    RT_D float4 ub(int i) const { return P.cprims[i].b; }
+    // per-lane index (hit record, shading): shared memory — an indexed constant load replays
+    // once per distinct address in the warp
+    RT_D float4 pa(int i) const { return sh[i].a; }
+    RT_D float4 pb(int i) const { return sh[i].b; }
+    RT_D float4 pc(int i) const { return sh[i].c; }
+    RT_D float4 pn(int i) const { return sh[i].n; }
     RT_D float4 nlo(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }  // no BVH in the constant bank
     RT_D float4 nhi(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
     RT_D const DevInstance* instances() const { return nullptr; }            // instanced scenes never take this path
@@ -139,9 +148,12 @@ struct PtrScene {  // shared or global, decided by where the pointers point
     int ref_aabb;              // 1: cull with the reference's per-axis Aabb::hit (scenes with RotateY, Q11/Q14)
     RT_D const DevInstance* instances() const { return inst; }
     RT_D bool reference_aabb() const { return ref_aabb != 0; }
+    RT_D float4 ua(int i) const { return prims[i].a; }
+    RT_D float4 ub(int i) const { return prims[i].b; }
     RT_D float4 pa(int i) const { return prims[i].a; }
     RT_D float4 pb(int i) const { return prims[i].b; }
     RT_D float4 pc(int i) const { return prims[i].c; }
+    RT_D float4 pn(int i) const { return prims[i].n; }
     RT_D float4 nlo(int i) const { return nodes[i].lo; }
     RT_D float4 nhi(int i) const { return nodes[i].hi; }
 };
@@ -330,8 +342,8 @@ RT_D void rect_group(const Scene& S, int begin, int end, const RayT<float>& r, i
     (void)last_prim;
 #pragma unroll 2
     for (int i = begin; i < end; ++i) {
-        const float4 a = S.pa(i);
-        const float k = S.pb(i).x;
+        const float4 a = S.ua(i);
+        const float k = S.ub(i).x;
         const float t = (k - on) * in;                   // (k - o_n) / d_n; exactly 0 on the plane the ray leaves
         const float pa = fmaf(t, da, oa), pb = fmaf(t, db, ob);
         const float tc = rect_candidate(t, pa - 0.5f * (a.x + a.y), pb - 0.5f * (a.z + a.w), 0.5f * (a.y - a.x), 0.5f * (a.w - a.z));
@@ -387,8 +399,8 @@ RT_D int closest_hit_linear(const KParams& P, const Scene& S, const RayT<float>&
         const float a = dot(r.d, r.d), inv_a = fast_rcp(a);
 #pragma unroll 1
         for (int i = 0; i < n_sph; ++i) {
-            const float4 pa = S.pa(i);
-            const float t = sphere_hit<float>(r.o, r.d, a, inv_a, mk3(pa.x, pa.y, pa.z), pa.w, S.pb(i).x, i == last_prim,
+            const float4 pa = S.ua(i);
+            const float t = sphere_hit<float>(r.o, r.d, a, inv_a, mk3(pa.x, pa.y, pa.z), pa.w, S.ub(i).x, i == last_prim,
                                               (float)RT_T_MIN, best_t);
             const bool hit = t >= 0.0f;
             best_t = hit ? t : best_t;
@@ -490,13 +502,19 @@ struct Hit {
     bool front_face;
 };
 
+// Which primitive kinds a scene contains (bit RT_PRIM_*).  A scene-specialised translation unit
+// defines it; the precompiled kernels keep every kind.
+#ifndef RT_SPEC_PRIMS
+#define RT_SPEC_PRIMS 0xF
+#endif
+#define RT_HAS_SPHERES (RT_SPEC_PRIMS & 1)
+#define RT_HAS_RECTS (RT_SPEC_PRIMS & 0xE)
+
 template <class Scene>
 RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT<float>& r, float t) {
-    (void)S; (void)prim;
     Hit h;
-    int type = kinds_prim(b.z);
     h.p = r.o + t * r.d;  // Ray::at
-    if (type == RT_PRIM_SPHERE) {
+    if (RT_HAS_SPHERES && (!RT_HAS_RECTS || kinds_prim(b.z) == RT_PRIM_SPHERE)) {
         vec3f ctr = mk3(a.x, a.y, a.z);
         const float aa = dot(r.d, r.d);
         h.outward = sphere_normal(r.o, r.d, aa, fast_rcp(aa), ctr, a.w, t);  // sphere.rs:61
@@ -504,15 +522,20 @@ RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT
         h.front_face = dot(r.d, h.outward) < 0.0f;  // geometry.rs:49-56
         h.n = h.front_face ? h.outward : -h.outward;
     } else {
-        // rectangles, branch-free: +axis normal (xy_rect.rs:45 etc.), point kept on the plane
-        // (the reference's f64 ray.at(t) lands on it to 1e-13)
-        const bool xy = type == RT_PRIM_XY, xz = type == RT_PRIM_XZ, yz = type == RT_PRIM_YZ;
-        h.outward = mk3(yz ? 1.0f : 0.0f, xz ? 1.0f : 0.0f, xy ? 1.0f : 0.0f);
-        h.p.x = yz ? b.x : h.p.x; h.p.y = xz ? b.x : h.p.y; h.p.z = xy ? b.x : h.p.z;
-        const float dn = xy ? r.d.z : (xz ? r.d.y : r.d.x);
+        // rectangles, branch- and select-free: N = the +axis unit normal (xy_rect.rs:45 etc.) read
+        // from the table.  The point is put back on the plane — the reference's f64 ray.at(t)
+        // lands on it to 1e-13 — by adding (k - p.N) N: k - p.N is exact (p.N is within rounding
+        // of k) and so is the sum, so the next segment's re-test of this plane gives t = 0.
+        const float4 n4 = S.pn(prim);
+        const vec3f N = mk3(n4.x, n4.y, n4.z);
+        const float e = b.x - dot(h.p, N);
+        h.p = mk3(fmaf(e, N.x, h.p.x), fmaf(e, N.y, h.p.y), fmaf(e, N.z, h.p.z));
+        const float dn = dot(r.d, N);
         h.front_face = dn < 0.0f;   // dot(d, axis) < 0, geometry.rs:49-56
-        const float sgn = h.front_face ? 1.0f : -1.0f;
-        h.n = mk3(sgn * h.outward.x, sgn * h.outward.y, sgn * h.outward.z);
+        // +1 if dn < 0 else -1: the inverted sign bit of dn over the bits of 1.0f (one LOP3)
+        const float sgn = __int_as_float((~__float_as_int(dn) & 0x80000000) | 0x3f800000);
+        h.outward = N;
+        h.n = mk3(sgn * N.x, sgn * N.y, sgn * N.z);
     }
     h.lp = h.p;
     return h;

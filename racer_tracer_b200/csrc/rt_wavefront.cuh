@@ -158,7 +158,7 @@ wf_generate(const __grid_constant__ KParams P, WfPool W, float* __restrict__ acc
         pc.dir0 = P.cam.upper_left_corner + W.pixel_u[info.x] * P.cam.horizontal;
         const uint32_t sample = info.y;
         float vjit = 0.5f;
-        if (!P.fixed_jitter) vjit = u24(philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(sample, 0u, RT_TAG_PATH), P.ks).x);
+        if (!P.fixed_jitter) vjit = u16lo(philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(sample, 0u, RT_TAG_PATH), P.ks));
         vec3f o, d;
         camera_ray<SAMPLER, ROUNDS>(P, pc, sample, vjit, o, d);
         info.y = sample + 1u;
@@ -201,7 +201,7 @@ wf_intersect(const __grid_constant__ KParams P, WfPool W) {
         float t;
         int prim;
         float packed;
-        if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P); prim = closest_hit<MODE>(P, S, r, last_prim, t); packed = prim >= 0 ? S.pb(prim).z : 0.f; }
+        if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, L.prims); prim = closest_hit<MODE>(P, S, r, last_prim, t); packed = prim >= 0 ? S.pb(prim).z : 0.f; }
         else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t); packed = prim >= 0 ? S.pb(prim).z : 0.f; }
         if (prim < 0) {  // renderer.rs:78-88
             vec3f bg = background_color(P, r.d);
@@ -245,7 +245,8 @@ RT_D void wf_shade_one(const KParams& P, const WfPool& W, const TexCtx& X, const
     const int prim = __float_as_int(dp.w);
     uint32_t bounce = (info.w & 0xffu) + 1u, depth_left = (info.w >> 8) & 0xffu;
     RngCtx R; R.ks = P.ks; R.pixel = info.x; R.sample = info.y - 1u;
-    const uint2 rnd = philox2x32_ks<ROUNDS>(R.pixel, rt_ctr1(R.sample, bounce, RT_TAG_PATH), P.ks);
+    // the block of the segment that ended in this hit (hit number `bounce` closes segment bounce - 1)
+    const uint2 rnd = philox2x32_ks<ROUNDS>(R.pixel, rt_ctr1(R.sample, bounce - 1u, RT_TAG_PATH), P.ks);
     vec3f X_end;
     bool alive = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, ot.w, bounce, rnd, o, d, T, X_end);
     if (alive) {
@@ -276,7 +277,7 @@ wf_shade(const __grid_constant__ KParams P, WfPool W) {
     const int cls = q < n0 ? 0 : (q < n1 ? 1 : 2);
     const int i = cls == 0 ? W.queue[0][q] : (cls == 1 ? W.queue[1][q - n0] : W.queue[2][q - n1]);
     if (MODE == RT_MODE_CONST_LINEAR) {
-        ConstScene S(P);
+        ConstScene S(P, L.prims);
         if (cls == 2) wf_shade_one<SAMPLER, ROUNDS, true>(P, W, X, S, i); else wf_shade_one<SAMPLER, ROUNDS, false>(P, W, X, S, i);
     } else {
         PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb;

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Compiles the scene-specialised megakernel source (rc_spec_source) with nvcc for sm_100a — no GPU
+needed — and prints registers, the static SASS opcode mix of the main loop and, with --dump, the SASS.
+
+    python tools/spec_sass.py cornell_box [--dump out.sass] [-D RT_REGEN_MIN=8]
+"""
+import argparse
+import collections
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from racer_tracer_b200 import capi, harness  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("scene")
+ap.add_argument("--dump")
+ap.add_argument("-D", action="append", default=[])
+args = ap.parse_args()
+
+lib = capi.load()
+cfg = harness.load_config(os.path.join(ROOT, "tests", "golden", "config.yml"))
+job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", args.scene + ".yml"), cfg, 64, 64)
+n = lib.rc_spec_source(job.scene.ptr, None, 0)
+buf = C.create_string_buffer(n + 1)
+lib.rc_spec_source(job.scene.ptr, buf, n + 1)
+src = buf.value.decode()
+tmp = tempfile.mkdtemp()
+cu = os.path.join(tmp, "spec.cu")
+open(cu, "w").write(src)
+cubin = os.path.join(tmp, "spec.cubin")
+cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-lineinfo", "-Xptxas", "-v",
+       "-I", os.path.join(ROOT, "racer_tracer_b200", "csrc"), "-cubin", "-o", cubin, cu] + ["-D" + d for d in args.D]
+r = subprocess.run(cmd, capture_output=True, text=True)
+if r.returncode:
+    print(r.stderr)
+    sys.exit(1)
+print("\n".join(l for l in r.stderr.splitlines() if "registers" in l or "spill" in l))
+sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", cubin], capture_output=True, text=True).stdout
+lines = [l for l in sass.splitlines() if re.match(r"\s+/\*[0-9a-f]{4}\*/", l)]
+ops = []
+for l in lines:
+    m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(@!?U?P\d\s+)?([A-Z0-9_.]+)", l)
+    if m:
+        ops.append((int(m.group(1), 16), m.group(3), l))
+print(f"{len(ops)} static instructions")
+mix = collections.Counter(o[1].split(".")[0] for o in ops)
+print(", ".join(f"{k} {v}" for k, v in mix.most_common(24)))
+if args.dump:
+    open(args.dump, "w").write("\n".join(o[2] for o in ops))
+    print("SASS ->", args.dump)
