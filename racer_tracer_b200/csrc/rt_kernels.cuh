@@ -158,7 +158,7 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
     if (RT_HAS_MAT(RT_MAT_LAMBERTIAN) && (mat == RT_MAT_LAMBERTIAN || !(RT_HAS_MAT(RT_MAT_METAL) || RT_HAS_MAT(RT_MAT_DIELECTRIC)))) {  // lambertian.rs:25-39
         vec3f rv;
         if (SAMPLER == 1) rv = unit_vector(reject_in_unit_sphere<ROUNDS>(R, bounce));
-        else rv = sphere_direct(u24(rnd.x), u24(rnd.y));
+        else rv = sphere_direct_w(rnd.x, rnd.y);
         nd = h.n + rv;
         // near_zero, vec3.rs:127-130: all three components below 1e-8 (rv = -n; one draw in 2^24)
         if (fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z)) < 1e-8f) nd = h.n;
@@ -254,8 +254,8 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     vec3f sum = mk3(0.0f, 0.0f, 0.0f);
     vec3f o = mk3(0.0f, 0.0f, 0.0f), d = o, T = o;
     int s = valid ? s_first : s_last;
-    bool alive = false;
-    int depth_left = 0, last_prim = -1;
+    int depth_left = 0;        // > 0: this lane is on a path that may still trace that many segments; 0: no path
+    int last_prim = -1;
     uint32_t seg = 0;          // index of the segment about to be traced (0 = primary ray)
     unsigned nseg = 0;
     if (P.max_depth <= 0) {    // renderer.rs:48-56: depth 0 is white, for every sample
@@ -267,22 +267,21 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
 #pragma unroll 1
     while (true) {
         // ---- lanes whose path ended take the next sample of their pixel (bookkeeping only) ----
-        bool fresh = !alive && s < s_last;
+        bool fresh = depth_left == 0 && s < s_last;
         if (RT_REGEN_MIN > 1) {
-            const unsigned want = __ballot_sync(0xffffffffu, fresh), live = __ballot_sync(0xffffffffu, alive);
+            const unsigned want = __ballot_sync(0xffffffffu, fresh), live = __ballot_sync(0xffffffffu, depth_left != 0);
             if ((want | live) == 0u) break;
             if (live != 0u && __popc(want) < RT_REGEN_MIN) fresh = false;
         } else {
-            if (!__any_sync(0xffffffffu, fresh || alive)) break;
+            if (!__any_sync(0xffffffffu, (depth_left != 0) | (s < s_last))) break;
         }
         if (fresh) {
             R.sample = (uint32_t)s++;
             seg = 0; last_prim = -1;
             T = mk3(1.0f, 1.0f, 1.0f);
             depth_left = P.max_depth;
-            alive = true;
         }
-        if (alive) {
+        if (depth_left != 0) {
             // ---- the segment's random block: drawn here, by all lanes together ----
             const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, seg, RT_TAG_PATH), P.ks);
             if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337
@@ -297,7 +296,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             ++nseg;
             if (prim < 0) {  // renderer.rs:78-88
                 if (!RT_SPEC_BG_BLACK) sum = sum + T * background_color(P, d);
-                alive = false;
+                depth_left = 0;
             } else {
                 ++seg;   // hit number along the path (1 = primary hit)
                 vec3f X_end;   // radiance that ends the path
@@ -306,10 +305,10 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                 else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
                 if (!cont) {                 // absorbed (X_end = 0) or a light (X_end = emission)
                     sum = sum + T * X_end;
-                    alive = false;
+                    depth_left = 0;
                 } else {
                     last_prim = prim;
-                    if (--depth_left == 0) { sum = sum + T; alive = false; }  // white at depth 0
+                    if (--depth_left == 0) sum = sum + T;   // white at depth 0, renderer.rs:48-56
                 }
             }
         }

@@ -697,6 +697,15 @@ RT_D vec3f sphere_direct(float u1, float u2) {
     return mk3(r * c, r * s, z);
 }
 
+// sphere_direct(u24(wx), u24(wy)) with the integer -> uniform scalings folded into the
+// multiply-adds (same values: u24 is exact in fp32 and the scale factors are powers of two)
+RT_D vec3f sphere_direct_w(uint32_t wx, uint32_t wy) {
+    const float z = fmaf((float)(wx >> 8), -1.0f / 8388608.0f, 1.0f);                 // 1 - 2 u1
+    const float r = fast_sqrt(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
+    const float phi = fmaf((float)(wy >> 8), 6.283185307179586f / 16777216.0f, -3.14159265358979323846f);
+    return mk3(-r * __cosf(phi), -r * __sinf(phi), z);
+}
+
 template <int ROUNDS>
 RT_D vec3f reject_in_unit_sphere(const RngCtx& R, uint32_t bounce) {  // vec3.rs:424-430
     for (uint32_t j = 0;; ++j) {
