@@ -268,6 +268,19 @@ int rc_set_camera(rc_ctx* ctx, const rc_camera* camera);
 int rc_render(rc_ctx* ctx, const rc_params* params, double* out_rgb,
               const volatile int32_t* cancel);
 
+/* The whole of CpuRendererScaled::render (src/renderer/cpu_scaled.rs:37-121), the preview renderer
+ * (`preview_renderer`, src/config.rs:203-207, used while the camera moves, src/main.rs:174-190).
+ * params->width/height are the screen; params->samples / max_depth come from config.preview
+ * (src/config.rs:75-82).  One colour is traced per scale_w x scale_h block of screen pixels — u from
+ * the block's left column with one jitter per block, v from its top row with one jitter per sample
+ * (cpu_scaled.rs:55-60) — and, after scale_sqrt, fills the block (cpu_scaled.rs:75-86).  scale_w and
+ * scale_h are what CpuRendererScaled::new derives (cpu_scaled.rs:31-34: the highest divisor of
+ * image.width / num_threads_width not above config.preview.scale); columns / rows beyond the last
+ * whole block stay 0 as in the reference.  out_rgb: width*height*3 doubles.  Cancel semantics as
+ * rc_render. */
+int rc_render_preview(rc_ctx* ctx, const rc_params* params, int32_t scale_w, int32_t scale_h,
+                      double* out_rgb, const volatile int32_t* cancel);
+
 /* Device-resident form for callers that own device memory (bench, multi-
  * process jobs): traces this participant's share (params->rank/world) and
  * ADDS linear radiance sums into d_accum (width*height*3 floats on device 0;

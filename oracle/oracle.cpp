@@ -818,6 +818,54 @@ int oracle_render(const rc_scene* scene, const rc_camera* camera, const rc_param
     return RC_OK;
 }
 
+int oracle_render_preview(const rc_scene* scene, const rc_camera* camera, const rc_params* params,
+                          const oracle_options* opt_in, int32_t scale_w, int32_t scale_h, double* out_rgb) {
+    int st = check(scene, camera, params);
+    if (st != RC_OK || !out_rgb || scale_w < 1 || scale_h < 1) return RC_ERR_INVALID;
+    oracle_options opt;
+    std::memset(&opt, 0, sizeof(opt));
+    if (opt_in) opt = *opt_in;
+    if (opt.tiles_w <= 0) opt.tiles_w = 10;
+    if (opt.tiles_h <= 0) opt.tiles_h = 10;
+    const int rounds = params->rng_rounds > 0 ? params->rng_rounds : 10;
+    const int W = params->width, H = params->height;
+    const int grid_w = W / scale_w;   // block grid of the whole screen (Philox pixel index)
+    std::memset(out_rgb, 0, sizeof(double) * 3 * (size_t)W * H);   // vec![Vec3::default(); ..], cpu_scaled.rs:53
+    std::vector<Tile> tiles = prepare_tiles(W, H, opt.tiles_w, opt.tiles_h);
+    Counters cnt;
+    for (size_t ti = 0; ti < tiles.size(); ++ti) {
+        const Tile& tile = tiles[ti];
+        Xoshiro seq;
+        seq.seed(params->seed * 0x9E3779B97F4A7C15ull + ti + 1);
+        const int scaled_width = tile.w / scale_w, scaled_height = tile.h / scale_h;   // cpu_scaled.rs:51-52
+        for (int row = 0; row < scaled_height; ++row)
+            for (int column = 0; column < scaled_width; ++column) {
+                const int x = tile.x + column * scale_w, y = tile.y + row * scale_h;
+                Draws dr;
+                dr.backend = opt.rng;
+                dr.key = (uint32_t)params->seed ^ (uint32_t)(params->seed >> 32);
+                dr.rounds = rounds;
+                dr.pixel = (uint32_t)((y / scale_h) * grid_w + x / scale_w);
+                dr.sample = 0;
+                dr.seq = &seq;
+                const double u = pixel_u(*params, dr, x);   // once per block, cpu_scaled.rs:55-56
+                V3 color = v3(0, 0, 0);
+                for (int s = 0; s < params->samples; ++s) {
+                    dr.sample = (uint32_t)s;
+                    color = color + trace_sample(*scene, *camera, *params, dr, u, x, y, cnt).rgb;   // v: cpu_scaled.rs:59-60
+                }
+                const double scale = 1.0 / (double)params->samples;   // scale_sqrt, cpu_scaled.rs:75
+                const V3 c = v3(std::sqrt(scale * color.x), std::sqrt(scale * color.y), std::sqrt(scale * color.z));
+                for (int sh = 0; sh < scale_h; ++sh)
+                    for (int sw = 0; sw < scale_w; ++sw) {
+                        double* o = out_rgb + 3 * ((size_t)(y + sh) * W + (x + sw));
+                        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+                    }
+            }
+    }
+    return RC_OK;
+}
+
 int oracle_primary_aov(const rc_scene* scene, const rc_camera* camera, const rc_params* params,
                        uint32_t* id, double* t, double* normal, double* point) {
     int st = check(scene, camera, params);

@@ -62,6 +62,13 @@ typedef struct oracle_options {
 int oracle_render(const rc_scene* scene, const rc_camera* camera, const rc_params* params,
                   const oracle_options* opt, double* out_rgb, oracle_counters* counters);
 
+/* CpuRendererScaled::render for one image (src/renderer/cpu_scaled.rs:37-121): params->width/height =
+ * screen, params->samples/max_depth = config.preview; one colour per scale_w x scale_h block, upscaled;
+ * pixels beyond a tile's last whole block stay 0.  Philox streams are keyed by the block's index in the
+ * (width / scale_w)-wide block grid. */
+int oracle_render_preview(const rc_scene* scene, const rc_camera* camera, const rc_params* params,
+                          const oracle_options* opt, int32_t scale_w, int32_t scale_h, double* out_rgb);
+
 /* Primary-visibility AOV with the fixed jitter (pixel centre, lens centre):
  * RayImageData of src/renderer.rs:33-39,58-88. */
 int oracle_primary_aov(const rc_scene* scene, const rc_camera* camera, const rc_params* params,

@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
         L = C.CDLL(LIB_PATH)
         L.oracle_render.argtypes = [C.POINTER(rc_scene), C.POINTER(rc_camera), C.POINTER(rc_params),
                                     C.POINTER(oracle_options), _pd, C.POINTER(oracle_counters)]
+        L.oracle_render_preview.argtypes = [C.POINTER(rc_scene), C.POINTER(rc_camera), C.POINTER(rc_params),
+                                            C.POINTER(oracle_options), C.c_int32, C.c_int32, _pd]
         L.oracle_primary_aov.argtypes = [C.POINTER(rc_scene), C.POINTER(rc_camera), C.POINTER(rc_params),
                                          C.POINTER(C.c_uint32), _pd, _pd, _pd]
         L.oracle_sample_radiance.argtypes = [C.POINTER(rc_scene), C.POINTER(rc_camera), C.POINTER(rc_params),
@@ -122,6 +124,17 @@ def render(job, params: rc_params, rng=RNG_PHILOX, threads=0, tiles=(10, 10), sa
     if st != 0:
         raise RuntimeError(f"oracle_render failed: {st}")
     return (out, cnt) if want_counters else out
+
+
+def render_preview(job, params: rc_params, scale_w: int, scale_h: int, rng=RNG_PHILOX, tiles=(10, 10)):
+    """oracle_render_preview (CpuRendererScaled, cpu_scaled.rs); returns (H,W,3) float64."""
+    opt = oracle_options(rng, 1, tiles[0], tiles[1], 0, 0, 0, 0)
+    out = np.empty((params.height, params.width, 3), dtype=np.float64)
+    st = lib().oracle_render_preview(job.scene.ptr, C.byref(job.camera), C.byref(params), C.byref(opt),
+                                     scale_w, scale_h, out.ctypes.data_as(_pd))
+    if st != 0:
+        raise RuntimeError(f"oracle_render_preview failed: {st}")
+    return out
 
 
 def primary_aov(job, params: rc_params):

@@ -94,6 +94,7 @@ struct rc_ctx {
     KParams kp;             // scene part filled at upload (device pointers of device 0 patched per launch)
     AovParamsD aov;
     int mode = RT_MODE_CONST_LINEAR;
+    int preview_sw = 0, preview_sh = 0, preview_w = 0, preview_h = 0;   // set for the duration of rc_render_preview
     size_t smem_bytes = 0;
     bool has_scene = false, has_camera = false;
     bool has_textures = false;   // any primitive whose texture is not a solid colour
@@ -268,6 +269,8 @@ void partition(KParams& kp, const rc_params* p, int part, int parts) {
     kp.key = (uint32_t)p->seed ^ (uint32_t)(p->seed >> 32);
     for (int r = 0; r < 10; ++r) kp.ks[r] = kp.key + (uint32_t)r * PHILOX2_W;
     kp.inv_wm1 = 1.0f / (float)(p->width - 1); kp.inv_hm1 = 1.0f / (float)(p->height - 1);
+    kp.wm1 = (float)(p->width - 1);
+    kp.px_scale_x = kp.px_scale_y = 1;
     kp.tile_w = RT_TILE_W; kp.tile_h = RT_TILE_H;
     kp.slices = 1; kp.slice_buf = nullptr;
     kp.tiles_x = (p->width + RT_TILE_W - 1) / RT_TILE_W;
@@ -316,6 +319,11 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         for (size_t i = 0; i < d.tex.size(); ++i) kp.images[i] = d.tex[i];
         kp.segment_counter = d.counter.p;
         partition(kp, p, p->rank * n_dev + k, parts);
+        if (ctx->preview_sw > 0) {   // scaled preview: p->width/height is the block grid, u and v refer to the screen
+            kp.px_scale_x = ctx->preview_sw; kp.px_scale_y = ctx->preview_sh;
+            kp.wm1 = (float)(ctx->preview_w - 1);
+            kp.inv_wm1 = 1.0f / (float)(ctx->preview_w - 1); kp.inv_hm1 = 1.0f / (float)(ctx->preview_h - 1);
+        }
         float* accum = (k == 0) ? accum0 : d.accum.p;
         if (kp.n_tiles == 0 || kp.s_end <= kp.s_begin) continue;
         if (p->variant == RC_VARIANT_WAVEFRONT) {
@@ -817,6 +825,54 @@ int rc_render(rc_ctx* ctx, const rc_params* p, double* out_rgb, const volatile i
     rc = finish_stats(ctx, p);
     if (rc != RC_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_rgb, d0.out64.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(cudaStreamSynchronize(d0.stream));
+    return RC_OK;
+}
+
+int rc_render_preview(rc_ctx* ctx, const rc_params* p, int32_t scale_w, int32_t scale_h, double* out_rgb,
+                      const volatile int32_t* cancel) {
+    if (!ctx || !out_rgb) return fail(RC_ERR_INVALID, "ctx or out_rgb is NULL");
+    int rc = check_params(p);
+    if (rc != RC_OK) return rc;
+    if (scale_w < 1 || scale_h < 1) return fail(RC_ERR_INVALID, "scale_w and scale_h must be >= 1");
+    if (!ctx->has_scene || !ctx->has_camera) return fail(RC_ERR_STATE, "upload a scene and set a camera first");
+    if (cancelled(cancel)) return fail(RC_ERR_CANCELLED, "cancel flag set before the render started");
+    // the grid of scaled blocks: image.width / scale_width per tile (cpu_scaled.rs:51-52); tiles start at
+    // multiples of the scale, so over the whole screen that is width / scale_w whole blocks
+    rc_params q = *p;
+    q.width = p->width / scale_w; q.height = p->height / scale_h;
+    DeviceState& d0 = ctx->devs[0];
+    const size_t n_out = (size_t)p->width * p->height;
+    CUDA_TRY(cudaSetDevice(d0.device));
+    CUDA_TRY(d0.out64.resize(n_out * 3));
+    if (q.width < 1 || q.height < 1) {   // no whole block fits: the reference's buffer stays zero
+        std::memset(out_rgb, 0, n_out * 3 * sizeof(double));
+        return RC_OK;
+    }
+    // single traced row/column: check_params wants >= 2 only because u divides by W-1, which is the screen's here
+    rc = ensure_accum(ctx, &q, true);
+    if (rc != RC_OK) return rc;
+    ctx->preview_sw = scale_w; ctx->preview_sh = scale_h; ctx->preview_w = p->width; ctx->preview_h = p->height;
+    bool was_cancelled = false;
+    rc = trace_share(ctx, &q, d0.accum.p, cancel, was_cancelled);
+    ctx->preview_sw = ctx->preview_sh = ctx->preview_w = ctx->preview_h = 0;
+    if (rc != RC_OK) return rc;
+    if (was_cancelled) return RC_OK;
+    if (ctx->devs.size() > 1) {
+        rc = multi_gather(ctx->multi, q.split, (size_t)q.width * q.height * 3, d0.accum.p,
+                          [&](size_t k) { return ctx->devs[k].accum.p; },
+                          [&](size_t k) { return ctx->devs[k].stream; },
+                          [&](size_t k) { return ctx->devs[k].device; });
+        if (rc != RC_OK) return fail(rc, std::string("multi-device gather failed: ") + multi_error(ctx->multi));
+    }
+    CUDA_TRY(cudaSetDevice(d0.device));
+    preview_expand_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, d0.stream>>>(
+        d0.accum.p, d0.out64.p, p->width, p->height, q.width, q.height, scale_w, scale_h, 1.0 / (double)p->samples);
+    CUDA_TRY(cudaGetLastError());
+    rc = finish_stats(ctx, &q);
+    if (rc != RC_OK) return rc;
+    ctx->stats.kernel_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, d0.out64.p, n_out * 3 * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
     CUDA_TRY(cudaStreamSynchronize(d0.stream));
     return RC_OK;
 }

@@ -100,7 +100,7 @@ RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
     c.pixel = (uint32_t)(py * P.width + px);
     float ujit = 0.5f;
     if (!P.fixed_jitter) ujit = u24(philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.ks).x);
-    float u = ((float)px + ujit) / (float)(P.width - 1);  // once per pixel, cpu.rs:35-36
+    float u = ((float)(px * P.px_scale_x) + ujit) / P.wm1;  // once per pixel, cpu.rs:35-36 (cpu_scaled.rs:55-56)
     // cam.upper_left_corner holds (upper_left_corner - origin), formed in f64 on the host
     c.dir0 = P.cam.upper_left_corner + u * P.cam.horizontal;
     return c;
@@ -109,7 +109,7 @@ RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
 // Primary ray of one sample.  `w` = the sample's start block (x -> v jitter).
 template <int SAMPLER, int ROUNDS>
 RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit, vec3f& o, vec3f& d) {
-    float v = ((float)c.py + vjit) * P.inv_hm1;  // cpu.rs:39-40
+    float v = ((float)(c.py * P.px_scale_y) + vjit) * P.inv_hm1;  // cpu.rs:39-40 (cpu_scaled.rs:59-60)
     d = c.dir0 - v * P.cam.vertical;
     o = P.cam.origin;
     if (P.lens_enabled && !P.fixed_jitter) {  // camera.rs:327-328; skipped when lens_radius == 0 (offset = 0)
@@ -566,6 +566,23 @@ __global__ void primary_aov_kernel_f64(const __grid_constant__ AovParamsD P, uin
 __global__ void finalize_kernel(const float* __restrict__ accum, float* __restrict__ rgb, size_t n, float scale) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) rgb[i] = sqrtf(scale * accum[i]);
+}
+
+// CpuRendererScaled's upscale (cpu_scaled.rs:75-86): every traced block colour, after scale_sqrt,
+// fills its scale_w x scale_h screen pixels; screen pixels beyond the last whole block stay 0
+// (the reference's buffer starts as Vec3::default()).
+__global__ void preview_expand_kernel(const float* __restrict__ accum, double* __restrict__ rgb, int width, int height,
+                                      int bw, int bh, int scale_w, int scale_h, double scale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)width * height) return;
+    const int x = (int)(i % width), y = (int)(i / width);
+    const int bx = x / scale_w, by = y / scale_h;
+    double r = 0.0, g = 0.0, b = 0.0;
+    if (bx < bw && by < bh) {
+        const float* a = accum + 3 * ((size_t)by * bw + bx);
+        r = sqrt(scale * (double)a[0]); g = sqrt(scale * (double)a[1]); b = sqrt(scale * (double)a[2]);
+    }
+    rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
 }
 
 __global__ void finalize_to_f64_kernel(const float* __restrict__ accum, double* __restrict__ rgb, size_t n, double scale) {

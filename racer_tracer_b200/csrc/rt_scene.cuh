@@ -82,8 +82,11 @@ struct DevCamera {    // CameraSharedData, src/camera.rs:57-72 (the fields get_r
 struct KParams {
     DevCamera<float> cam;
     float4 bg_a, bg_b;          // background colours; bg_a.w = bits(bg type)
-    int width, height;
-    float inv_wm1, inv_hm1;     // 1/(W-1), 1/(H-1) (cpu.rs:35-40 divide by W-1 and H-1)
+    int width, height;          // the grid of traced pixels (preview: the grid of scaled blocks)
+    float inv_wm1, inv_hm1;     // 1/(W-1), 1/(H-1) of the SCREEN (cpu.rs:35-40 divide by W-1 and H-1)
+    float wm1;                  // (float)(screen width - 1)
+    int px_scale_x, px_scale_y; // screen pixels per traced pixel: 1 for a full render; the preview renderer's
+                                // scale_width / scale_height (cpu_scaled.rs:31-34) otherwise
     int s_begin, s_end;         // sample range traced by this launch
     int max_depth;
     int fixed_jitter;

@@ -92,7 +92,7 @@ __global__ void wf_pixel_u_kernel(const __grid_constant__ KParams P, float* __re
     uint32_t pixel = (uint32_t)(py * P.width + px);
     float ujit = 0.5f;
     if (!P.fixed_jitter) ujit = u24(philox2x32_ks<ROUNDS>(pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.ks).x);
-    pixel_u[pixel] = ((float)px + ujit) / (float)(P.width - 1);
+    pixel_u[pixel] = ((float)(px * P.px_scale_x) + ujit) / P.wm1;
 }
 
 __global__ void wf_reset_kernel(WfPool W) {

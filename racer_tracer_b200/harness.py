@@ -615,6 +615,18 @@ def make_params(width, height, samples, max_depth, seed=0, variant=capi.RC_VARIA
     return p
 
 
+def preview_scales(cfg: "Config", width: int, height: int) -> tuple[int, int]:
+    """CpuRendererScaled::new (src/renderer/cpu_scaled.rs:17-43): the highest divisor of
+    image.width / num_threads_width (height likewise) that does not exceed config.preview.scale."""
+    def highest_divisible(value: int, div: int) -> int:
+        while value % div != 0:
+            div -= 1
+        return div
+    pv = cfg.preview
+    return (highest_divisible(width // max(1, pv.num_threads_width), max(1, pv.scale)),
+            highest_divisible(height // max(1, pv.num_threads_height), max(1, pv.scale)))
+
+
 def partition(params: rc_params, part: int, parts: int) -> dict:
     """rc_partition: the share of participant `part` of `parts` (host arithmetic only)."""
     lib = capi.load()
@@ -698,6 +710,14 @@ class CudaRenderer:
         cptr = C.cast(C.pointer(cancel), C.POINTER(C.c_int32)) if cancel is not None else None
         capi.check(self.lib, self.lib.rc_render(self.ctx, C.byref(params),
                                                 out.ctypes.data_as(C.POINTER(C.c_double)), cptr))
+        return out
+
+    def render_preview(self, params: rc_params, scale_w: int, scale_h: int, cancel=None) -> np.ndarray:
+        """rc_render_preview: what CpuRendererScaled sends (cpu_scaled.rs); params = screen size + config.preview."""
+        out = np.empty((params.height, params.width, 3), dtype=np.float64)
+        cptr = C.cast(C.pointer(cancel), C.POINTER(C.c_int32)) if cancel is not None else None
+        capi.check(self.lib, self.lib.rc_render_preview(self.ctx, C.byref(params), scale_w, scale_h,
+                                                        out.ctypes.data_as(C.POINTER(C.c_double)), cptr))
         return out
 
     def render_accumulate(self, params: rc_params, d_accum_ptr: int):

@@ -366,3 +366,36 @@ def test_scene_specialised_kernel_matches_the_generic_one(renderer, cfg):
     t0 = time.perf_counter()
     renderer.render(harness.make_params(w, h, 1, 20, seed=6, specialize=1))
     assert time.perf_counter() - t0 < 0.5
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell_box", 600, 600), ("three_balls", 610, 330)])
+def test_preview_renderer_matches_oracle(renderer, oracle, cfg, name, w, h):
+    """rc_render_preview = CpuRendererScaled (src/renderer/cpu_scaled.rs): one colour per scale x scale
+    block from config.preview's samples / depth, upscaled; same Philox streams as the oracle's restatement.
+    610x330: the last tile column has a remainder, whose pixels beyond the last whole block stay 0."""
+    job = job_for(name, cfg, w, h)
+    renderer.upload(job)
+    sw, sh = harness.preview_scales(cfg, w, h)
+    assert (sw, sh) == ((4, 4) if w == 600 else (1, 3))     # 60 % 4 == 0; 61 is prime, 33 -> 3
+    p = harness.make_params(w, h, cfg.preview.samples, cfg.preview.max_depth, seed=2)
+    img = renderer.render_preview(p, sw, sh)
+    ref = oracle.render_preview(job, p, sw, sh)
+    assert img.shape == (h, w, 3) and np.isfinite(img).all()
+    # constant over every block
+    bw, bh = w // sw, h // sh
+    blocks = img[:bh * sh, :bw * sw].reshape(bh, sh, bw, sw, 3)
+    assert np.array_equal(blocks, np.broadcast_to(blocks[:, :1, :, :1], blocks.shape))
+    # beyond the last whole block: zero, on both sides
+    assert not img[bh * sh:].any() and not img[:, bw * sw:].any()
+    assert not ref[bh * sh:].any() and not ref[:, bw * sw:].any()
+    err = np.abs(img - ref).max(axis=2)
+    assert float((err > 2e-3).mean()) < 0.03 and np.median(err) < 1e-5
+    st = renderer.stats()
+    assert st.samples == bw * bh * cfg.preview.samples
+    # scale 1 == the full renderer's pixels (same u/v, same streams)
+    q = harness.make_params(64, 48, 8, 10, seed=2)
+    small = job_for(name, cfg, 64, 48)
+    renderer.upload(small)
+    assert np.allclose(renderer.render_preview(q, 1, 1), renderer.render(q), rtol=1e-6, atol=1e-7)
+    with pytest.raises(capi.RacerCudaError):
+        renderer.render_preview(q, 0, 1)

@@ -463,3 +463,22 @@ def test_bvh_and_linear_list_give_the_same_image(oracle, cfg, name):
     ia, ib = oracle.render(a, p), oracle.render(b, p)
     assert np.array_equal(ia, ib)
     assert np.array_equal(oracle.primary_aov(a, p)[0], oracle.primary_aov(b, p)[0])
+
+
+def test_preview_renderer_semantics(cfg):
+    """CpuRendererScaled (src/renderer/cpu_scaled.rs): scale derivation (:17-43), one colour per block
+    (:75-86), remainder pixels of a tile left at Vec3::default() (:53), scale 1 == the full renderer."""
+    from oracle import oracle as O
+    assert harness.preview_scales(cfg, 600, 600) == (4, 4)
+    assert harness.preview_scales(cfg, 610, 330) == (1, 3)
+    assert harness.preview_scales(cfg, 1920, 1080) == (4, 4)
+    w, h = 50, 35
+    job = harness.prepare_job(scene_path("three_balls"), cfg, w, h)
+    p = harness.make_params(w, h, 4, 5, seed=1)
+    # 5x5 tiles of 10x7 pixels, 3x3 blocks: 3 whole blocks per tile row (9 of 10 columns), 2 per column (6 of 7 rows)
+    img = O.render_preview(job, p, 3, 3, tiles=(5, 5))
+    tile = img[:7, :10]
+    assert tile[:6, :9].any() and not tile[6:].any() and not tile[:, 9:].any()
+    assert np.array_equal(tile[0:3, 0:3], np.broadcast_to(tile[0, 0], (3, 3, 3)))
+    one = O.render_preview(job, p, 1, 1, tiles=(5, 5))
+    assert np.allclose(one, O.render(job, p, tiles=(5, 5)), rtol=0, atol=1e-12)
