@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RC_ABI_VERSION 1
+#define RC_ABI_VERSION 2
 
 /* ---- status ------------------------------------------------------------ */
 typedef enum rc_status {
@@ -51,7 +51,12 @@ typedef enum rc_status {
 /* ---- primitives (SoA) -------------------------------------------------- */
 /* src/geometry/sphere.rs:31-68, xy_rect.rs:21-48, xz_rect.rs:21-49,
  * yz_rect.rs:21-49 */
-enum { RC_PRIM_SPHERE = 0, RC_PRIM_XY_RECT = 1, RC_PRIM_XZ_RECT = 2, RC_PRIM_YZ_RECT = 3 };
+enum { RC_PRIM_SPHERE = 0, RC_PRIM_XY_RECT = 1, RC_PRIM_XZ_RECT = 2, RC_PRIM_YZ_RECT = 3,
+       /* src/geometry/moving_sphere.rs:19-100: a sphere whose centre moves linearly from
+        * pos (ray time time_a) to pos_b (ray time time_b); prim_data = pos, radius and
+        * prim_motion = pos_b, time_a, time_b.  Only the Random loader creates it
+        * (src/scene/random.rs:53-56). */
+       RC_PRIM_MOVING_SPHERE = 4 };
 
 /* src/material/lambertian.rs, metal.rs, dialectric.rs, diffuse_light.rs */
 enum { RC_MAT_LAMBERTIAN = 0, RC_MAT_METAL = 1, RC_MAT_DIELECTRIC = 2, RC_MAT_DIFFUSE_LIGHT = 3 };
@@ -153,6 +158,10 @@ typedef struct rc_scene {
     int32_t reserved;
     double  bg_a[3];      /* sky: top; solid: colour                        */
     double  bg_b[3];      /* sky: bottom                                    */
+    /* ABI 2 */
+    const double* prim_motion;  /* 5 per prim (pos_b xyz, time_a, time_b), read
+                                   for RC_PRIM_MOVING_SPHERE only; may be NULL
+                                   when the scene has no moving sphere       */
 } rc_scene;
 
 /* The 14 fields of CameraSharedData, src/camera.rs:57-72. */

@@ -267,13 +267,19 @@ bool prim_hit_local(const rc_scene& sc, int i, const Ray& ray, double t_min, dou
                     HitRecord& rec, Counters& cnt) {
     const double* d = sc.prim_data + 5 * (size_t)i;
     int type = sc.prim_type[i];
+    const bool moving = type == RC_PRIM_MOVING_SPHERE;
+    if (moving) type = RC_PRIM_SPHERE;   // counted with the spheres
     cnt.c.prim_tests[type]++;
     rec.material = sc.prim_material[i];
     rec.obj_id = sc.prim_id[i];
     rec.prim = i;
     if (type == RC_PRIM_SPHERE) {
-        // src/geometry/sphere.rs:31-68
+        // src/geometry/sphere.rs:31-68; moving_sphere.rs:42-88 is the same body around pos(time)
         V3 center = v3(d[0], d[1], d[2]);
+        if (moving) {   // MovingSphere::pos, moving_sphere.rs:37-39
+            const double* m = sc.prim_motion + 5 * (size_t)i;
+            center = center + ((ray.time - m[3]) / (m[4] - m[3])) * (v3(m[0], m[1], m[2]) - center);
+        }
         double radius = d[3];
         V3 oc = ray.origin - center;
         double a = length_squared(ray.direction);
@@ -290,7 +296,8 @@ bool prim_hit_local(const rc_scene& sc, int i, const Ray& ray, double t_min, dou
         rec.t = root;
         rec.point = ray.at(root);
         V3 outward_normal = (rec.point - center) / radius;
-        sphere_uv(outward_normal, rec.u, rec.v);
+        // sphere.rs:62 takes uv from the outward normal; moving_sphere.rs:76 from the POINT (quirk, Q27)
+        sphere_uv(moving ? rec.point : outward_normal, rec.u, rec.v);
         set_face_normal(rec, ray, outward_normal);
         cnt.c.prim_hits[type]++;
         return true;

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("RC_CUDA_LIB", os.path.join(HERE, "libracer_cuda.so"))
 RC_OK = 0
 RC_ERR_INVALID, RC_ERR_NO_DEVICE, RC_ERR_CUDA, RC_ERR_STATE, RC_ERR_CANCELLED, RC_ERR_NCCL = -1, -2, -3, -4, -5, -6
 
-RC_PRIM_SPHERE, RC_PRIM_XY_RECT, RC_PRIM_XZ_RECT, RC_PRIM_YZ_RECT = 0, 1, 2, 3
+RC_PRIM_SPHERE, RC_PRIM_XY_RECT, RC_PRIM_XZ_RECT, RC_PRIM_YZ_RECT, RC_PRIM_MOVING_SPHERE = 0, 1, 2, 3, 4
 RC_MAT_LAMBERTIAN, RC_MAT_METAL, RC_MAT_DIELECTRIC, RC_MAT_DIFFUSE_LIGHT = 0, 1, 2, 3
 RC_TEX_SOLID, RC_TEX_CHECKER, RC_TEX_IMAGE, RC_TEX_NOISE = 0, 1, 2, 3
 RC_BG_SKY, RC_BG_SOLID = 0, 1
@@ -72,6 +72,7 @@ class rc_scene(C.Structure):
         ("n_nodes", C.c_int32), ("nodes", C.POINTER(rc_bvh_node)),
         ("bg_type", C.c_int32), ("reserved", C.c_int32),
         ("bg_a", c_double3), ("bg_b", c_double3),
+        ("prim_motion", C.POINTER(C.c_double)),
     ]
 
 

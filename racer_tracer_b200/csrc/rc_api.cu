@@ -127,7 +127,12 @@ int validate_scene(const rc_scene* s) {
     if (s->n_images > RT_MAX_IMAGES) return fail(RC_ERR_INVALID, "more than 8 image textures");
     if (s->n_prims >= (1 << 24)) return fail(RC_ERR_INVALID, "too many primitives");
     for (int i = 0; i < s->n_prims; ++i) {
-        if (s->prim_type[i] < 0 || s->prim_type[i] > 3) return fail(RC_ERR_INVALID, "unknown primitive type");
+        if (s->prim_type[i] < 0 || s->prim_type[i] > RC_PRIM_MOVING_SPHERE) return fail(RC_ERR_INVALID, "unknown primitive type");
+        if (s->prim_type[i] == RC_PRIM_MOVING_SPHERE) {
+            if (!s->prim_motion) return fail(RC_ERR_INVALID, "moving sphere without prim_motion");
+            if (s->prim_motion[5 * (size_t)i + 4] == s->prim_motion[5 * (size_t)i + 3]) return fail(RC_ERR_INVALID, "moving sphere with time_a == time_b");
+            if (s->prim_instance && s->n_instances > 0 && s->prim_instance[i] >= 0) return fail(RC_ERR_INVALID, "instanced moving spheres are not supported");
+        }
         int m = s->prim_material[i];
         if (m < 0 || m >= s->n_materials) return fail(RC_ERR_INVALID, "primitive material index out of range");
         if (s->prim_id[i] == 0) return fail(RC_ERR_INVALID, "object id 0 is reserved for a miss");
@@ -327,6 +332,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         float* accum = (k == 0) ? accum0 : d.accum.p;
         if (kp.n_tiles == 0 || kp.s_end <= kp.s_begin) continue;
         if (p->variant == RC_VARIANT_WAVEFRONT) {
+            if (kp.has_motion && rounds != 10) return fail(RC_ERR_INVALID, "the wavefront variant traces moving spheres with 10 Philox rounds only");
             int rc = wavefront_render(d.wf, ctx->mode, kp, accum, p->sampler, rounds, ctx->smem_bytes, d.stream, d.sm_count, launches);
             if (rc != RC_OK) return fail(rc, "wavefront launch failed: " + std::string(cudaGetErrorString(cudaGetLastError())));
             continue;
@@ -452,7 +458,7 @@ static void build_tables(const rc_scene* s, HostTables& t) {
     std::vector<int>& kinds = t.kinds; kinds.assign(s->n_prims, 0);
     std::vector<uint32_t>& ids = t.ids; ids.assign(s->n_prims, 0u);
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    bool any_textured = false;
+    bool any_textured = false, any_motion = false;
     for (int i = 0; i < s->n_prims; ++i) {
         const double* d = s->prim_data + 5 * (size_t)i;
         const rc_material& m = s->materials[s->prim_material[i]];
@@ -460,11 +466,24 @@ static void build_tables(const rc_scene* s, HostTables& t) {
         DevPrim& p = prims[i];
         DevPrimD& q = prims_d[i];
         for (int k = 0; k < 4; ++k) q.a[k] = d[k];
+        for (int k = 0; k < 5; ++k) q.motion[k] = 0.0;
+        double vel[3] = {0.0, 0.0, 0.0};
         if (type == RC_PRIM_SPHERE) {
             double cc = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] - d[3] * d[3];
             p.a = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
             p.b.x = (float)cc;
             q.k_or_cc = cc;
+        } else if (type == RC_PRIM_MOVING_SPHERE) {
+            // MovingSphere::pos (moving_sphere.rs:37-39) = pos + (time - ta)/(tb - ta) (pos_b - pos)
+            //                                            = (pos - ta v) + time v,  v = (pos_b - pos)/(tb - ta)
+            const double* m = s->prim_motion + 5 * (size_t)i;
+            for (int k = 0; k < 5; ++k) q.motion[k] = m[k];
+            double c0[3];
+            for (int k = 0; k < 3; ++k) { vel[k] = (m[k] - d[k]) / (m[4] - m[3]); c0[k] = d[k] - m[3] * vel[k]; }
+            p.a = make_float4((float)c0[0], (float)c0[1], (float)c0[2], (float)d[3]);
+            p.b.x = 0.f;
+            q.k_or_cc = 0.0;
+            any_motion = true;
         } else {
             p.a = make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]);
             p.b.x = (float)d[4];
@@ -486,7 +505,9 @@ static void build_tables(const rc_scene* s, HostTables& t) {
         p.b.w = bits(tex_index);
         p.c = f4(col[0], col[1], col[2], ubits(s->prim_id[i]));
         // +axis unit normal of a rectangle (xy_rect.rs:45, xz_rect.rs:46, yz_rect.rs:46); 0 for a sphere
+        // a sphere: the centre's velocity per unit of ray time (0 when it does not move)
         p.n = make_float4(type == RC_PRIM_YZ_RECT ? 1.f : 0.f, type == RC_PRIM_XZ_RECT ? 1.f : 0.f, type == RC_PRIM_XY_RECT ? 1.f : 0.f, 0.f);
+        if (type == RC_PRIM_MOVING_SPHERE) p.n = make_float4((float)vel[0], (float)vel[1], (float)vel[2], 0.f);
         kinds[i] = type;
         ids[i] = s->prim_id[i];
         if (s->prim_aabb)
@@ -553,6 +574,7 @@ static void build_tables(const rc_scene* s, HostTables& t) {
     }
     KParams& kp = t.kp;
     kp.ref_aabb = any_rotate ? 1 : 0;
+    kp.has_motion = any_motion ? 1 : 0;
     kp.n_prims = s->n_prims; kp.n_nodes = s->n_nodes; kp.n_perlin = s->n_perlin;
     kp.bg_a = f4(s->bg_a[0], s->bg_a[1], s->bg_a[2], bits(s->bg_type));
     kp.bg_b = f4(s->bg_b[0], s->bg_b[1], s->bg_b[2], 0.f);
@@ -561,8 +583,8 @@ static void build_tables(const rc_scene* s, HostTables& t) {
     prims_lin.clear();
     prims_lin.reserve(s->n_prims);
     for (int type = 0; type < 4; ++type) {
-        for (int i = 0; i < s->n_prims; ++i)
-            if (kinds[i] == type) prims_lin.push_back(prims[i]);
+        for (int i = 0; i < s->n_prims; ++i)   // moving spheres (kind 4) share group 0 with the static ones
+            if ((kinds[i] == RC_PRIM_MOVING_SPHERE ? 0 : kinds[i]) == type) prims_lin.push_back(prims[i]);
         kp.lin_end[type] = (int)prims_lin.size();
     }
     for (int i = 0; i < RT_MAX_CONST_PRIMS; ++i)

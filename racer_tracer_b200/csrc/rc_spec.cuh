@@ -116,10 +116,18 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
     o << "RT_D int spec_closest_hit(const RayT<float>& r, int last_prim, float& best_t) {\n";
     o << "    int best = -1;\n    best_t = RT_NO_HIT;\n    (void)last_prim;\n";
     const int n_sph = kp.lin_end[0];
+    bool any_motion = false;
     if (n_sph > 0) {
         o << "    {\n        const float a = dot(r.d, r.d), inv_a = fast_rcp(a);\n        float t;\n";
         for (int i = 0; i < n_sph; ++i) {
             const DevPrim& p = kp.cprims[i];
+            const bool moving = (__float_as_int_host(p.b.z) & 15) == RT_PRIM_MOVING;
+            if (moving) {
+                any_motion = true;
+                o << "        t = sphere_hit<float>(r.o, r.d, a, inv_a, mk3(fmaf(r.time, " << spec_float(p.n.x) << ", " << spec_float(p.a.x)
+                  << "), fmaf(r.time, " << spec_float(p.n.y) << ", " << spec_float(p.a.y) << "), fmaf(r.time, " << spec_float(p.n.z) << ", "
+                  << spec_float(p.a.z) << ")), " << spec_float(p.a.w) << ", 0.0f, last_prim == " << i << ", (float)RT_T_MIN, best_t, false);\n";
+            } else
             o << "        t = sphere_hit<float>(r.o, r.d, a, inv_a, mk3(" << spec_float(p.a.x) << ", " << spec_float(p.a.y) << ", "
               << spec_float(p.a.z) << "), " << spec_float(p.a.w) << ", " << spec_float(p.b.x) << ", last_prim == " << i
               << ", (float)RT_T_MIN, best_t);\n";
@@ -170,6 +178,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
     o << "    return best;\n}\n";
     o << "#define RT_SPECIALIZED 1\n";
     o << "#define RT_SPEC_MATS " << mats_mask << "\n";
+    o << "#define RT_HAS_MOTION " << (any_motion ? 1 : 0) << "\n";
     o << "#include \"rt_kernels.cuh\"\n";
     o << "extern \"C\" __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)\n"
          "spec_megakernel(const __grid_constant__ KParams P, float* __restrict__ accum) {\n"

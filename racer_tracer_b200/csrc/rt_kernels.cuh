@@ -72,6 +72,9 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
 #define RT_SPEC_MATS 0xF      /* bit m set: material kind m occurs in the scene */
 #endif
 #define RT_HAS_MAT(m) ((RT_SPEC_MATS >> (m)) & 1)
+#ifndef RT_HAS_MOTION
+#define RT_HAS_MOTION 1     /* a scene-specialised kernel sets 0 when no sphere moves */
+#endif
 
 template <int MODE, class Scene>
 RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& t) {
@@ -108,10 +111,16 @@ RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
 
 // Primary ray of one sample.  `w` = the sample's start block (x -> v jitter).
 template <int SAMPLER, int ROUNDS>
-RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit, vec3f& o, vec3f& d) {
+RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit, vec3f& o, vec3f& d, float& time) {
     float v = ((float)(c.py * P.px_scale_y) + vjit) * P.inv_hm1;  // cpu.rs:39-40 (cpu_scaled.rs:59-60)
     d = c.dir0 - v * P.cam.vertical;
     o = P.cam.origin;
+    time = P.cam.time_a;
+    if (RT_HAS_MOTION && P.has_motion && !P.fixed_jitter) {
+        // camera.rs:335: random_double_range(time_a, time_b); the draw is the spare 16 bits of LENS block 0
+        const uint2 w = philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.ks);
+        time = fmaf(P.cam.time_b - P.cam.time_a, u16lo(w), P.cam.time_a);
+    }
     if (P.lens_enabled && !P.fixed_jitter) {  // camera.rs:327-328; skipped when lens_radius == 0 (offset = 0)
         float dx, dy;
         if (SAMPLER == 1) {  // random_in_unit_disk, util.rs:25-39
@@ -122,7 +131,7 @@ RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float
                 break;
             }
         } else {
-            uint2 w = philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.ks);
+            uint2 w = philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.ks);   // the same block as the time's: CSE
             float r = fast_sqrt(u24(w.x)), s, cs;
             fast_sincos_2pi(u24(w.y), s, cs);
             dx = r * cs; dy = r * s;
@@ -253,6 +262,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     // ray_color's `emitted + attenuation * recurse` collapses to throughput x terminal radiance.
     vec3f sum = mk3(0.0f, 0.0f, 0.0f);
     vec3f o = mk3(0.0f, 0.0f, 0.0f), d = o, T = o;
+    float time = 0.0f;         // Ray::time of the path (scattered rays inherit it, lambertian.rs:36 etc.)
     int s = valid ? s_first : s_last;
     int depth_left = 0;        // > 0: this lane is on a path that may still trace that many segments; 0: no path
     int last_prim = -1;
@@ -286,9 +296,9 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, seg, RT_TAG_PATH), P.ks);
             if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337
                 const float vjit = P.fixed_jitter ? 0.5f : u16lo(rnd);
-                camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d);
+                camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d, time);
             }
-            RayT<float> r = make_ray(o, d);
+            RayT<float> r = make_ray(o, d, time);
             float t;
             int prim;
             if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, L.prims); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
@@ -373,8 +383,9 @@ primary_aov_kernel(const __grid_constant__ KParams P, uint32_t* __restrict__ id,
     if (px >= P.width || py >= P.height) return;
     PixelCtx pc = pixel_setup<10>(P, px, py);
     vec3f o, d;
-    camera_ray<0, 10>(P, pc, 0u, 0.5f, o, d);
-    RayT<float> r = make_ray(o, d);
+    float time;
+    camera_ray<0, 10>(P, pc, 0u, 0.5f, o, d, time);   // fixed jitter: time = time_a
+    RayT<float> r = make_ray(o, d, time);
     float t;
     int prim;
     Hit h;
@@ -428,6 +439,14 @@ RT_D Vec3T<double> sd_sub3(Vec3T<double> a, Vec3T<double> b) { return mk3(sd_sub
 RT_D Vec3T<double> sd_add3(Vec3T<double> a, Vec3T<double> b) { return mk3(sd_add(a.x, b.x), sd_add(a.y, b.y), sd_add(a.z, b.z)); }
 RT_D Vec3T<double> sd_scale(double s, Vec3T<double> a) { return mk3(sd_mul(s, a.x), sd_mul(s, a.y), sd_mul(s, a.z)); }
 
+// MovingSphere::pos in reference order (moving_sphere.rs:37-39) at the fixed-jitter ray time
+RT_D Vec3T<double> sphere_centre_d(const DevPrimD& p, int type, double time) {
+    Vec3T<double> c = mk3(p.a[0], p.a[1], p.a[2]);
+    if (type != RT_PRIM_MOVING) return c;
+    const double f = sd_div(sd_sub(time, p.motion[3]), sd_sub(p.motion[4], p.motion[3]));
+    return sd_add3(c, sd_scale(f, sd_sub3(mk3(p.motion[0], p.motion[1], p.motion[2]), c)));
+}
+
 // ray into an instance's space, reference order: translate.rs:32, rotate_y.rs:38-47
 RT_D void to_local_d(const DevInstanceD& in, Vec3T<double>& o, Vec3T<double>& d) {
     if (in.flags & 2) o = sd_sub3(o, mk3(in.offset[0], in.offset[1], in.offset[2]));
@@ -445,8 +464,8 @@ RT_D double prim_test_d(const AovParamsD& P, int i, Vec3T<double> o, Vec3T<doubl
     int type = P.prim_kind[i];
     const int inst = P.prim_inst[i];
     if (inst >= 0) to_local_d(P.instances[inst], o, d);
-    if (type == RT_PRIM_SPHERE) {  // sphere.rs:39-58
-        Vec3T<double> oc = sd_sub3(o, mk3(p.a[0], p.a[1], p.a[2]));
+    if (RT_IS_SPHERE(type)) {  // sphere.rs:39-58, moving_sphere.rs:50-66
+        Vec3T<double> oc = sd_sub3(o, sphere_centre_d(p, type, P.cam.time_a));
         double a = sd_dot(d, d), half_b = sd_dot(oc, d);
         double c = sd_sub(sd_dot(oc, oc), sd_mul(p.a[3], p.a[3]));
         double disc = sd_sub(sd_mul(half_b, half_b), sd_mul(a, c));
@@ -533,8 +552,8 @@ __global__ void primary_aov_kernel_f64(const __grid_constant__ AovParamsD P, uin
     Vec3T<double> lo = o, ld = d;           // ray in the primitive's space
     if (inst >= 0) to_local_d(P.instances[inst], lo, ld);
     Vec3T<double> hp = sd_add3(lo, sd_scale(best_t, ld)), on;   // Ray::at
-    if (type == RT_PRIM_SPHERE) {
-        Vec3T<double> pc = sd_sub3(hp, mk3(p.a[0], p.a[1], p.a[2]));
+    if (RT_IS_SPHERE(type)) {
+        Vec3T<double> pc = sd_sub3(hp, sphere_centre_d(p, type, P.cam.time_a));
         on = mk3(sd_div(pc.x, p.a[3]), sd_div(pc.y, p.a[3]), sd_div(pc.z, p.a[3]));  // sphere.rs:61
     } else on = mk3(type == RT_PRIM_YZ ? 1.0 : 0.0, type == RT_PRIM_XZ ? 1.0 : 0.0, type == RT_PRIM_XY ? 1.0 : 0.0);
     bool front = sd_dot(ld, on) < 0.0;

@@ -15,7 +15,9 @@
 //   c: (r, g, b) of a solid-colour texture (albedo or emission), c.w = bits of
 //      the canonical object id
 //   n: rect: the +axis unit normal (xy_rect.rs:45 etc.), so that the hit record
-//      is formed with multiply-adds instead of per-type selects;  sphere: 0
+//      is formed with multiply-adds instead of per-type selects;  sphere: the
+//      centre's velocity per unit of ray time, centre(time) = a.xyz + time * n.xyz
+//      (MovingSphere::pos, moving_sphere.rs:37-39; 0 for a static sphere)
 // packed kinds (b.z bits): [0:4) prim type, [4:8) material type, [8:12)
 // texture type, [12:32) instance index + 1 (0 = none)
 // ---------------------------------------------------------------------------
@@ -23,6 +25,9 @@
 #define RT_PRIM_XY 1
 #define RT_PRIM_XZ 2
 #define RT_PRIM_YZ 3
+#define RT_PRIM_MOVING 4        // moving sphere (moving_sphere.rs): a = centre at ray time 0, r; n = centre velocity
+// spheres (static and moving) are the kinds whose low two bits are 0
+#define RT_IS_SPHERE(type) (((type) & 3) == 0)
 #define RT_MAT_LAMBERTIAN 0
 #define RT_MAT_METAL 1
 #define RT_MAT_DIELECTRIC 2
@@ -44,6 +49,7 @@ struct DevPrim {      // fp32 primitive record, 64 B
 struct DevPrimD {     // f64 geometry of the same primitive (AOV f64 instantiation)
     double a[4];
     double k_or_cc;
+    double motion[5];  // moving sphere: pos_b xyz, time_a, time_b
 };
 
 struct DevNode {      // threaded BVH node, pre-order; 32 B
@@ -100,6 +106,7 @@ struct KParams {
     int lin_end[4];             // type-sorted linear table: [0,lin_end[0]) spheres, then xy, xz, yz rects
     int n_perlin;
     int lens_enabled;
+    int has_motion;             // the scene has a moving sphere: primary rays carry a time (camera.rs:335)
     int ref_aabb;               // scenes with RotateY: BVH culling uses the reference's per-axis Aabb::hit
     const DevPrim* prims;       // all primitives, BVH depth-first order (global memory)
     const DevPrim* prims_lin;   // the same primitives sorted by type (linear modes)
@@ -132,6 +139,7 @@ struct ConstScene {
     // uniform index (the intersection loops): constant-bank operands
     RT_D float4 ua(int i) const { return P.cprims[i].a; }
     RT_D float4 ub(int i) const { return P.cprims[i].b; }
+    RT_D float4 un(int i) const { return P.cprims[i].n; }
     // per-lane index (hit record, shading): shared memory — an indexed constant load replays
     // once per distinct address in the warp
     RT_D float4 pa(int i) const { return sh[i].a; }
@@ -153,6 +161,7 @@ struct PtrScene {  // shared or global, decided by where the pointers point
     RT_D bool reference_aabb() const { return ref_aabb != 0; }
     RT_D float4 ua(int i) const { return prims[i].a; }
     RT_D float4 ub(int i) const { return prims[i].b; }
+    RT_D float4 un(int i) const { return prims[i].n; }
     RT_D float4 pa(int i) const { return prims[i].a; }
     RT_D float4 pb(int i) const { return prims[i].b; }
     RT_D float4 pc(int i) const { return prims[i].c; }
@@ -191,7 +200,7 @@ RT_D int kinds_inst(float packed) { return (int)((unsigned)__float_as_int(packed
 // Both use the stable root formula q = -(b + sign(b) sqrt(disc)); t = q/a, c/q.
 #define RT_SPHERE_FAR_RATIO 2.6f
 template <typename T>
-RT_D T sphere_hit(Vec3T<T> o, Vec3T<T> d, T a, T inv_a, Vec3T<T> ctr, T radius, T cc, bool self, T t_min, T t_max) {
+RT_D T sphere_hit(Vec3T<T> o, Vec3T<T> d, T a, T inv_a, Vec3T<T> ctr, T radius, T cc, bool self, T t_min, T t_max, bool use_cc = true) {
     Vec3T<T> oc = o - ctr;
     T b = dot(oc, d);  // half_b
     T oc2 = dot(oc, oc), r2 = radius * radius;
@@ -202,8 +211,10 @@ RT_D T sphere_hit(Vec3T<T> o, Vec3T<T> d, T a, T inv_a, Vec3T<T> ctr, T radius, 
         disc = a * (r2 - dot(l, l));
         c = oc2 - r2;
     } else {
+        // a moving sphere has no precomputed |ctr|^2 - r^2; its radius is small against its distance
+        // from the origin only when oc is small too, so |oc|^2 - r^2 is the accurate form there
         Vec3T<T> o2 = mk3<T>(o.x - T(2) * ctr.x, o.y - T(2) * ctr.y, o.z - T(2) * ctr.z);
-        c = self ? T(0) : (dot(o, o2) + cc);
+        c = self ? T(0) : (use_cc ? dot(o, o2) + cc : oc2 - r2);
         disc = b * b - a * c;
     }
     if (!(disc >= T(0))) return T(-1);
@@ -256,12 +267,13 @@ RT_D T rect_hit(int type, Vec3T<T> o, Vec3T<T> d, Vec3T<T> inv_d, T a0, T a1, T 
 template <typename T>
 struct RayT {
     Vec3T<T> o, d, inv_d;
+    T time;   // Ray::time (src/ray.rs), read by moving spheres only
 };
 
 template <typename T>
-RT_D RayT<T> make_ray(Vec3T<T> o, Vec3T<T> d) {
+RT_D RayT<T> make_ray(Vec3T<T> o, Vec3T<T> d, T time = T(0)) {
     RayT<T> r;
-    r.o = o; r.d = d;
+    r.o = o; r.d = d; r.time = time;
     r.inv_d = mk3<T>(rt_rcp(d.x), rt_rcp(d.y), rt_rcp(d.z));
     return r;
 }
@@ -276,17 +288,23 @@ RT_D RayT<float> to_local(const DevInstance& in, const RayT<float>& r) {
         o = mk3(c * o.x - s * o.z, o.y, s * o.x + c * o.z);
         d = mk3(c * d.x - s * d.z, d.y, s * d.x + c * d.z);
     }
-    return make_ray(o, d);
+    return make_ray(o, d, r.time);
+}
+
+// centre of a (possibly moving) sphere at the ray's time
+RT_D vec3f sphere_centre(float4 a, float4 n, float time) {
+    return mk3(fmaf(time, n.x, a.x), fmaf(time, n.y, a.y), fmaf(time, n.z, a.z));
 }
 
 // One primitive of the fp32 tables against a ray already in the primitive's space; returns t or -1.
 template <class Scene>
 RT_D float prim_test_local(const Scene& S, int i, float4 a, float4 b, const RayT<float>& r, bool self, bool instanced, float t_max) {
-    (void)S; (void)i;
     int type = kinds_prim(b.z);
-    if (type == RT_PRIM_SPHERE) {
+    if (RT_IS_SPHERE(type)) {
         const float aa = dot(r.d, r.d);
-        return sphere_hit<float>(r.o, r.d, aa, fast_rcp(aa), mk3(a.x, a.y, a.z), a.w, b.x, self, (float)RT_T_MIN, t_max);
+        const bool moving = type == RT_PRIM_MOVING;
+        const vec3f ctr = moving ? sphere_centre(a, S.pn(i), r.time) : mk3(a.x, a.y, a.z);
+        return sphere_hit<float>(r.o, r.d, aa, fast_rcp(aa), ctr, a.w, b.x, self, (float)RT_T_MIN, t_max, !moving);
     }
     // an instanced rectangle's hit point goes through a rotation before it becomes the next
     // origin, so it is not exactly on the plane any more: the rectangle a ray leaves is skipped
@@ -402,9 +420,11 @@ RT_D int closest_hit_linear(const KParams& P, const Scene& S, const RayT<float>&
         const float a = dot(r.d, r.d), inv_a = fast_rcp(a);
 #pragma unroll 1
         for (int i = 0; i < n_sph; ++i) {
-            const float4 pa = S.ua(i);
-            const float t = sphere_hit<float>(r.o, r.d, a, inv_a, mk3(pa.x, pa.y, pa.z), pa.w, S.ub(i).x, i == last_prim,
-                                              (float)RT_T_MIN, best_t);
+            const float4 pa = S.ua(i), pb = S.ub(i);
+            const bool moving = kinds_prim(pb.z) == RT_PRIM_MOVING;   // uniform: i is
+            const vec3f ctr = moving ? sphere_centre(pa, S.un(i), r.time) : mk3(pa.x, pa.y, pa.z);
+            const float t = sphere_hit<float>(r.o, r.d, a, inv_a, ctr, pa.w, pb.x, i == last_prim,
+                                              (float)RT_T_MIN, best_t, !moving);
             const bool hit = t >= 0.0f;
             best_t = hit ? t : best_t;
             best = hit ? i : best;
@@ -517,8 +537,8 @@ template <class Scene>
 RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT<float>& r, float t) {
     Hit h;
     h.p = r.o + t * r.d;  // Ray::at
-    if (RT_HAS_SPHERES && (!RT_HAS_RECTS || kinds_prim(b.z) == RT_PRIM_SPHERE)) {
-        vec3f ctr = mk3(a.x, a.y, a.z);
+    if (RT_HAS_SPHERES && (!RT_HAS_RECTS || RT_IS_SPHERE(kinds_prim(b.z)))) {
+        vec3f ctr = kinds_prim(b.z) == RT_PRIM_MOVING ? sphere_centre(a, S.pn(prim), r.time) : mk3(a.x, a.y, a.z);
         const float aa = dot(r.d, r.d);
         h.outward = sphere_normal(r.o, r.d, aa, fast_rcp(aa), ctr, a.w, t);  // sphere.rs:61
         h.p = ctr + a.w * h.outward;   // the point on the surface that normal belongs to
@@ -577,9 +597,11 @@ RT_D void hit_uv(const Scene& S, int prim, const Hit& h, float& u, float& v) {
     float4 a = S.pa(prim), b = S.pb(prim);
     int type = kinds_prim(b.z);
     const float PI_F = 3.14159265358979323846f;
-    if (type == RT_PRIM_SPHERE) {
-        float theta = acosf(fminf(fmaxf(-h.outward.y, -1.0f), 1.0f));
-        float phi = atan2f(-h.outward.z, h.outward.x) + PI_F;
+    if (RT_IS_SPHERE(type)) {
+        // sphere.rs:62 takes uv from the outward normal, moving_sphere.rs:76 from the POINT (Q27)
+        const vec3f q = type == RT_PRIM_MOVING ? h.p : h.outward;
+        float theta = acosf(fminf(fmaxf(-q.y, -1.0f), 1.0f));
+        float phi = atan2f(-q.z, q.x) + PI_F;
         u = phi / (2.0f * PI_F);
         v = theta / PI_F;
     } else {

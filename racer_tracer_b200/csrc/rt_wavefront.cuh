@@ -103,6 +103,15 @@ __global__ void wf_reset_kernel(WfPool W) {
     W.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Ray::time of the path of (pixel, sample): the same draw camera_ray() makes (10-round Philox: the
+// wavefront kernels that need it are not templated on the round count; rounds != 10 with a moving
+// sphere is rejected at launch)
+RT_D float wf_path_time(const KParams& P, uint32_t pixel, uint32_t sample) {
+    if (!P.has_motion || P.fixed_jitter) return P.cam.time_a;
+    const uint2 w = philox2x32_ks<10>(pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.ks);
+    return fmaf(P.cam.time_b - P.cam.time_a, u16lo(w), P.cam.time_a);
+}
+
 // warp-aggregated fetch of `want` consecutive work items
 RT_D unsigned long long wf_take_work(unsigned int* counters, bool want) {
     const unsigned mask = __ballot_sync(0xffffffffu, want);
@@ -160,7 +169,8 @@ wf_generate(const __grid_constant__ KParams P, WfPool W, float* __restrict__ acc
         float vjit = 0.5f;
         if (!P.fixed_jitter) vjit = u16lo(philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(sample, 0u, RT_TAG_PATH), P.ks));
         vec3f o, d;
-        camera_ray<SAMPLER, ROUNDS>(P, pc, sample, vjit, o, d);
+        float time;   // not stored in the pool: wf_path_time() recomputes it from (pixel, sample)
+        camera_ray<SAMPLER, ROUNDS>(P, pc, sample, vjit, o, d, time);
         info.y = sample + 1u;
         if (P.max_depth > 0) {
             W.o_t[i] = make_float4(o.x, o.y, o.z, 0.f);
@@ -196,7 +206,7 @@ wf_intersect(const __grid_constant__ KParams P, WfPool W) {
     int cls = -1;
     if (alive) {
         float4 ot = W.o_t[i], dp = W.d_prim[i], th = W.thr[i];
-        RayT<float> r = make_ray(mk3(ot.x, ot.y, ot.z), mk3(dp.x, dp.y, dp.z));
+        RayT<float> r = make_ray(mk3(ot.x, ot.y, ot.z), mk3(dp.x, dp.y, dp.z), wf_path_time(P, info.x, info.y - 1u));
         const int last_prim = __float_as_int(th.w);
         float t;
         int prim;
@@ -241,7 +251,7 @@ RT_D void wf_shade_one(const KParams& P, const WfPool& W, const TexCtx& X, const
     float4 ot = W.o_t[i], dp = W.d_prim[i], th = W.thr[i];
     uint4 info = W.info[i];
     vec3f o = mk3(ot.x, ot.y, ot.z), d = mk3(dp.x, dp.y, dp.z), T = mk3(th.x, th.y, th.z);
-    const RayT<float> r = make_ray(o, d);
+    const RayT<float> r = make_ray(o, d, wf_path_time(P, info.x, info.y - 1u));
     const int prim = __float_as_int(dp.w);
     uint32_t bounce = (info.w & 0xffu) + 1u, depth_left = (info.w >> 8) & 0xffu;
     RngCtx R; R.ks = P.ks; R.pixel = info.x; R.sample = info.y - 1u;

@@ -114,6 +114,7 @@ class Prim:
     obj: int          # top-level object ordinal (1-based, canonical)
     side: int = 0
     instance: int = -1
+    motion: list | None = None   # moving sphere: [pos_b x, y, z, time_a, time_b]
 
 
 @dataclass
@@ -156,6 +157,98 @@ class FlatScene:
     @property
     def ptr(self):
         return C.byref(self.c)
+
+
+def _flatten(fs: "FlatScene", objects: dict, textures, materials, images, perlins, use_bvh=None):
+    """Top-level objects -> structure-of-arrays primitives + host BVH (what the Rust shim does before
+    rc_upload_scene)."""
+    # canonical ids (SURVEY §8(c)): objects numbered 1..N by sorted lower-cased
+    # key; reported id = (object << 3) | box side
+    instances: list[rc_instance] = []
+    ordered = [objects[k] for k in sorted(objects)]
+    for n, o in enumerate(ordered, start=1):
+        inst = -1
+        if o.rotate_deg is not None or o.translate is not None:
+            ri = rc_instance()
+            if o.rotate_deg is not None:
+                ri.flags |= 1
+                rad = o.rotate_deg * math.pi / 180.0  # util.rs:5-7
+                ri.sin_theta, ri.cos_theta = math.sin(rad), math.cos(rad)
+            if o.translate is not None:
+                ri.flags |= 2
+                ri.offset[:] = o.translate
+            inst = len(instances)
+            instances.append(ri)
+        for p in o.prims:
+            p.obj, p.instance = n, inst
+    fs.object_keys = [o.key for o in ordered]
+
+    if use_bvh is None:
+        use_bvh = True
+    nodes: list[rc_bvh_node] = []
+    if use_bvh and ordered:
+        order: list[TopObject] = []
+        _build_bvh(ordered, nodes, order)
+        ordered = order
+        # fix leaf prim offsets now that the DFS order is known
+        first = {}
+        n = 0
+        for o in ordered:
+            first[id(o)] = n
+            n += len(o.prims)
+        for nd in nodes:
+            if nd.left < 0:
+                o = ordered[~nd.left]
+                nd.left = ~first[id(o)]
+                nd.right = len(o.prims)
+
+    prims = [p for o in ordered for p in o.prims]
+    aabbs = [o.aabb_min + o.aabb_max for o in ordered for _ in o.prims]
+    fs.prims = prims
+    n = len(prims)
+    prim_type = np.array([p.type for p in prims], dtype=np.int32)
+    prim_data = np.array([p.data for p in prims], dtype=np.float64).reshape(n, 5)
+    prim_material = np.array([p.material for p in prims], dtype=np.int32)
+    prim_id = np.array([(p.obj << 3) | p.side for p in prims], dtype=np.uint32)
+    prim_instance = np.array([p.instance for p in prims], dtype=np.int32)
+    prim_aabb = np.array(aabbs, dtype=np.float64).reshape(n, 6)
+    prim_motion = np.array([p.motion if p.motion is not None else [0.0] * 5 for p in prims], dtype=np.float64).reshape(n, 5)
+
+    c = fs.c
+    c.n_prims = n
+    c.prim_type = prim_type.ctypes.data_as(C.POINTER(C.c_int32))
+    c.prim_data = prim_data.ctypes.data_as(C.POINTER(C.c_double))
+    c.prim_material = prim_material.ctypes.data_as(C.POINTER(C.c_int32))
+    c.prim_id = prim_id.ctypes.data_as(C.POINTER(C.c_uint32))
+    c.prim_instance = prim_instance.ctypes.data_as(C.POINTER(C.c_int32))
+    c.prim_aabb = prim_aabb.ctypes.data_as(C.POINTER(C.c_double))
+    if any(p.motion is not None for p in prims):
+        c.prim_motion = prim_motion.ctypes.data_as(C.POINTER(C.c_double))
+    fs.keep += [prim_type, prim_data, prim_material, prim_id, prim_instance, prim_aabb, prim_motion]
+    fs.np = dict(prim_type=prim_type, prim_data=prim_data, prim_material=prim_material, prim_id=prim_id,
+                 prim_instance=prim_instance, prim_aabb=prim_aabb, prim_motion=prim_motion)
+
+    def arr(ctype, items):
+        a = (ctype * max(1, len(items)))(*items)
+        fs.keep.append(a)
+        return a
+
+    c.n_instances, c.instances = len(instances), arr(rc_instance, instances)
+    c.n_materials, c.materials = len(materials), arr(rc_material, materials)
+    c.n_textures, c.textures = len(textures), arr(rc_texture, textures)
+    c.n_perlin, c.perlin = len(perlins), arr(rc_perlin, perlins)
+    c.n_nodes, c.nodes = len(nodes), arr(rc_bvh_node, nodes)
+    imgs = []
+    for (w, h, px) in images:
+        im = rc_image()
+        im.width, im.height = w, h
+        im.rgba = px.ctypes.data_as(C.POINTER(C.c_uint8))
+        fs.keep.append(px)
+        imgs.append(im)
+    c.n_images, c.images = len(imgs), arr(rc_image, imgs)
+    fs.images = images
+    fs.textures, fs.materials, fs.nodes, fs.instances = textures, materials, nodes, instances
+
 
 
 def load_scene(path: str, seed: int = 0, use_bvh: bool | None = None, image_dirs=()) -> FlatScene:
@@ -297,89 +390,8 @@ def load_scene(path: str, seed: int = 0, use_bvh: bool | None = None, image_dirs
         o.aabb_min = [o.aabb_min[i] + off[i] for i in range(3)]  # translate.rs:44-47
         o.aabb_max = [o.aabb_max[i] + off[i] for i in range(3)]
 
-    # canonical ids: objects numbered 1..N by sorted lower-cased
-    # key; reported id = (object << 3) | box side
-    instances: list[rc_instance] = []
-    ordered = [objects[k] for k in sorted(objects)]
-    for n, o in enumerate(ordered, start=1):
-        inst = -1
-        if o.rotate_deg is not None or o.translate is not None:
-            ri = rc_instance()
-            if o.rotate_deg is not None:
-                ri.flags |= 1
-                rad = o.rotate_deg * math.pi / 180.0  # util.rs:5-7
-                ri.sin_theta, ri.cos_theta = math.sin(rad), math.cos(rad)
-            if o.translate is not None:
-                ri.flags |= 2
-                ri.offset[:] = o.translate
-            inst = len(instances)
-            instances.append(ri)
-        for p in o.prims:
-            p.obj, p.instance = n, inst
-    fs.object_keys = [o.key for o in ordered]
-
-    if use_bvh is None:
-        use_bvh = True
-    nodes: list[rc_bvh_node] = []
-    if use_bvh and ordered:
-        order: list[TopObject] = []
-        _build_bvh(ordered, nodes, order)
-        ordered = order
-        # fix leaf prim offsets now that the DFS order is known
-        first = {}
-        n = 0
-        for o in ordered:
-            first[id(o)] = n
-            n += len(o.prims)
-        for nd in nodes:
-            if nd.left < 0:
-                o = ordered[~nd.left]
-                nd.left = ~first[id(o)]
-                nd.right = len(o.prims)
-
-    prims = [p for o in ordered for p in o.prims]
-    aabbs = [o.aabb_min + o.aabb_max for o in ordered for _ in o.prims]
-    fs.prims = prims
-    n = len(prims)
-    prim_type = np.array([p.type for p in prims], dtype=np.int32)
-    prim_data = np.array([p.data for p in prims], dtype=np.float64).reshape(n, 5)
-    prim_material = np.array([p.material for p in prims], dtype=np.int32)
-    prim_id = np.array([(p.obj << 3) | p.side for p in prims], dtype=np.uint32)
-    prim_instance = np.array([p.instance for p in prims], dtype=np.int32)
-    prim_aabb = np.array(aabbs, dtype=np.float64).reshape(n, 6)
-
+    _flatten(fs, objects, textures, materials, images, perlins, use_bvh)
     c = fs.c
-    c.n_prims = n
-    c.prim_type = prim_type.ctypes.data_as(C.POINTER(C.c_int32))
-    c.prim_data = prim_data.ctypes.data_as(C.POINTER(C.c_double))
-    c.prim_material = prim_material.ctypes.data_as(C.POINTER(C.c_int32))
-    c.prim_id = prim_id.ctypes.data_as(C.POINTER(C.c_uint32))
-    c.prim_instance = prim_instance.ctypes.data_as(C.POINTER(C.c_int32))
-    c.prim_aabb = prim_aabb.ctypes.data_as(C.POINTER(C.c_double))
-    fs.keep += [prim_type, prim_data, prim_material, prim_id, prim_instance, prim_aabb]
-    fs.np = dict(prim_type=prim_type, prim_data=prim_data, prim_material=prim_material, prim_id=prim_id,
-                 prim_instance=prim_instance, prim_aabb=prim_aabb)
-
-    def arr(ctype, items):
-        a = (ctype * max(1, len(items)))(*items)
-        fs.keep.append(a)
-        return a
-
-    c.n_instances, c.instances = len(instances), arr(rc_instance, instances)
-    c.n_materials, c.materials = len(materials), arr(rc_material, materials)
-    c.n_textures, c.textures = len(textures), arr(rc_texture, textures)
-    c.n_perlin, c.perlin = len(perlins), arr(rc_perlin, perlins)
-    c.n_nodes, c.nodes = len(nodes), arr(rc_bvh_node, nodes)
-    imgs = []
-    for (w, h, px) in images:
-        im = rc_image()
-        im.width, im.height = w, h
-        im.rgba = px.ctypes.data_as(C.POINTER(C.c_uint8))
-        fs.keep.append(px)
-        imgs.append(im)
-    c.n_images, c.images = len(imgs), arr(rc_image, imgs)
-    fs.images = images
-    fs.textures, fs.materials, fs.nodes, fs.instances = textures, materials, nodes, instances
 
     # background, yml.rs:443-453; default Sky (background_color.rs:18-25)
     bg = doc.get("background")
@@ -400,6 +412,96 @@ def load_scene(path: str, seed: int = 0, use_bvh: bool | None = None, image_dirs
             raise SceneLoadError(f"Configuration({path}): unknown background `{variant}`")
     fs.camera_cfg = doc.get("camera")
     fs.tone_map_cfg = doc.get("tone_map")
+    return fs
+
+
+TAG_SCENE = 3
+
+
+class _SceneRng:
+    """Sequential uniforms for procedural scenes: Philox4x32-10(counter = (n, 0, 0, TAG_SCENE << 24),
+    key = seed), four 24-bit uniforms per block, consumed in order.  The reference draws from the
+    OS-seeded thread_rng (src/util.rs:9-23), so its Random scene is different on every run."""
+
+    def __init__(self, seed: int):
+        self.key = (seed & MASK, (seed >> 32) & MASK)
+        self.n, self.buf = 0, []
+
+    def uniform(self) -> float:
+        if not self.buf:
+            self.buf = [u01(w) for w in philox4x32((self.n, 0, 0, TAG_SCENE << 24), self.key)]
+            self.n += 1
+        return self.buf.pop(0)
+
+    def range(self, lo: float, hi: float) -> float:   # random_double_range, util.rs:19-23
+        return lo + (hi - lo) * self.uniform()
+
+
+def random_scene(seed: int = 0, use_bvh: bool | None = None) -> FlatScene:
+    """Random::load (src/scene/random.rs:25-95): a checkered ground sphere, a 22 x 22 grid of small
+    spheres (80 % diffuse MOVING spheres, 5 % metal, 15 % glass; skipped near (4, 0.2, 0)) and three
+    large spheres; default Sky; camera vfov 20, aperture 0.1, focus 10, from (0, 2, 10) to the origin."""
+    rng = _SceneRng(seed)
+    fs = FlatScene()
+    textures, materials, objects = [], [], {}
+
+    def solid(rgb):
+        t = rc_texture()
+        t.type = capi.RC_TEX_SOLID
+        t.color[:] = rgb
+        textures.append(t)
+        return len(textures) - 1
+
+    def material(kind, texture=0, param=0.0):
+        m = rc_material()
+        m.type, m.texture, m.param = kind, texture, param
+        materials.append(m)
+        return len(materials) - 1
+
+    def sphere(center, radius, mat, center_b=None):
+        key = f"obj{len(objects):04d}"      # creation order == sorted key order
+        lo, hi = _aabb([center[i] - radius for i in range(3)], [center[i] + radius for i in range(3)])
+        prim = Prim(capi.RC_PRIM_SPHERE, list(center) + [radius, 0.0], mat, 0)
+        if center_b is not None:   # create_movable_sphere, geometry_creation.rs:23-38; union box, moving_sphere.rs:90-99
+            prim.type = capi.RC_PRIM_MOVING_SPHERE
+            prim.motion = list(center_b) + [0.0, 1.0]
+            lo2, hi2 = _aabb([center_b[i] - radius for i in range(3)], [center_b[i] + radius for i in range(3)])
+            lo, hi = [min(lo[i], lo2[i]) for i in range(3)], [max(hi[i], hi2[i]) for i in range(3)]
+        objects[key] = TopObject(key, [prim], lo, hi, list(center))
+
+    even, odd = solid([0.2, 0.3, 0.1]), solid([0.9, 0.9, 0.9])
+    chk = rc_texture()
+    chk.type, chk.a, chk.b, chk.scale = capi.RC_TEX_CHECKER, even, odd, 10.0
+    textures.append(chk)
+    sphere([0.0, -1000.0, 0.0], 1000.0, material(capi.RC_MAT_LAMBERTIAN, len(textures) - 1))
+    for a in range(-11, 11):
+        for b in range(-11, 11):
+            choose_mat = rng.uniform()
+            center = [a + 0.9 * rng.uniform(), 0.2, b + 0.9 * rng.uniform()]
+            if math.sqrt((center[0] - 4.0) ** 2 + (center[1] - 0.2) ** 2 + center[2] ** 2) > 0.9:
+                if choose_mat < 0.8:      # diffuse, moving
+                    c1 = [rng.uniform() for _ in range(3)]
+                    c2 = [rng.uniform() for _ in range(3)]
+                    albedo = [c1[i] * c2[i] for i in range(3)]
+                    center2 = [center[0], center[1] + rng.range(0.0, 0.5), center[2]]
+                    sphere(center, 0.2, material(capi.RC_MAT_LAMBERTIAN, solid(albedo)), center2)
+                elif choose_mat > 0.95:   # metal
+                    albedo = [rng.range(0.5, 1.0) for _ in range(3)]
+                    fuzz = rng.range(0.0, 0.5)
+                    sphere(center, 0.2, material(capi.RC_MAT_METAL, solid(albedo), fuzz))
+                else:                     # glass
+                    sphere(center, 0.2, material(capi.RC_MAT_DIELECTRIC, 0, 1.5))
+    sphere([0.0, 1.0, 0.0], 1.0, material(capi.RC_MAT_DIELECTRIC, 0, 1.5))
+    sphere([-4.0, 1.0, 0.0], 1.0, material(capi.RC_MAT_LAMBERTIAN, solid([0.4, 0.2, 0.1])))
+    sphere([4.0, 1.0, 0.0], 1.0, material(capi.RC_MAT_METAL, solid([0.7, 0.6, 0.5]), 0.0))
+    _flatten(fs, objects, textures, materials, [], [], use_bvh)
+    c = fs.c
+    c.bg_type = capi.RC_BG_SKY
+    c.bg_a[:] = [1.0, 1.0, 1.0]
+    c.bg_b[:] = [0.5, 0.7, 1.0]
+    fs.camera_cfg = {"vfov": 20.0, "aperture": 0.1, "focus_distance": 10.0,
+                     "pos": [0.0, 2.0, 10.0], "look_at": [0.0, 0.0, 0.0]}
+    fs.tone_map_cfg = None
     return fs
 
 
@@ -663,7 +765,10 @@ def prepare_job(scene_path: str, config: Config | None = None, width=None, heigh
     """The wiring of src/main.rs:74-119 up to the point where render() is called."""
     cfg = config or default_config()
     w, h = width or cfg.width, height or cfg.height
-    fs = load_scene(scene_path, seed=seed, use_bvh=use_bvh, image_dirs=image_dirs)
+    if scene_path == "random":      # SceneLoaderConfig::Random, config.rs:84-93
+        fs = random_scene(seed=seed, use_bvh=use_bvh)
+    else:
+        fs = load_scene(scene_path, seed=seed, use_bvh=use_bvh, image_dirs=image_dirs)
     cam = make_camera(merged_camera(fs.camera_cfg, cfg.camera), w, h)
     tm = make_tone_map(fs.tone_map_cfg if fs.tone_map_cfg is not None else cfg.tone_map)  # main.rs:84-86
     return Job(fs, cam, tm, cfg, w, h)

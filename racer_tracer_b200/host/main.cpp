@@ -51,11 +51,13 @@ int main(int argc, char** argv) {
         if (max_depth >= 0) (preview ? config.preview : config.render).max_depth = (size_t)max_depth;
         if (have_seed) config.gpu.seed = seed;
         if (scene_path.empty() && config.loader.kind == SceneLoaderConfig::Yml) scene_path = config.loader.path;
+        if (scene_path.empty() && config.loader.kind == SceneLoaderConfig::Random) scene_path = "random";
         if (scene_path.empty()) throw TracerError(TracerError::ArgumentParsingError, "Argument parsing Error: --scene (or loader: Yml) is required");
         if (config.screen.width < 2 || config.screen.height < 2)
             throw TracerError(TracerError::Configuration, "Config Error (screen): width and height must be >= 2");
 
-        std::unique_ptr<SceneData> scene = SceneData::load_yml(scene_path, config.gpu.seed, image_dirs);
+        std::unique_ptr<SceneData> scene = scene_path == "random" ? SceneData::load_random(config.gpu.seed)   // SceneLoaderConfig::Random
+                                                                  : SceneData::load_yml(scene_path, config.gpu.seed, image_dirs);
         const Image image(config.screen.width, config.screen.height);
         const rc_camera camera = make_camera(merge_camera(scene->camera, config.camera), image);   // main.rs:95-111
         const rc_tone_map tone_map = scene->has_tone_map ? scene->tone_map : config.tone_map;       // main.rs:84-86

@@ -88,6 +88,12 @@ struct Prim {
     int type;
     double data[5];
     int material, obj, side, instance;
+    bool moving = false;
+    double motion[5] = {0, 0, 0, 0, 0};   // pos_b xyz, time_a, time_b
+    Prim(int t, std::initializer_list<double> d, int m, int o, int s, int i) : type(t), material(m), obj(o), side(s), instance(i) {
+        int k = 0;
+        for (double v : d) data[k++] = v;
+    }
 };
 
 struct TopObject {
@@ -105,7 +111,7 @@ void aabb_of(const double a[3], const double b[3], double lo[3], double hi[3]) {
 // a rectangle's data, padded Aabb and position (xy_rect.rs:50-55, xz_rect.rs:51-56, yz_rect.rs:51-56,
 // geometry_creation.rs:41-96)
 Prim rect_prim(int kind, double a0, double a1, double b0, double b1, double k, int material, double lo[3], double hi[3], double pos[3]) {
-    Prim p{kind, {a0, a1, b0, b1, k}, material, 0, 0, -1};
+    Prim p(kind, {a0, a1, b0, b1, k}, material, 0, 0, -1);
     double a[3], b[3];
     if (kind == RC_PRIM_XY_RECT) { a[0] = a0; a[1] = b0; a[2] = k - 0.0001; b[0] = a1; b[1] = b1; b[2] = k + 0.0001; pos[0] = a0; pos[1] = b0; pos[2] = k; }
     else if (kind == RC_PRIM_XZ_RECT) { a[0] = a0; a[1] = k - 0.0001; a[2] = b0; b[0] = a1; b[1] = k + 0.0001; b[2] = b1; pos[0] = a0; pos[1] = k; pos[2] = b0; }
@@ -166,6 +172,58 @@ int build_bvh(std::vector<TopObject*> objs, std::vector<rc_bvh_node>& nodes, std
         nodes[idx].bmax[a] = std::max(nodes[l].bmax[a], nodes[r].bmax[a]);
     }
     return idx;
+}
+
+// Top-level objects (canonical order) -> structure-of-arrays primitives + host BVH: what the Rust shim
+// does before rc_upload_scene.
+void flatten_objects(SceneData& sd, std::vector<TopObject*> ordered) {
+    // ---- canonical ids: objects numbered 1..N by sorted lower-cased key; id = (object << 3) | side
+    int n = 0;
+    for (TopObject* o : ordered) {
+        ++n;
+        int inst = -1;
+        if (o->has_rotate || o->has_translate) {
+            rc_instance ri;
+            std::memset(&ri, 0, sizeof(ri));
+            if (o->has_rotate) {
+                ri.flags |= 1;
+                const double rad = o->rotate_deg * PI / 180.0;   // util.rs:5-7
+                ri.sin_theta = std::sin(rad); ri.cos_theta = std::cos(rad);
+            }
+            if (o->has_translate) { ri.flags |= 2; std::memcpy(ri.offset, o->translate, sizeof(ri.offset)); }
+            inst = (int)sd.instances.size();
+            sd.instances.push_back(ri);
+        }
+        for (Prim& p : o->prims) { p.obj = n; p.instance = inst; }
+        sd.object_keys.push_back(o->key);
+    }
+    // ---- BVH over the top-level objects; primitives stored in its depth-first leaf order
+    if (!ordered.empty()) {
+        std::vector<TopObject*> order;
+        build_bvh(ordered, sd.nodes, order);
+        ordered = order;
+        std::vector<int> first(ordered.size());
+        int count = 0;
+        for (size_t i = 0; i < ordered.size(); ++i) { first[i] = count; count += (int)ordered[i]->prims.size(); }
+        for (auto& nd : sd.nodes)
+            if (nd.left < 0) {
+                const int oi = ~nd.left;
+                nd.left = ~first[oi];
+                nd.right = (int)ordered[oi]->prims.size();
+            }
+    }
+    for (TopObject* o : ordered)
+        for (const Prim& p : o->prims) {
+            sd.prim_type.push_back(p.type);
+            for (int k = 0; k < 5; ++k) sd.prim_data.push_back(p.data[k]);
+            sd.prim_material.push_back(p.material);
+            sd.prim_id.push_back(((uint32_t)p.obj << 3) | (uint32_t)p.side);
+            sd.prim_instance.push_back(p.instance);
+            for (int a = 0; a < 3; ++a) sd.prim_aabb.push_back(o->lo[a]);
+            for (int a = 0; a < 3; ++a) sd.prim_aabb.push_back(o->hi[a]);
+            for (int k = 0; k < 5; ++k) sd.prim_motion.push_back(p.motion[k]);
+            if (p.moving) sd.has_motion = true;
+        }
 }
 
 CameraConfig camera_config_of(const Node* n) {
@@ -467,7 +525,7 @@ std::unique_ptr<SceneData> SceneData::load_yml(const std::string& path, uint64_t
                 const double r = f.at("radius").as_double();
                 TopObject o;
                 o.key = key;
-                o.prims.push_back(Prim{RC_PRIM_SPHERE, {p.x, p.y, p.z, r, 0.0}, mat(f), 0, 0, -1});
+                o.prims.push_back(Prim(RC_PRIM_SPHERE, {p.x, p.y, p.z, r, 0.0}, mat(f), 0, 0, -1));
                 const double a[3] = {p.x - r, p.y - r, p.z - r}, b[3] = {p.x + r, p.y + r, p.z + r};   // sphere.rs:72-77
                 aabb_of(a, b, o.lo, o.hi);
                 o.pos[0] = p.x; o.pos[1] = p.y; o.pos[2] = p.z;
@@ -520,53 +578,9 @@ std::unique_ptr<SceneData> SceneData::load_yml(const std::string& path, uint64_t
             o.translate[0] = t.second.x; o.translate[1] = t.second.y; o.translate[2] = t.second.z;
             for (int a = 0; a < 3; ++a) { o.lo[a] += o.translate[a]; o.hi[a] += o.translate[a]; }   // translate.rs:44-47
         }
-        // ---- canonical ids: objects numbered 1..N by sorted lower-cased key; id = (object << 3) | side
         std::vector<TopObject*> ordered;
         for (auto& kv : objects) ordered.push_back(&kv.second);   // std::map iterates in sorted key order
-        int n = 0;
-        for (TopObject* o : ordered) {
-            ++n;
-            int inst = -1;
-            if (o->has_rotate || o->has_translate) {
-                rc_instance ri;
-                std::memset(&ri, 0, sizeof(ri));
-                if (o->has_rotate) {
-                    ri.flags |= 1;
-                    const double rad = o->rotate_deg * PI / 180.0;   // util.rs:5-7
-                    ri.sin_theta = std::sin(rad); ri.cos_theta = std::cos(rad);
-                }
-                if (o->has_translate) { ri.flags |= 2; std::memcpy(ri.offset, o->translate, sizeof(ri.offset)); }
-                inst = (int)sd->instances.size();
-                sd->instances.push_back(ri);
-            }
-            for (Prim& p : o->prims) { p.obj = n; p.instance = inst; }
-            sd->object_keys.push_back(o->key);
-        }
-        // ---- BVH over the top-level objects; primitives stored in its depth-first leaf order
-        if (!ordered.empty()) {
-            std::vector<TopObject*> order;
-            build_bvh(ordered, sd->nodes, order);
-            ordered = order;
-            std::vector<int> first(ordered.size());
-            int count = 0;
-            for (size_t i = 0; i < ordered.size(); ++i) { first[i] = count; count += (int)ordered[i]->prims.size(); }
-            for (auto& nd : sd->nodes)
-                if (nd.left < 0) {
-                    const int oi = ~nd.left;
-                    nd.left = ~first[oi];
-                    nd.right = (int)ordered[oi]->prims.size();
-                }
-        }
-        for (TopObject* o : ordered)
-            for (const Prim& p : o->prims) {
-                sd->prim_type.push_back(p.type);
-                for (int k = 0; k < 5; ++k) sd->prim_data.push_back(p.data[k]);
-                sd->prim_material.push_back(p.material);
-                sd->prim_id.push_back(((uint32_t)p.obj << 3) | (uint32_t)p.side);
-                sd->prim_instance.push_back(p.instance);
-                for (int a = 0; a < 3; ++a) sd->prim_aabb.push_back(o->lo[a]);
-                for (int a = 0; a < 3; ++a) sd->prim_aabb.push_back(o->hi[a]);
-            }
+        flatten_objects(*sd, ordered);
         // ---- background, yml.rs:443-453; default Sky (background_color.rs:18-25)
         rc_scene& c = sd->scene;
         const Node* bg = doc.find("background");
@@ -590,19 +604,133 @@ std::unique_ptr<SceneData> SceneData::load_yml(const std::string& path, uint64_t
         if (doc.has("tone_map")) { sd->has_tone_map = true; sd->tone_map = tone_map_of(doc.find("tone_map")); }
     } catch (const yaml_lite::ParseError& e) { throw cfg_err(e.what()); }
 
-    // ---- wire the rc_scene to the owned arrays
-    rc_scene& c = sd->scene;
-    c.n_prims = (int32_t)sd->prim_type.size();
-    c.prim_type = sd->prim_type.data(); c.prim_data = sd->prim_data.data(); c.prim_material = sd->prim_material.data();
-    c.prim_id = sd->prim_id.data(); c.prim_instance = sd->prim_instance.data(); c.prim_aabb = sd->prim_aabb.data();
-    c.n_instances = (int32_t)sd->instances.size(); c.instances = sd->instances.data();
-    c.n_materials = (int32_t)sd->materials.size(); c.materials = sd->materials.data();
-    c.n_textures = (int32_t)sd->textures.size(); c.textures = sd->textures.data();
-    for (size_t i = 0; i < sd->images.size(); ++i) sd->images[i].rgba = sd->image_pixels[i].data();
-    c.n_images = (int32_t)sd->images.size(); c.images = sd->images.data();
-    c.n_perlin = (int32_t)sd->perlin.size(); c.perlin = sd->perlin.data();
-    c.n_nodes = (int32_t)sd->nodes.size(); c.nodes = sd->nodes.data();
+    sd->wire();
     return sd;
+}
+
+namespace {
+// Sequential uniforms for procedural scenes: Philox4x32-10(counter = (n, 0, 0, 3 << 24), key = seed), four
+// 24-bit uniforms per block, consumed in order (the same stream as the Python harness's _SceneRng).  The
+// reference draws from the OS-seeded thread_rng (util.rs:9-23): its Random scene differs on every run.
+struct SceneRng {
+    uint32_t key[2];
+    uint32_t n = 0;
+    double buf[4];
+    int left = 0;
+    explicit SceneRng(uint64_t seed) { key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32); }
+    double uniform() {
+        if (left == 0) {
+            const uint32_t ctr[4] = {n++, 0u, 0u, 3u << 24};
+            uint32_t r[4];
+            philox4x32(ctr, key, r);
+            for (int k = 0; k < 4; ++k) buf[k] = (double)(r[k] >> 8) / 16777216.0;
+            left = 4;
+        }
+        return buf[4 - left--];
+    }
+    double range(double lo, double hi) { return lo + (hi - lo) * uniform(); }   // random_double_range, util.rs:19-23
+};
+}  // namespace
+
+// Random::load, scene/random.rs:25-95
+std::unique_ptr<SceneData> SceneData::load_random(uint64_t seed) {
+    std::unique_ptr<SceneData> sd(new SceneData());
+    SceneRng rng(seed);
+    std::vector<TopObject> objects;
+    objects.reserve(512);
+    auto solid = [&](double r, double g, double b) {
+        rc_texture t;
+        std::memset(&t, 0, sizeof(t));
+        t.type = RC_TEX_SOLID; t.color[0] = r; t.color[1] = g; t.color[2] = b;
+        sd->textures.push_back(t);
+        return (int)sd->textures.size() - 1;
+    };
+    auto material = [&](int kind, int texture, double param) {
+        rc_material m;
+        std::memset(&m, 0, sizeof(m));
+        m.type = kind; m.texture = texture; m.param = param;
+        sd->materials.push_back(m);
+        return (int)sd->materials.size() - 1;
+    };
+    auto sphere = [&](const double c[3], double radius, int mat, const double* c2) {
+        TopObject o;
+        char key[16];
+        std::snprintf(key, sizeof(key), "obj%04d", (int)objects.size());
+        o.key = key;
+        Prim p(RC_PRIM_SPHERE, {c[0], c[1], c[2], radius, 0.0}, mat, 0, 0, -1);
+        const double a[3] = {c[0] - radius, c[1] - radius, c[2] - radius}, b[3] = {c[0] + radius, c[1] + radius, c[2] + radius};
+        aabb_of(a, b, o.lo, o.hi);
+        if (c2) {   // create_movable_sphere, geometry_creation.rs:23-38; box = union of both ends, moving_sphere.rs:90-99
+            p.type = RC_PRIM_MOVING_SPHERE; p.moving = true;
+            p.motion[0] = c2[0]; p.motion[1] = c2[1]; p.motion[2] = c2[2]; p.motion[3] = 0.0; p.motion[4] = 1.0;
+            for (int k = 0; k < 3; ++k) { o.lo[k] = std::min(o.lo[k], c2[k] - radius); o.hi[k] = std::max(o.hi[k], c2[k] + radius); }
+        }
+        o.prims.push_back(p);
+        o.pos[0] = c[0]; o.pos[1] = c[1]; o.pos[2] = c[2];
+        objects.push_back(o);
+    };
+    const int even = solid(0.2, 0.3, 0.1), odd = solid(0.9, 0.9, 0.9);
+    rc_texture chk;
+    std::memset(&chk, 0, sizeof(chk));
+    chk.type = RC_TEX_CHECKER; chk.a = even; chk.b = odd; chk.scale = 10.0;
+    sd->textures.push_back(chk);
+    const double ground[3] = {0.0, -1000.0, 0.0};
+    sphere(ground, 1000.0, material(RC_MAT_LAMBERTIAN, (int)sd->textures.size() - 1, 0.0), nullptr);
+    for (int a = -11; a < 11; ++a)
+        for (int b = -11; b < 11; ++b) {
+            const double choose_mat = rng.uniform();
+            const double cx = a + 0.9 * rng.uniform();
+            const double cz = b + 0.9 * rng.uniform();
+            const double center[3] = {cx, 0.2, cz};
+            if (std::sqrt((cx - 4.0) * (cx - 4.0) + (0.2 - 0.2) * (0.2 - 0.2) + cz * cz) > 0.9) {
+                if (choose_mat < 0.8) {   // diffuse, moving
+                    double c1[3], c2[3];
+                    for (double& v : c1) v = rng.uniform();
+                    for (double& v : c2) v = rng.uniform();
+                    const double dy = rng.range(0.0, 0.5);
+                    const double center2[3] = {cx, 0.2 + dy, cz};
+                    sphere(center, 0.2, material(RC_MAT_LAMBERTIAN, solid(c1[0] * c2[0], c1[1] * c2[1], c1[2] * c2[2]), 0.0), center2);
+                } else if (choose_mat > 0.95) {   // metal
+                    double al[3];
+                    for (double& v : al) v = rng.range(0.5, 1.0);
+                    const double fuzz = rng.range(0.0, 0.5);
+                    sphere(center, 0.2, material(RC_MAT_METAL, solid(al[0], al[1], al[2]), fuzz), nullptr);
+                } else sphere(center, 0.2, material(RC_MAT_DIELECTRIC, 0, 1.5), nullptr);   // glass
+            }
+        }
+    const double b1[3] = {0.0, 1.0, 0.0}, b2[3] = {-4.0, 1.0, 0.0}, b3[3] = {4.0, 1.0, 0.0};
+    sphere(b1, 1.0, material(RC_MAT_DIELECTRIC, 0, 1.5), nullptr);
+    sphere(b2, 1.0, material(RC_MAT_LAMBERTIAN, solid(0.4, 0.2, 0.1), 0.0), nullptr);
+    sphere(b3, 1.0, material(RC_MAT_METAL, solid(0.7, 0.6, 0.5), 0.0), nullptr);
+    std::vector<TopObject*> ordered;
+    for (auto& o : objects) ordered.push_back(&o);
+    flatten_objects(*sd, ordered);
+    rc_scene& c = sd->scene;
+    c.bg_type = RC_BG_SKY;
+    c.bg_a[0] = c.bg_a[1] = c.bg_a[2] = 1.0;
+    c.bg_b[0] = 0.5; c.bg_b[1] = 0.7; c.bg_b[2] = 1.0;
+    CameraConfig& cam = sd->camera;
+    cam.has_vfov = cam.has_aperture = cam.has_focus_distance = cam.has_pos = cam.has_look_at = true;
+    cam.vfov = 20.0; cam.aperture = 0.1; cam.focus_distance = 10.0;
+    cam.pos = Vec3{0.0, 2.0, 10.0}; cam.look_at = Vec3{0.0, 0.0, 0.0};
+    sd->wire();
+    return sd;
+}
+
+void SceneData::wire() {
+    // ---- wire the rc_scene to the owned arrays
+    rc_scene& c = scene;
+    c.n_prims = (int32_t)prim_type.size();
+    c.prim_type = prim_type.data(); c.prim_data = prim_data.data(); c.prim_material = prim_material.data();
+    c.prim_id = prim_id.data(); c.prim_instance = prim_instance.data(); c.prim_aabb = prim_aabb.data();
+    c.n_instances = (int32_t)instances.size(); c.instances = instances.data();
+    c.n_materials = (int32_t)materials.size(); c.materials = materials.data();
+    c.n_textures = (int32_t)textures.size(); c.textures = textures.data();
+    for (size_t i = 0; i < images.size(); ++i) images[i].rgba = image_pixels[i].data();
+    c.n_images = (int32_t)images.size(); c.images = images.data();
+    c.n_perlin = (int32_t)perlin.size(); c.perlin = perlin.data();
+    c.n_nodes = (int32_t)nodes.size(); c.nodes = nodes.data();
+    c.prim_motion = has_motion ? prim_motion.data() : nullptr;
 }
 
 std::string SceneData::to_json() const {
@@ -613,6 +741,7 @@ std::string SceneData::to_json() const {
     o << ",\"prim_id\":"; json_ints(o, prim_id.data(), prim_id.size());
     o << ",\"prim_instance\":"; json_ints(o, prim_instance.data(), prim_instance.size());
     o << ",\"prim_aabb\":"; json_doubles(o, prim_aabb.data(), prim_aabb.size());
+    o << ",\"prim_motion\":"; json_doubles(o, prim_motion.data(), prim_motion.size());
     o << ",\"instances\":[";
     for (size_t i = 0; i < instances.size(); ++i) {
         const double v[5] = {instances[i].sin_theta, instances[i].cos_theta, instances[i].offset[0], instances[i].offset[1], instances[i].offset[2]};

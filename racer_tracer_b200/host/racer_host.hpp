@@ -110,7 +110,8 @@ rc_camera make_camera(const CameraData& cam, const Image& image);
 struct SceneData {
     // owned arrays the rc_scene points into
     std::vector<int32_t> prim_type, prim_material, prim_instance;
-    std::vector<double> prim_data, prim_aabb;
+    std::vector<double> prim_data, prim_aabb, prim_motion;
+    bool has_motion = false;
     std::vector<uint32_t> prim_id;
     std::vector<rc_instance> instances;
     std::vector<rc_material> materials;
@@ -133,6 +134,10 @@ struct SceneData {
     // FailedToOpenImage exactly where the reference returns them.
     static std::unique_ptr<SceneData> load_yml(const std::string& path, uint64_t seed = 0,
                                                const std::vector<std::string>& image_dirs = {});
+    // Random::load (scene/random.rs:25-95): checkered ground, 22 x 22 small spheres (diffuse ones move), three
+    // large spheres; its own camera (vfov 20, aperture 0.1, focus 10).  Deterministic in `seed`.
+    static std::unique_ptr<SceneData> load_random(uint64_t seed = 0);
+    void wire();                   // point `scene` at the owned arrays
     std::string to_json() const;   // flat tables as JSON (tests compare them with the Python harness)
 };
 

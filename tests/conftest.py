@@ -10,7 +10,8 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 SCENES = ["three_balls", "emissive", "noise_and_textures", "cornell_box", "clown"]   # the BASELINE configs
 # + the reference's Sandbox scene (Box / RotateY / Translate instances) in YAML form
-SCENES_X = SCENES + ["sandbox_boxes"]
+# + the reference's Random scene (scene/random.rs: ~480 spheres, moving spheres + ray time, lens), §8(f)-4
+SCENES_X = SCENES + ["sandbox_boxes", "random"]
 
 
 def pytest_configure(config):
@@ -18,6 +19,8 @@ def pytest_configure(config):
 
 
 def scene_path(name):
+    if name == "random":      # SceneLoaderConfig::Random: generated, not a file
+        return name
     return os.path.join(GOLDEN, "scenes", name + ".yml")
 
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     for name in declared_symbols():
         assert name in exported, f"{name} is declared in racer_cuda.h but not exported"
         assert hasattr(cuda_lib, name)
-    assert cuda_lib.rc_abi_version() == 1
+    assert cuda_lib.rc_abi_version() == 2
     assert not any(s.startswith("oracle_") for s in exported), "the product must not contain the oracle"
 
 

@@ -56,6 +56,7 @@ def test_flattened_scene_equals_the_python_harness(racer_render, tmp_path, cfg, 
     assert s["prim_instance"] == fs.np["prim_instance"].tolist()
     assert s["prim_data"] == fs.np["prim_data"].ravel().tolist()          # bit-exact f64
     assert s["prim_aabb"] == fs.np["prim_aabb"].ravel().tolist()
+    assert s["prim_motion"] == fs.np["prim_motion"].ravel().tolist()
     assert s["object_keys"] == fs.object_keys
     assert [(m["type"], m["texture"], m["param"][0]) for m in s["materials"]] == [(m.type, m.texture, m.param) for m in fs.materials]
     assert [(t["type"], t["a"], t["b"], t["v"]) for t in s["textures"]] == \

@@ -482,3 +482,36 @@ def test_preview_renderer_semantics(cfg):
     assert np.array_equal(tile[0:3, 0:3], np.broadcast_to(tile[0, 0], (3, 3, 3)))
     one = O.render_preview(job, p, 1, 1, tiles=(5, 5))
     assert np.allclose(one, O.render(job, p, tiles=(5, 5)), rtol=0, atol=1e-12)
+
+
+def test_moving_sphere_and_random_scene(cfg):
+    """MovingSphere (src/geometry/moving_sphere.rs): centre = pos + (time - ta)/(tb - ta) (pos_b - pos), the
+    Sphere quadratic around it, box = union of both ends; Random::load (src/scene/random.rs) builds ~480
+    spheres of which the diffuse ones move; its camera has an aperture, so the lens is sampled."""
+    from oracle import oracle as O
+    job = harness.prepare_job("random", cfg, 64, 48, seed=3)
+    fs = job.scene
+    types = fs.np["prim_type"]
+    assert fs.c.n_prims > 400 and fs.c.n_nodes == 2 * fs.c.n_prims - 1
+    mov = np.flatnonzero(types == capi.RC_PRIM_MOVING_SPHERE)
+    assert 0.7 < len(mov) / (fs.c.n_prims - 4) < 0.9                   # 80 % of the small spheres
+    i = int(mov[0])
+    pos, r = fs.np["prim_data"][i, :3], fs.np["prim_data"][i, 3]
+    pos_b, ta, tb = fs.np["prim_motion"][i, :3], fs.np["prim_motion"][i, 3], fs.np["prim_motion"][i, 4]
+    assert (ta, tb) == (0.0, 1.0) and pos_b[0] == pos[0] and pos_b[2] == pos[2] and 0.0 <= pos_b[1] - pos[1] < 0.5
+    box = fs.np["prim_aabb"][i]
+    assert np.allclose(box[:3], np.minimum(pos, pos_b) - r) and np.allclose(box[3:], np.maximum(pos, pos_b) + r)
+    # a ray straight down onto the sphere hits its top at the centre of that ray time; fixed jitter = time_a
+    out = (C.c_double * 10)()
+    org = O.d3([pos[0], pos[1] + 5.0, pos[2]])
+    assert O.lib().oracle_prim_hit(fs.ptr, i, org, O.d3([0.0, -1.0, 0.0]), 0.001, 1e30, out) == 1
+    assert abs(out[0] - (5.0 - r)) < 1e-12 and abs(out[5] - 1.0) < 1e-12   # t, normal.y at time 0
+    # the generator is deterministic in the seed and differs between seeds
+    again = harness.prepare_job("random", cfg, 64, 48, seed=3).scene
+    other = harness.prepare_job("random", cfg, 64, 48, seed=4).scene
+    assert np.array_equal(again.np["prim_data"], fs.np["prim_data"]) and not np.array_equal(other.np["prim_data"][:8], fs.np["prim_data"][:8])
+    assert job.camera.lens_radius == 0.05 and job.camera.focus_distance == 10.0
+    # motion blur: a moving sphere's pixels differ between time-sampled and time-frozen renders
+    p = harness.make_params(64, 48, 4, 5, seed=1)
+    img = O.render(job, p)
+    assert np.isfinite(img).all() and img.std() > 0.05
