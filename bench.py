@@ -42,7 +42,13 @@ WORKLOADS = {
     "three_balls_600_200spp": ("three_balls", 600, 600, 200, 20, "tiles"),
     "emissive_600_200spp": ("emissive", 600, 600, 200, 20, "tiles"),
     "noise_and_textures_600_200spp": ("noise_and_textures", 600, 600, 200, 20, "tiles"),
+    # the reference's Random loader (scene/random.rs): ~480 spheres, moving spheres, lens; BVH traversal
+    "random_1080p_256spp": ("random", 1920, 1080, 256, 20, "tiles"),
 }
+
+
+def scene_file(scene):
+    return scene if scene == "random" else os.path.join(ROOT, "tests", "golden", "scenes", scene + ".yml")
 
 # Algorithmic FP32 flop cost table, SURVEY.md §8(d) (FMA = 2, SFU = 1)
 COST = {
@@ -132,7 +138,7 @@ def run_reference(args, wl_name):
         return 0
     scene, w, h, spp, depth, split = WORKLOADS[wl_name]
     cfg = harness.load_config(os.path.join(ROOT, "tests", "golden", "config.yml"))
-    job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".yml"), cfg, w, h)
+    job = harness.prepare_job(scene_file(scene), cfg, w, h)
     params = harness.make_params(w, h, spp, depth, seed=0, sampler=capi.RC_SAMPLER_REJECTION)
     cores = os.cpu_count() or 1
     # bounded sample per step: ~4 s of CPU work, sized from a 2-spp probe of the same frame
@@ -176,6 +182,7 @@ def main():
     ap.add_argument("--specialize", type=int, default=int(os.environ.get("RC_SPECIALIZE", "1")), choices=[0, 1, 2],
                     help="1: scene compiled into the megakernel with NVRTC (default); 0: precompiled kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lbvh", action="store_true", help="rebuild the BVH on the GPU (rc_build_lbvh) after the upload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -202,10 +209,12 @@ def main():
         spp = args.spp
     split = capi.RC_SPLIT_TILES if split_name == "tiles" else capi.RC_SPLIT_SAMPLES
     cfg = harness.load_config(os.path.join(ROOT, "tests", "golden", "config.yml"))
-    job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", scene + ".yml"), cfg, w, h)
+    job = harness.prepare_job(scene_file(scene), cfg, w, h)
     variant = capi.RC_VARIANT_MEGAKERNEL if args.variant == "megakernel" else capi.RC_VARIANT_WAVEFRONT
     sampler = capi.RC_SAMPLER_DIRECT if args.sampler == "direct" else capi.RC_SAMPLER_REJECTION
     spec = args.specialize if (args.variant == "megakernel" and args.sampler == "direct" and args.rng_rounds == 10) else 0
+    if spec == 1 and args.workload.startswith("random"):
+        spec = 2     # ~480 primitives do not fit the constant-bank path: precompiled BVH kernels
     params = harness.make_params(w, h, spp, depth, seed=0, variant=variant, sampler=sampler, split=split,
                                  rank=rank, world=world, rng_rounds=args.rng_rounds, specialize=spec)
 
@@ -213,6 +222,8 @@ def main():
     stream = torch.cuda.current_stream()
     r.set_stream(stream.cuda_stream)
     r.upload(job)
+    if args.lbvh:
+        r.build_lbvh()
     n = w * h * 3
     accum = torch.zeros(n, dtype=torch.float32, device="cuda")
     rgb = torch.empty(n, dtype=torch.float32, device="cuda")
@@ -284,6 +295,8 @@ def main():
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         r.upload(job)                       # host -> device: scene tables + camera
+        if args.lbvh:
+            r.build_lbvh()
         if world == 1:
             out = r.render(e2e_params, out=host_out)   # render + device -> host of the gamma'd f64 image
         else:
@@ -314,6 +327,7 @@ def main():
                        "max_depth": depth, "variant": args.variant, "sampler": args.sampler,
                        "rng": f"philox2x32-{args.rng_rounds}", "split": split_name,
                        "kernel": "scene-specialised (NVRTC)" if spec else "precompiled",
+                       "bvh": "gpu-lbvh" if args.lbvh else ("host" if job.scene.c.n_nodes else "none"),
                        "l2": "256 MiB buffer written between timed iterations (flush)",
                        "parallelism": f"tiles{world}" if split_name == "tiles" else f"samples{world}"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(scene_bytes),

@@ -261,6 +261,20 @@ int rc_set_stream(rc_ctx* ctx, void* cuda_stream);
  * (src/main.rs:178-183, src/bvh_node.rs:176-205). */
 int rc_upload_scene(rc_ctx* ctx, const rc_scene* scene);
 
+/* Build the acceleration structure of the uploaded scene ON THE GPU: a linear BVH over the
+ * Morton codes of the top-level objects' Aabb centres (prim_aabb must have been supplied), in
+ * the traversal layout the kernels read.  Replaces BoundingVolumeHirearchy::new / Node::build
+ * (src/bvh_node.rs:31-82,142-170) and the host rebuild after an edit (bvh_node.rs:176-205); the
+ * nodes passed to rc_upload_scene, if any, are superseded.  Leaves keep the reference's semantics:
+ * one top-level object each, its stored Aabb is its cull volume (bvh_node.rs:119). */
+int rc_build_lbvh(rc_ctx* ctx);
+
+/* The acceleration structure currently on the device, as rc_bvh_node records in pre-order, and
+ * prim_order[i] = index (in the uploaded arrays) of the primitive now stored at position i — so
+ * that a host (or the parity oracle) can trace the very same tree.  Returns the node count (0 for
+ * the linear modes); fills only the arrays whose capacity suffices. */
+int rc_get_bvh(rc_ctx* ctx, rc_bvh_node* nodes, int32_t node_capacity, int32_t* prim_order, int32_t prim_capacity);
+
 /* Replaces `camera_data: &CameraSharedData` (src/renderer.rs:93). */
 int rc_set_camera(rc_ctx* ctx, const rc_camera* camera);
 

@@ -13,7 +13,10 @@
 
 #include "rt_kernels.cuh"
 #include "rt_wavefront.cuh"
+#include <algorithm>
+
 #include "rc_multi.cuh"
+#include "rc_lbvh.cuh"
 #include "rc_spec.cuh"
 
 namespace {
@@ -100,6 +103,11 @@ struct rc_ctx {
     bool has_textures = false;   // any primitive whose texture is not a solid colour
     int mats_mask = 0xF;         // material kinds the scene uses
     std::string spec_source;     // generated source of the scene-specialised kernel ("" = not generated yet)
+    std::vector<LbvhObject> objects, objects_next;   // top-level objects of the uploaded scene (rc_build_lbvh)
+    std::vector<int> prim_order;       // device primitive i = uploaded primitive prim_order[i] (empty: identity)
+    bool lbvh = false;
+    int n_prims = 0, n_perlin = 0;
+    bool instanced = false;
     rc_camera camera;
     rc_stats stats;
     MultiState multi;
@@ -715,6 +723,25 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     ctx->mats_mask = t.mats_mask;
     ctx->spec_source.clear();
     ctx->aov.n_prims = s->n_prims; ctx->aov.n_nodes = s->n_nodes;
+    // top-level objects = runs of primitives that share an object id (id >> 3; a Box's six sides) and a stored Aabb
+    ctx->objects.clear();
+    ctx->prim_order.clear();
+    ctx->lbvh = false;
+    ctx->n_prims = s->n_prims; ctx->n_perlin = s->n_perlin;
+    ctx->instanced = !t.instances.empty();
+    if (s->prim_aabb)
+        for (int i = 0; i < s->n_prims; ++i) {
+            const double* b = s->prim_aabb + 6 * (size_t)i;
+            if (!ctx->objects.empty()) {
+                LbvhObject& o = ctx->objects.back();
+                if ((s->prim_id[i] >> 3) == (s->prim_id[o.first] >> 3) && o.count < 127 && std::memcmp(o.lo, b, 3 * sizeof(double)) == 0 &&
+                    std::memcmp(o.hi, b + 3, 3 * sizeof(double)) == 0) { ++o.count; continue; }
+            }
+            LbvhObject o;
+            std::memcpy(o.lo, b, 3 * sizeof(double)); std::memcpy(o.hi, b + 3, 3 * sizeof(double));
+            o.first = i; o.count = 1;
+            ctx->objects.push_back(o);
+        }
     std::vector<DevPrim>& prims = t.prims; std::vector<DevPrim>& prims_lin = t.prims_lin;
     std::vector<DevPrimD>& prims_d = t.prims_d; std::vector<int>& kinds = t.kinds; std::vector<uint32_t>& ids = t.ids;
     std::vector<DevNode>& nodes = t.nodes; std::vector<DevNodeD>& nodes_d = t.nodes_d;
@@ -897,6 +924,124 @@ int rc_render_preview(rc_ctx* ctx, const rc_params* p, int32_t scale_w, int32_t 
     CUDA_TRY(cudaMemcpyAsync(out_rgb, d0.out64.p, n_out * 3 * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
     CUDA_TRY(cudaStreamSynchronize(d0.stream));
     return RC_OK;
+}
+
+int rc_build_lbvh(rc_ctx* ctx) {
+    if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
+    if (!ctx->has_scene) return fail(RC_ERR_STATE, "upload a scene first");
+    const int n = (int)ctx->objects.size();
+    if (n < 1) return fail(RC_ERR_INVALID, "the uploaded scene has no prim_aabb: nothing to build a BVH over");
+    int padded = 1;
+    while (padded < n) padded <<= 1;
+    const int n_nodes = 2 * n - 1, np = ctx->n_prims;
+    const unsigned B = 256;
+    auto grid = [&](int count) { return (unsigned)((count + (int)B - 1) / (int)B); };
+    for (auto& d : ctx->devs) {
+        CUDA_TRY(cudaSetDevice(d.device));
+        DevBuf<LbvhObject> obj;
+        DevBuf<unsigned long long> keys;
+        DevBuf<long long> bounds;
+        DevBuf<LbvhNode> tree;
+        DevBuf<int> leaf_parent, arrived, first_new, order, preorder;
+        CUDA_TRY(obj.assign(ctx->objects));
+        CUDA_TRY(keys.resize((size_t)padded));
+        CUDA_TRY(bounds.resize(6));
+        CUDA_TRY(tree.resize((size_t)(n > 1 ? n - 1 : 1)));
+        CUDA_TRY(leaf_parent.resize((size_t)n));
+        CUDA_TRY(arrived.resize((size_t)n));
+        CUDA_TRY(first_new.resize((size_t)n));
+        CUDA_TRY(order.resize((size_t)np));
+        CUDA_TRY(preorder.resize((size_t)n_nodes));
+        const long long init[6] = {0x7fffffffffffffffLL, 0x7fffffffffffffffLL, 0x7fffffffffffffffLL,
+                                   (long long)0x8000000000000000ULL, (long long)0x8000000000000000ULL, (long long)0x8000000000000000ULL};
+        CUDA_TRY(cudaMemcpyAsync(bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, d.stream));
+        CUDA_TRY(cudaMemsetAsync(arrived.p, 0, (size_t)n * sizeof(int), d.stream));
+        lbvh_bounds<<<grid(n), B, 0, d.stream>>>(obj.p, n, bounds.p);
+        lbvh_morton<<<grid(padded), B, 0, d.stream>>>(obj.p, n, padded, bounds.p, keys.p);
+        if (padded <= LBVH_SMEM_KEYS) {
+            const size_t smem = (size_t)padded * sizeof(unsigned long long);
+            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(lbvh_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            lbvh_sort_smem<<<1, 1024, smem, d.stream>>>(keys.p, padded);
+        } else {
+            for (int k = 2; k <= padded; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) lbvh_sort_step<<<grid(padded), B, 0, d.stream>>>(keys.p, padded, j, k);
+        }
+        if (n > 1) {
+            lbvh_topology<<<grid(n - 1), B, 0, d.stream>>>(keys.p, n, tree.p, leaf_parent.p);
+            lbvh_fit<<<grid(n), B, 0, d.stream>>>(keys.p, obj.p, n, tree.p, leaf_parent.p, arrived.p);
+        }
+        lbvh_prim_offsets<<<1, 1024, 0, d.stream>>>(keys.p, obj.p, n, first_new.p);
+        lbvh_prim_order<<<grid(n), B, 0, d.stream>>>(keys.p, obj.p, n, first_new.p, order.p);
+        DevBuf<DevNode> nodes;
+        DevBuf<DevNodeD> nodes_d;
+        CUDA_TRY(nodes.resize((size_t)n_nodes));
+        CUDA_TRY(nodes_d.resize((size_t)n_nodes));
+        lbvh_emit<<<grid(n_nodes), B, 0, d.stream>>>(keys.p, obj.p, n, tree.p, leaf_parent.p, first_new.p, nodes.p, nodes_d.p, preorder.p);
+        // primitive tables into the tree's depth-first leaf order
+        DevBuf<DevPrim> prims;
+        DevBuf<DevPrimD> prims_d;
+        DevBuf<int> kind, inst;
+        DevBuf<uint32_t> id;
+        CUDA_TRY(prims.resize((size_t)np)); CUDA_TRY(prims_d.resize((size_t)np)); CUDA_TRY(kind.resize((size_t)np));
+        CUDA_TRY(inst.resize((size_t)np)); CUDA_TRY(id.resize((size_t)np));
+        lbvh_gather<<<grid(np), B, 0, d.stream>>>(d.prims.p, prims.p, order.p, np);
+        lbvh_gather<<<grid(np), B, 0, d.stream>>>(d.prims_d.p, prims_d.p, order.p, np);
+        lbvh_gather<<<grid(np), B, 0, d.stream>>>(d.prim_kind.p, kind.p, order.p, np);
+        lbvh_gather<<<grid(np), B, 0, d.stream>>>(d.prim_inst.p, inst.p, order.p, np);
+        lbvh_gather<<<grid(np), B, 0, d.stream>>>(d.prim_id.p, id.p, order.p, np);
+        CUDA_TRY(cudaGetLastError());
+        if (&d == &ctx->devs[0]) {   // the composed permutation and the object table follow the primitives
+            std::vector<int> ord((size_t)np);
+            CUDA_TRY(cudaMemcpyAsync(ord.data(), order.p, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            if (ctx->prim_order.empty()) ctx->prim_order = ord;
+            else { std::vector<int> c((size_t)np); for (int i = 0; i < np; ++i) c[i] = ctx->prim_order[ord[i]]; ctx->prim_order = c; }
+            std::vector<LbvhObject> moved;
+            std::vector<int> seen((size_t)np, -1);
+            for (int i = 0; i < np; ++i) seen[ord[i]] = i;
+            for (const LbvhObject& o : ctx->objects) { LbvhObject q = o; q.first = seen[o.first]; moved.push_back(q); }
+            std::sort(moved.begin(), moved.end(), [](const LbvhObject& a, const LbvhObject& b) { return a.first < b.first; });
+            ctx->objects_next = moved;
+        }
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        std::swap(d.prims, prims); std::swap(d.prims_d, prims_d); std::swap(d.prim_kind, kind); std::swap(d.prim_inst, inst); std::swap(d.prim_id, id);
+        std::swap(d.nodes, nodes); std::swap(d.nodes_d, nodes_d);
+        prims.release(); prims_d.release(); kind.release(); inst.release(); id.release(); nodes.release(); nodes_d.release();
+        obj.release(); keys.release(); bounds.release(); tree.release(); leaf_parent.release(); arrived.release(); first_new.release();
+        order.release(); preorder.release();
+    }
+    ctx->objects = ctx->objects_next;
+    ctx->kp.n_nodes = n_nodes;
+    ctx->aov.n_nodes = n_nodes;
+    // the traversal modes: shared memory when nodes + primitives (+ Perlin tables) fit, global memory otherwise
+    const size_t perlin_bytes = (size_t)ctx->n_perlin * (256 * 16 + 768);
+    const size_t bvh_bytes = (size_t)n_nodes * sizeof(DevNode) + (size_t)np * sizeof(DevPrim);
+    ctx->mode = bvh_bytes + perlin_bytes <= 200 * 1024 ? RT_MODE_SMEM_BVH : RT_MODE_GLOBAL_BVH;
+    ctx->smem_bytes = perlin_bytes + (ctx->mode == RT_MODE_SMEM_BVH ? bvh_bytes : 0);
+    ctx->spec_source.clear();
+    ctx->lbvh = true;
+    CUDA_TRY(cudaSetDevice(ctx->devs[0].device));
+    return RC_OK;
+}
+
+int rc_get_bvh(rc_ctx* ctx, rc_bvh_node* nodes, int32_t node_capacity, int32_t* prim_order, int32_t prim_capacity) {
+    if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
+    if (!ctx->has_scene) return fail(RC_ERR_STATE, "upload a scene first");
+    const int n_nodes = ctx->kp.n_nodes, np = ctx->n_prims;
+    if (nodes && node_capacity >= n_nodes && n_nodes > 0) {
+        DeviceState& d = ctx->devs[0];
+        CUDA_TRY(cudaSetDevice(d.device));
+        std::vector<DevNodeD> h((size_t)n_nodes);
+        CUDA_TRY(cudaMemcpy(h.data(), d.nodes_d.p, (size_t)n_nodes * sizeof(DevNodeD), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n_nodes; ++i) {
+            for (int a = 0; a < 3; ++a) { nodes[i].bmin[a] = h[i].lo[a]; nodes[i].bmax[a] = h[i].hi[a]; }
+            if (h[i].leaf >= 0) { nodes[i].left = ~(h[i].leaf & 0xffffff); nodes[i].right = h[i].leaf >> 24; }
+            else { nodes[i].left = i + 1; nodes[i].right = h[i + 1].skip; }   // right child = first node after the left subtree
+        }
+    }
+    if (prim_order && prim_capacity >= np)
+        for (int i = 0; i < np; ++i) prim_order[i] = ctx->prim_order.empty() ? i : ctx->prim_order[i];
+    return n_nodes;
 }
 
 int rc_postprocess(rc_ctx* ctx, const rc_tone_map* tm, const double* rgb, int32_t width, int32_t height,

@@ -729,6 +729,35 @@ def preview_scales(cfg: "Config", width: int, height: int) -> tuple[int, int]:
             highest_divisible(height // max(1, pv.num_threads_height), max(1, pv.scale)))
 
 
+def with_bvh(job: "Job", nodes, prim_order) -> "Job":
+    """A copy of `job` whose primitives are permuted by prim_order and whose BVH is `nodes` — the tree a
+    GPU build (rc_build_lbvh / rc_get_bvh) produced — so the oracle traces the very same structure."""
+    import copy
+    fs, src = FlatScene(), job.scene
+    fs.c = rc_scene.from_buffer_copy(src.c)
+    fs.keep = list(src.keep)
+    order = np.asarray(prim_order, dtype=np.int64)
+    fs.np = {k: np.ascontiguousarray(v[order]) for k, v in src.np.items()}
+    c = fs.c
+    c.prim_type = fs.np["prim_type"].ctypes.data_as(C.POINTER(C.c_int32))
+    c.prim_data = fs.np["prim_data"].ctypes.data_as(C.POINTER(C.c_double))
+    c.prim_material = fs.np["prim_material"].ctypes.data_as(C.POINTER(C.c_int32))
+    c.prim_id = fs.np["prim_id"].ctypes.data_as(C.POINTER(C.c_uint32))
+    c.prim_instance = fs.np["prim_instance"].ctypes.data_as(C.POINTER(C.c_int32))
+    c.prim_aabb = fs.np["prim_aabb"].ctypes.data_as(C.POINTER(C.c_double))
+    if src.c.prim_motion:
+        c.prim_motion = fs.np["prim_motion"].ctypes.data_as(C.POINTER(C.c_double))
+    arr = (rc_bvh_node * max(1, len(nodes)))(*nodes)
+    fs.keep.append(arr)
+    c.n_nodes, c.nodes = len(nodes), arr
+    fs.nodes = list(nodes)
+    for name in ("images", "textures", "materials", "instances", "object_keys", "camera_cfg", "tone_map_cfg"):
+        setattr(fs, name, getattr(src, name, None))
+    out = copy.copy(job)
+    out.scene = fs
+    return out
+
+
 def partition(params: rc_params, part: int, parts: int) -> dict:
     """rc_partition: the share of participant `part` of `parts` (host arithmetic only)."""
     lib = capi.load()
@@ -806,6 +835,23 @@ class CudaRenderer:
     def upload(self, job: Job):
         capi.check(self.lib, self.lib.rc_upload_scene(self.ctx, job.scene.ptr))
         capi.check(self.lib, self.lib.rc_set_camera(self.ctx, C.byref(job.camera)))
+
+    def build_lbvh(self):
+        """rc_build_lbvh: rebuild the uploaded scene's BVH on the GPU (LBVH over Morton codes)."""
+        capi.check(self.lib, self.lib.rc_build_lbvh(self.ctx))
+
+    def get_bvh(self, n_prims: int):
+        """rc_get_bvh -> (list of rc_bvh_node in pre-order, prim_order int32 array of length n_prims)."""
+        n = self.lib.rc_get_bvh(self.ctx, None, 0, None, 0)
+        if n < 0:
+            capi.check(self.lib, n)
+        nodes = (rc_bvh_node * max(1, n))()
+        order = np.full(n_prims, -1, dtype=np.int32)
+        got = self.lib.rc_get_bvh(self.ctx, nodes, n, order.ctypes.data_as(C.POINTER(C.c_int32)), n_prims)
+        if got < 0:
+            capi.check(self.lib, got)
+        assert got == n and (order >= 0).all()
+        return [nodes[i] for i in range(n)], order
 
     def render(self, params: rc_params, cancel=None, out: np.ndarray | None = None) -> np.ndarray:
         """rc_render into `out` ((H, W, 3) float64, C-contiguous; e.g. a pinned buffer) or a new array."""
