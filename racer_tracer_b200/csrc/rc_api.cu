@@ -199,6 +199,7 @@ void set_skip(const rc_scene* s, int i, int skip, std::vector<int>& out) {
     }
 }
 
+#define RC_SMEM_STAGE_LIMIT (36 * 1024)
 int pick_mode(const rc_scene* s, bool rects_fit, bool instanced, size_t& smem_bytes) {
     const char* force = std::getenv("RC_SCENE_MODE");  // experiments: const | smem | global | smemlin
     size_t perlin_bytes = (size_t)s->n_perlin * (256 * 16 + 768);
@@ -206,7 +207,10 @@ int pick_mode(const rc_scene* s, bool rects_fit, bool instanced, size_t& smem_by
     int mode;
     // instanced scenes always traverse the BVH: its (possibly non-bounding, Q14) boxes are part of the semantics
     if (!instanced && s->n_prims <= RT_MAX_CONST_PRIMS && rects_fit) mode = RT_MODE_CONST_LINEAR;
-    else if (s->n_nodes > 0 && bvh_bytes + perlin_bytes <= 200 * 1024) mode = RT_MODE_SMEM_BVH;
+    // shared-memory staging pays only while it does not cost occupancy (profiles/r01_random_bvh_v1_ncu.md:
+    // 62 KB per CTA left 12 warps per SM and 44 % issue utilisation; the same tables read through L1 ran 1.5x
+    // faster): keep the per-CTA copy below a sixth of the SM's 227 KB, larger tables are read through L1/L2
+    else if (s->n_nodes > 0 && bvh_bytes + perlin_bytes <= RC_SMEM_STAGE_LIMIT) mode = RT_MODE_SMEM_BVH;
     else if (s->n_nodes > 0) mode = RT_MODE_GLOBAL_BVH;
     else mode = RT_MODE_SMEM_LINEAR;
     if (force && !instanced) {
@@ -1016,7 +1020,7 @@ int rc_build_lbvh(rc_ctx* ctx) {
     // the traversal modes: shared memory when nodes + primitives (+ Perlin tables) fit, global memory otherwise
     const size_t perlin_bytes = (size_t)ctx->n_perlin * (256 * 16 + 768);
     const size_t bvh_bytes = (size_t)n_nodes * sizeof(DevNode) + (size_t)np * sizeof(DevPrim);
-    ctx->mode = bvh_bytes + perlin_bytes <= 200 * 1024 ? RT_MODE_SMEM_BVH : RT_MODE_GLOBAL_BVH;
+    ctx->mode = bvh_bytes + perlin_bytes <= RC_SMEM_STAGE_LIMIT ? RT_MODE_SMEM_BVH : RT_MODE_GLOBAL_BVH;
     ctx->smem_bytes = perlin_bytes + (ctx->mode == RT_MODE_SMEM_BVH ? bvh_bytes : 0);
     ctx->spec_source.clear();
     ctx->lbvh = true;
