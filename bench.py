@@ -231,12 +231,43 @@ def main():
 
     launches = [0]
 
-    def step():
+    # Tile split over several processes: rank 0 owns the frame buffer (two of them, alternating, so that a
+    # rank already tracing the next step never stores into the buffer rank 0 is still reading) and every rank
+    # maps it (CUDA IPC); the render kernel of every rank STORES its tiles into it over NVLink as they finish.
+    # The only exchange step left is a one-element all-reduce that orders rank 0's stream after the others.
+    shared = None
+    if world > 1 and split == capi.RC_SPLIT_TILES and variant == capi.RC_VARIANT_MEGAKERNEL and not os.environ.get("RC_BENCH_NCCL_GATHER"):
+        shared = []
+        for _ in range(2):
+            if rank == 0:
+                ptr, handle = r.shared_alloc(n * 4)
+                hbuf = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+            else:
+                hbuf = torch.empty(64, dtype=torch.uint8, device="cuda")
+            dist.broadcast(hbuf, 0)
+            if rank != 0:
+                ptr = r.shared_open(bytes(hbuf.cpu().tolist()))
+            shared.append(ptr)
+    join = torch.zeros(1, dtype=torch.float32, device="cuda")
+    step_no = [0]
+
+    def step(p=None):
+        p = params if p is None else p
+        if shared is not None:
+            frame = shared[step_no[0] & 1]
+            step_no[0] += 1
+            r.render_tiles_into(p, frame)
+            launches[0] += int(r.stats().kernel_launches)
+            dist.all_reduce(join)             # stream-ordered join; the pixels already travelled inside the kernel
+            if rank == 0:
+                r.finalize(frame, w, h, spp, rgb.data_ptr())
+                launches[0] += 1
+            return
         accum.zero_()
-        r.render_accumulate(params, accum.data_ptr())
+        r.render_accumulate(p, accum.data_ptr())
         launches[0] += int(r.stats().kernel_launches) + 1
         if world > 1:
-            # exchange step: disjoint tiles (or partial sample sums) summed onto rank 0 over NVLink
+            # exchange step: partial sample sums (or, with RC_BENCH_NCCL_GATHER, disjoint tiles) summed onto rank 0
             dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0:
             r.finalize(accum.data_ptr(), w, h, spp, rgb.data_ptr())
@@ -300,11 +331,8 @@ def main():
         if world == 1:
             out = r.render(e2e_params, out=host_out)   # render + device -> host of the gamma'd f64 image
         else:
-            accum.zero_()
-            r.render_accumulate(e2e_params, accum.data_ptr())
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            step(e2e_params)
             if rank == 0:
-                r.finalize(accum.data_ptr(), w, h, spp, rgb.data_ptr())
                 host32.copy_(rgb, non_blocking=True)
         torch.cuda.synchronize()
     barrier()
@@ -329,7 +357,9 @@ def main():
                        "kernel": "scene-specialised (NVRTC)" if spec else "precompiled",
                        "bvh": "gpu-lbvh" if args.lbvh else ("host" if job.scene.c.n_nodes else "none"),
                        "l2": "256 MiB buffer written between timed iterations (flush)",
-                       "parallelism": f"tiles{world}" if split_name == "tiles" else f"samples{world}"},
+                       "parallelism": f"tiles{world}" if split_name == "tiles" else f"samples{world}",
+                       "exchange": ("none" if world == 1 else ("in-kernel peer stores into rank 0's frame buffer (CUDA IPC, NVLink) + 1-element all-reduce"
+                                                               if shared is not None else "NCCL reduce of the accumulation buffer to rank 0"))},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(scene_bytes),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
             "gpu_launches": launches[0],
@@ -370,6 +400,9 @@ def main():
         line["cpu_baseline"] = cpu
         print(json.dumps(line))
     barrier()
+    if shared is not None:
+        for ptr in shared:
+            r.shared_close(ptr)
     r.close()
     if world > 1:
         dist.destroy_process_group()

@@ -311,6 +311,25 @@ int rc_render_preview(rc_ctx* ctx, const rc_params* params, int32_t scale_w, int
 int rc_render_accumulate(rc_ctx* ctx, const rc_params* params, float* d_accum,
                          const volatile int32_t* cancel);
 
+/* Tile split across the GPUs of one box without an exchange step: this participant's tiles
+ * (params->rank / params->world, RC_SPLIT_TILES, megakernel) are traced and their radiance sums
+ * STORED into d_image (width*height*3 floats), which may live on ANOTHER GPU — a buffer opened
+ * with rc_shared_open, or device 0's buffer when the context spans several devices.  Every pixel is
+ * owned by exactly one participant, so after all of them have finished (the caller's barrier)
+ * d_image holds the whole frame: the gather of SURVEY §8(e) ("tiles are gathered peer-to-peer")
+ * happens inside the render kernel, over NVLink, as each tile completes. */
+int rc_render_tiles_into(rc_ctx* ctx, const rc_params* params, float* d_image,
+                         const volatile int32_t* cancel);
+
+/* A device buffer on device 0 of `ctx` that the other processes of the box can map (CUDA IPC):
+ * rc_shared_alloc creates it (zero-filled) and returns the 64-byte handle to pass on (any byte
+ * channel: a file, a pipe, a broadcast); rc_shared_open maps it into the calling process with peer
+ * access to its GPU; rc_shared_close unmaps / frees.  The one-process-per-GPU form of the tile-split
+ * gather (the reference itself is a single process, so this has no counterpart there). */
+int rc_shared_alloc(rc_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle[64]);
+int rc_shared_open(rc_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+int rc_shared_close(rc_ctx* ctx, void* d_ptr);
+
 /* scale_sqrt on a device accumulation buffer: d_rgb[i] = sqrt(d_accum[i] /
  * samples) (src/vec3.rs:119-125).  d_rgb may alias d_accum. */
 int rc_finalize(rc_ctx* ctx, const float* d_accum, int32_t width, int32_t height,

@@ -106,6 +106,8 @@ struct rc_ctx {
     std::vector<LbvhObject> objects, objects_next;   // top-level objects of the uploaded scene (rc_build_lbvh)
     std::vector<int> prim_order;       // device primitive i = uploaded primitive prim_order[i] (empty: identity)
     bool lbvh = false;
+    bool overwrite = false;            // set for the duration of rc_render_tiles_into
+    std::vector<void*> shared_owned, shared_opened;   // rc_shared_alloc / rc_shared_open
     int n_prims = 0, n_perlin = 0;
     bool instanced = false;
     rc_camera camera;
@@ -290,6 +292,7 @@ void partition(KParams& kp, const rc_params* p, int part, int parts) {
     kp.px_scale_x = kp.px_scale_y = 1;
     kp.tile_w = RT_TILE_W; kp.tile_h = RT_TILE_H;
     kp.slices = 1; kp.slice_buf = nullptr;
+    kp.overwrite = 0;
     kp.tiles_x = (p->width + RT_TILE_W - 1) / RT_TILE_W;
     int tiles_y = (p->height + RT_TILE_H - 1) / RT_TILE_H;
     int total = kp.tiles_x * tiles_y;
@@ -307,6 +310,11 @@ void partition(KParams& kp, const rc_params* p, int part, int parts) {
 }
 
 bool cancelled(const volatile int32_t* cancel) { return cancel && *cancel != 0; }
+
+// tile split over the devices of one context with peer stores into device 0's buffer (rc_multi.cuh)
+bool direct_tiles(const rc_ctx* ctx, const rc_params* p) {
+    return ctx->devs.size() > 1 && p->split == RC_SPLIT_TILES && ctx->multi.peer_write_ok && p->variant == RC_VARIANT_MEGAKERNEL;
+}
 
 // Trace this context's share into each device's own accumulation buffer
 // (device 0 uses `accum0`).  Does not gather.
@@ -341,7 +349,10 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
             kp.wm1 = (float)(ctx->preview_w - 1);
             kp.inv_wm1 = 1.0f / (float)(ctx->preview_w - 1); kp.inv_hm1 = 1.0f / (float)(ctx->preview_h - 1);
         }
-        float* accum = (k == 0) ? accum0 : d.accum.p;
+        // direct tile split: every device stores its pixels into device 0's buffer (peer memory) itself
+        const bool direct = n_dev > 1 && p->split == RC_SPLIT_TILES && ctx->multi.peer_write_ok && p->variant == RC_VARIANT_MEGAKERNEL;
+        float* accum = (k == 0 || direct) ? accum0 : d.accum.p;
+        kp.overwrite = ctx->overwrite ? 1 : 0;
         if (kp.n_tiles == 0 || kp.s_end <= kp.s_begin) continue;
         if (p->variant == RC_VARIANT_WAVEFRONT) {
             if (kp.has_motion && rounds != 10) return fail(RC_ERR_INVALID, "the wavefront variant traces moving spheres with 10 Philox rounds only");
@@ -682,6 +693,9 @@ int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
 
 int rc_destroy(rc_ctx* ctx) {
     if (!ctx) return RC_OK;
+    cudaSetDevice(ctx->devs.empty() ? 0 : ctx->devs[0].device);
+    for (void* q : ctx->shared_opened) cudaIpcCloseMemHandle(q);
+    for (void* q : ctx->shared_owned) cudaFree(q);
     multi_destroy(ctx->multi);
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.device);
@@ -830,7 +844,10 @@ int rc_render_accumulate(rc_ctx* ctx, const rc_params* p, float* d_accum, const 
     bool was_cancelled = false;
     rc = trace_share(ctx, p, d_accum, cancel, was_cancelled);
     if (rc != RC_OK) return rc;
-    if (!was_cancelled && ctx->devs.size() > 1) {
+    if (!was_cancelled && ctx->devs.size() > 1 && direct_tiles(ctx, p)) {
+        if (multi_join(ctx->multi, [&](size_t k) { return ctx->devs[k].stream; }, [&](size_t k) { return ctx->devs[k].device; }) != 0)
+            return fail(RC_ERR_CUDA, std::string("multi-device join failed: ") + multi_error(ctx->multi));
+    } else if (!was_cancelled && ctx->devs.size() > 1) {
         rc = multi_gather(ctx->multi, p->split, (size_t)p->width * p->height * 3, d_accum,
                           [&](size_t k) { return ctx->devs[k].accum.p; },
                           [&](size_t k) { return ctx->devs[k].stream; },
@@ -838,6 +855,59 @@ int rc_render_accumulate(rc_ctx* ctx, const rc_params* p, float* d_accum, const 
         if (rc != RC_OK) return fail(rc, std::string("multi-device gather failed: ") + multi_error(ctx->multi));
     }
     return finish_stats(ctx, p);
+}
+
+int rc_render_tiles_into(rc_ctx* ctx, const rc_params* p, float* d_image, const volatile int32_t* cancel) {
+    if (!ctx || !d_image) return fail(RC_ERR_INVALID, "ctx or d_image is NULL");
+    int rc = check_params(p);
+    if (rc != RC_OK) return rc;
+    if (p->split != RC_SPLIT_TILES || p->variant != RC_VARIANT_MEGAKERNEL)
+        return fail(RC_ERR_INVALID, "rc_render_tiles_into needs the tile split and the megakernel (pixels are stored, not added)");
+    if (ctx->devs.size() > 1 && !ctx->multi.peer_write_ok) return fail(RC_ERR_INVALID, "rc_render_tiles_into over several devices needs peer access");
+    ctx->overwrite = true;
+    rc = rc_render_accumulate(ctx, p, d_image, cancel);
+    ctx->overwrite = false;
+    return rc;
+}
+
+// ---- a device buffer shared by the processes of one box (CUDA IPC over NVLink / PCIe peer mappings) ----
+int rc_shared_alloc(rc_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle[64]) {
+    if (!ctx || !d_ptr || !handle || bytes == 0) return fail(RC_ERR_INVALID, "bad rc_shared_alloc arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUDA_TRY(cudaSetDevice(ctx->devs[0].device));
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t)bytes));
+    CUDA_TRY(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(RC_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    std::memcpy(handle, &h, 64);
+    ctx->shared_owned.push_back(p);
+    *d_ptr = p;
+    return RC_OK;
+}
+
+int rc_shared_open(rc_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
+    if (!ctx || !d_ptr || !handle) return fail(RC_ERR_INVALID, "bad rc_shared_open arguments");
+    CUDA_TRY(cudaSetDevice(ctx->devs[0].device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    ctx->shared_opened.push_back(p);
+    *d_ptr = p;
+    return RC_OK;
+}
+
+int rc_shared_close(rc_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return fail(RC_ERR_INVALID, "bad rc_shared_close arguments");
+    CUDA_TRY(cudaSetDevice(ctx->devs[0].device));
+    for (size_t i = 0; i < ctx->shared_owned.size(); ++i)
+        if (ctx->shared_owned[i] == d_ptr) { ctx->shared_owned.erase(ctx->shared_owned.begin() + i); CUDA_TRY(cudaFree(d_ptr)); return RC_OK; }
+    for (size_t i = 0; i < ctx->shared_opened.size(); ++i)
+        if (ctx->shared_opened[i] == d_ptr) { ctx->shared_opened.erase(ctx->shared_opened.begin() + i); CUDA_TRY(cudaIpcCloseMemHandle(d_ptr)); return RC_OK; }
+    return fail(RC_ERR_INVALID, "pointer was not returned by rc_shared_alloc / rc_shared_open on this context");
 }
 
 int rc_finalize(rc_ctx* ctx, const float* d_accum, int32_t width, int32_t height, int32_t samples, float* d_rgb) {
@@ -864,7 +934,10 @@ int rc_render(rc_ctx* ctx, const rc_params* p, double* out_rgb, const volatile i
     rc = trace_share(ctx, p, d0.accum.p, cancel, was_cancelled);
     if (rc != RC_OK) return rc;
     if (was_cancelled) return RC_OK;  // a cancelled render writes nothing, cpu.rs:55-62
-    if (ctx->devs.size() > 1) {
+    if (ctx->devs.size() > 1 && direct_tiles(ctx, p)) {
+        if (multi_join(ctx->multi, [&](size_t k) { return ctx->devs[k].stream; }, [&](size_t k) { return ctx->devs[k].device; }) != 0)
+            return fail(RC_ERR_CUDA, std::string("multi-device join failed: ") + multi_error(ctx->multi));
+    } else if (ctx->devs.size() > 1) {
         rc = multi_gather(ctx->multi, p->split, n, d0.accum.p,
                           [&](size_t k) { return ctx->devs[k].accum.p; },
                           [&](size_t k) { return ctx->devs[k].stream; },
@@ -911,7 +984,10 @@ int rc_render_preview(rc_ctx* ctx, const rc_params* p, int32_t scale_w, int32_t 
     ctx->preview_sw = ctx->preview_sh = ctx->preview_w = ctx->preview_h = 0;
     if (rc != RC_OK) return rc;
     if (was_cancelled) return RC_OK;
-    if (ctx->devs.size() > 1) {
+    if (ctx->devs.size() > 1 && direct_tiles(ctx, &q)) {
+        if (multi_join(ctx->multi, [&](size_t k) { return ctx->devs[k].stream; }, [&](size_t k) { return ctx->devs[k].device; }) != 0)
+            return fail(RC_ERR_CUDA, std::string("multi-device join failed: ") + multi_error(ctx->multi));
+    } else if (ctx->devs.size() > 1) {
         rc = multi_gather(ctx->multi, q.split, (size_t)q.width * q.height * 3, d0.accum.p,
                           [&](size_t k) { return ctx->devs[k].accum.p; },
                           [&](size_t k) { return ctx->devs[k].stream; },

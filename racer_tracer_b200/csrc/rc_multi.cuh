@@ -1,11 +1,13 @@
 // rc_multi.cuh — exchange step of a multi-device render inside one process
 // (the reference is a single process).
 //
-//   tile split    every device traced a disjoint set of interleaved tiles into
-//                 its own zero-initialised buffer; device 0 pulls the other
-//                 buffers straight out of peer memory over NVLink (one kernel,
-//                 peer loads) and adds them — no reduction is semantically
-//                 needed because the tile sets are disjoint.
+//   tile split    every device traces a disjoint set of interleaved tiles.  With peer
+//                 access in both directions the megakernel of device k stores its
+//                 pixels STRAIGHT INTO device 0's accumulation buffer over NVLink as
+//                 each tile finishes (compute and gather in one kernel; device 0 only
+//                 waits on an event).  Without it every device fills its own
+//                 zero-initialised buffer and device 0 pulls them out of peer memory
+//                 (or a staging copy) and adds them.
 //   sample split  every device holds a partial sum of ALL pixels; the buffers
 //                 are summed onto device 0 with ncclReduce (NCCL is loaded
 //                 lazily with dlopen so a 1-GPU host needs no NCCL at all).
@@ -58,7 +60,8 @@ struct NcclApi {
 
 struct MultiState {
     size_t n_dev = 0;
-    bool peer_ok = false;
+    bool peer_ok = false;               // device 0 can read every other device's memory
+    bool peer_write_ok = false;         // every other device can write device 0's memory
     std::vector<cudaEvent_t> done;      // per device: tracing finished
     float* staging = nullptr;           // device 0, used when peer access is unavailable
     size_t staging_n = 0;
@@ -82,6 +85,15 @@ int multi_init(MultiState& m, size_t n_dev, DevOf device_of) {
         cudaError_t e = cudaDeviceEnablePeerAccess(device_of(k), 0);
         if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
         if (e != cudaSuccess) { cudaGetLastError(); m.peer_ok = false; }
+    }
+    m.peer_write_ok = m.peer_ok;
+    for (size_t k = 1; k < n_dev && m.peer_write_ok; ++k) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, device_of(k), device_of(0)) != cudaSuccess || !can) { m.peer_write_ok = false; break; }
+        cudaSetDevice(device_of(k));
+        cudaError_t e = cudaDeviceEnablePeerAccess(device_of(0), 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        if (e != cudaSuccess) { cudaGetLastError(); m.peer_write_ok = false; }
     }
     m.done.resize(n_dev);
     for (size_t k = 0; k < n_dev; ++k) {
@@ -126,6 +138,19 @@ int multi_nccl_init(MultiState& m, DevOf device_of) {
     m.comms.assign(m.n_dev, nullptr);
     int rc = m.nccl.CommInitAll(m.comms.data(), (int)m.n_dev, devs.data());
     if (rc != 0) { m.err = std::string("ncclCommInitAll: ") + m.nccl.GetErrorString(rc); m.comms.clear(); return -6; }
+    return 0;
+}
+
+// Direct tile split: the other devices wrote into device 0's buffer themselves; its stream waits for them.
+template <class StreamOf, class DevOf>
+int multi_join(MultiState& m, StreamOf stream_of, DevOf device_of) {
+    for (size_t k = 1; k < m.n_dev; ++k) {
+        cudaSetDevice(device_of(k));
+        if (cudaEventRecord(m.done[k], stream_of(k)) != cudaSuccess) { m.err = "event record failed"; return -3; }
+    }
+    cudaSetDevice(device_of(0));
+    for (size_t k = 1; k < m.n_dev; ++k)
+        if (cudaStreamWaitEvent(stream_of(0), m.done[k], 0) != cudaSuccess) { m.err = "stream wait failed"; return -3; }
     return 0;
 }
 

@@ -328,8 +328,10 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         float* a = P.slice_buf + 3 * ((size_t)slice * ((size_t)P.n_tiles * RT_BLOCK) + (size_t)tile_k * RT_BLOCK + threadIdx.x);
         a[0] = sum.x; a[1] = sum.y; a[2] = sum.z;
     } else if (valid) {
+        // (possibly a peer GPU's memory: the gather of a multi-GPU tile split happens here, over NVLink)
         float* a = accum + 3 * (size_t)pc.pixel;
-        a[0] += sum.x; a[1] += sum.y; a[2] += sum.z;
+        if (P.overwrite) { a[0] = sum.x; a[1] = sum.y; a[2] = sum.z; }
+        else { a[0] += sum.x; a[1] += sum.y; a[2] += sum.z; }
     }
     // segment statistics: one atomic per warp
     for (int off = 16; off > 0; off >>= 1) nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
@@ -354,7 +356,8 @@ __global__ void reduce_slices_kernel(const __grid_constant__ KParams P, float* _
         sx += a[0]; sy += a[1]; sz += a[2];
     }
     float* dst = accum + 3 * ((size_t)py * P.width + px);
-    dst[0] += sx; dst[1] += sy; dst[2] += sz;
+    if (P.overwrite) { dst[0] = sx; dst[1] = sy; dst[2] = sz; }
+    else { dst[0] += sx; dst[1] += sy; dst[2] += sz; }
 }
 
 template <int MODE, int SAMPLER, int ROUNDS, bool TEX>

@@ -99,6 +99,8 @@ struct KParams {
     uint32_t key;               // Philox2x32 key = seed_lo ^ seed_hi
     uint32_t ks[10];            // its key schedule: key + r * 0x9E3779B9
     int tile_first, tile_stride, n_tiles;   // interleaved tile partition
+    int overwrite;              // 1: pixel sums are STORED (rc_render_tiles_into: a buffer shared by several GPUs,
+                                // every pixel owned by one of them); 0: added to the accumulation buffer
     int slices;                 // > 1: every tile's sample range is cut into this many CTAs (few tiles per GPU)
     float* slice_buf;           // [slices][n_tiles * 128][3] partial sums, reduced in slice order afterwards
     int tiles_x, tile_w, tile_h;

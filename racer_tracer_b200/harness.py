@@ -875,6 +875,24 @@ class CudaRenderer:
         capi.check(self.lib, self.lib.rc_render_accumulate(self.ctx, C.byref(params),
                                                            C.c_void_p(d_accum_ptr), None))
 
+    def render_tiles_into(self, params: rc_params, d_image_ptr: int):
+        """rc_render_tiles_into: this participant's tiles STORED into a (possibly remote) frame buffer."""
+        capi.check(self.lib, self.lib.rc_render_tiles_into(self.ctx, C.byref(params), C.c_void_p(d_image_ptr), None))
+
+    def shared_alloc(self, nbytes: int):
+        """rc_shared_alloc -> (device pointer, 64-byte IPC handle)."""
+        ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        capi.check(self.lib, self.lib.rc_shared_alloc(self.ctx, nbytes, C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def shared_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        capi.check(self.lib, self.lib.rc_shared_open(self.ctx, (C.c_uint8 * 64).from_buffer_copy(handle), C.byref(ptr)))
+        return ptr.value
+
+    def shared_close(self, ptr: int):
+        capi.check(self.lib, self.lib.rc_shared_close(self.ctx, C.c_void_p(ptr)))
+
     def finalize(self, d_accum_ptr: int, width: int, height: int, samples: int, d_rgb_ptr: int):
         capi.check(self.lib, self.lib.rc_finalize(self.ctx, C.c_void_p(d_accum_ptr), width, height,
                                                   samples, C.c_void_p(d_rgb_ptr)))

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Two (or more) processes, one GPU each, one frame: every rank stores its tiles into rank 0's frame buffer
+(rc_shared_alloc / rc_shared_open / rc_render_tiles_into) and rank 0 compares the frame with its own
+single-GPU render of the whole image.  Run under torchrun; prints IPC_TILES_OK on success.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/ipc_tiles_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from racer_tracer_b200 import capi, harness  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+w, h, spp = 333, 201, 64
+cfg = harness.load_config(os.path.join(ROOT, "tests", "golden", "config.yml"))
+job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", "cornell_box.yml"), cfg, w, h)
+r = harness.CudaRenderer([local])
+r.set_stream(torch.cuda.current_stream().cuda_stream)
+r.upload(job)
+n = w * h * 3
+if rank == 0:
+    ptr, handle = r.shared_alloc(n * 4)
+    hbuf = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+else:
+    hbuf = torch.empty(64, dtype=torch.uint8, device="cuda")
+dist.broadcast(hbuf, 0)
+if rank != 0:
+    ptr = r.shared_open(bytes(hbuf.cpu().tolist()))
+join = torch.zeros(1, device="cuda")
+for spec in (0, 2):
+    p = harness.make_params(w, h, spp, 20, seed=9, rank=rank, world=world, specialize=spec)
+    r.render_tiles_into(p, ptr)
+    dist.all_reduce(join)
+    torch.cuda.synchronize()
+    if rank == 0:
+        rgb = torch.empty(n, dtype=torch.float32, device="cuda")
+        r.finalize(ptr, w, h, spp, rgb.data_ptr())
+        got = rgb.cpu().numpy().reshape(h, w, 3)
+        want = r.render(harness.make_params(w, h, spp, 20, seed=9, specialize=spec)).astype(np.float32)
+        assert np.array_equal(got, want), f"specialize={spec}: {np.abs(got - want).max()}"
+    dist.barrier()
+r.shared_close(ptr)
+r.close()
+if rank == 0:
+    print("IPC_TILES_OK")
+dist.destroy_process_group()
