@@ -25,7 +25,9 @@ pub trait Flatten {
 #[derive(Default)]
 pub struct FlatScene {
     pub prim_type: Vec<i32>, pub prim_data: Vec<f64>, pub prim_material: Vec<i32>, pub prim_id: Vec<u32>,
-    pub prim_instance: Vec<i32>, pub prim_aabb: Vec<f64>, pub instances: Vec<sys::rc_instance>,
+    pub prim_instance: Vec<i32>, pub prim_aabb: Vec<f64>,
+    pub prim_motion: Vec<f64>,   // 5 per prim (pos_b, time_a, time_b): MovingSphere, src/geometry/moving_sphere.rs
+    pub instances: Vec<sys::rc_instance>,
     pub materials: Vec<sys::rc_material>, pub textures: Vec<sys::rc_texture>,
     pub images: Vec<(u32, u32, Vec<u8>)>, pub perlin: Vec<sys::rc_perlin>, pub nodes: Vec<sys::rc_bvh_node>,
     pub bg_type: i32, pub bg_a: [f64; 3], pub bg_b: [f64; 3],
@@ -69,6 +71,7 @@ impl CudaRenderer {
             n_perlin: flat.perlin.len() as i32, perlin: flat.perlin.as_ptr(),
             n_nodes: flat.nodes.len() as i32, nodes: flat.nodes.as_ptr(),
             bg_type: flat.bg_type, reserved: 0, bg_a: flat.bg_a, bg_b: flat.bg_b,
+            prim_motion: if flat.prim_motion.is_empty() { std::ptr::null() } else { flat.prim_motion.as_ptr() },
         };
         check(unsafe { sys::rc_upload_scene(*self.ctx.lock().unwrap(), &scene) })
     }
@@ -101,6 +104,42 @@ impl Renderer for CudaRenderer {
             writer.write(ImageBufferEvent::BufferUpdate { rgb: px, r, c: 0, width: w, height: rows })?;
         }
         Ok(())
+    }
+}
+
+/// `preview_renderer: CudaPreview` — the drop-in for CpuRendererScaled (src/renderer/cpu_scaled.rs).
+pub struct CudaPreviewRenderer { inner: CudaRenderer, scale_width: usize, scale_height: usize }
+
+fn get_highest_divdable(value: usize, mut div: usize) -> usize {   // cpu_scaled.rs:17-23
+    while (value % div) != 0 { div -= 1; }
+    div
+}
+
+impl CudaPreviewRenderer {
+    pub fn new(config: RenderConfig, image: &Image, devices: &[i32], seed: u64) -> Result<Self, TracerError> {
+        let scale_width = get_highest_divdable(image.width / config.num_threads_width, config.scale);     // cpu_scaled.rs:31-34
+        let scale_height = get_highest_divdable(image.height / config.num_threads_height, config.scale);
+        Ok(Self { inner: CudaRenderer::new(config, devices, seed)?, scale_width, scale_height })
+    }
+}
+
+impl Renderer for CudaPreviewRenderer {
+    fn render(&self, rd: RenderData, writer: &DataWriter<ImageBufferEvent>) -> Result<(), TracerError> {
+        let ctx = *self.inner.ctx.lock().unwrap();
+        check(unsafe { sys::rc_set_camera(ctx, &rd.camera_data.to_rc_camera()) })?;
+        let (w, h) = (rd.image.width, rd.image.height);
+        let params = sys::rc_params {
+            width: w as i32, height: h as i32,
+            samples: self.inner.config.samples as i32, max_depth: self.inner.config.max_depth as i32,   // config.preview
+            seed: self.inner.seed, world: 1, ..Default::default()
+        };
+        let cancel = CancelFlag::watch(rd.cancel_event);
+        let mut rgb = vec![0f64; w * h * 3];
+        check(unsafe { sys::rc_render_preview(ctx, &params, self.scale_width as i32, self.scale_height as i32,
+                                              rgb.as_mut_ptr(), cancel.as_ptr()) })?;
+        if cancel.is_set() { return Ok(()); }
+        let px: Vec<Vec3> = rgb.chunks_exact(3).map(|c| Vec3::new(c[0], c[1], c[2])).collect();
+        writer.write(ImageBufferEvent::BufferUpdate { rgb: px, r: 0, c: 0, width: w, height: h })
     }
 }
 

@@ -1,4 +1,4 @@
-//! Raw bindings to `include/racer_cuda.h` (RC_ABI_VERSION 1).  Field order and types follow the
+//! Raw bindings to `include/racer_cuda.h` (RC_ABI_VERSION 2).  Field order and types follow the
 //! header exactly; `tests/test_abi.py::test_struct_layouts_match_the_header` pins the sizes the
 //! C compiler sees.  NOT COMPILED in this repository's CI: the build image has no Rust toolchain.
 #![allow(non_camel_case_types)]
@@ -16,6 +16,7 @@ pub const RC_PRIM_SPHERE: i32 = 0;
 pub const RC_PRIM_XY_RECT: i32 = 1;
 pub const RC_PRIM_XZ_RECT: i32 = 2;
 pub const RC_PRIM_YZ_RECT: i32 = 3;
+pub const RC_PRIM_MOVING_SPHERE: i32 = 4;
 pub const RC_MAT_LAMBERTIAN: i32 = 0;
 pub const RC_MAT_METAL: i32 = 1;
 pub const RC_MAT_DIELECTRIC: i32 = 2;
@@ -68,6 +69,7 @@ pub struct rc_scene {
     pub n_nodes: i32, pub nodes: *const rc_bvh_node,
     pub bg_type: i32, pub reserved: i32,
     pub bg_a: [f64; 3], pub bg_b: [f64; 3],
+    pub prim_motion: *const f64,   // ABI 2: 5 per prim (pos_b, time_a, time_b) for RC_PRIM_MOVING_SPHERE; may be null
 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -99,7 +101,15 @@ extern "C" {
     pub fn rc_set_stream(ctx: *mut rc_ctx, cuda_stream: *mut c_void) -> c_int;
     pub fn rc_upload_scene(ctx: *mut rc_ctx, scene: *const rc_scene) -> c_int;
     pub fn rc_set_camera(ctx: *mut rc_ctx, camera: *const rc_camera) -> c_int;
+    pub fn rc_build_lbvh(ctx: *mut rc_ctx) -> c_int;
+    pub fn rc_get_bvh(ctx: *mut rc_ctx, nodes: *mut rc_bvh_node, node_capacity: i32, prim_order: *mut i32, prim_capacity: i32) -> c_int;
     pub fn rc_render(ctx: *mut rc_ctx, params: *const rc_params, out_rgb: *mut f64, cancel: *const i32) -> c_int;
+    pub fn rc_render_preview(ctx: *mut rc_ctx, params: *const rc_params, scale_w: i32, scale_h: i32, out_rgb: *mut f64,
+                             cancel: *const i32) -> c_int;
+    pub fn rc_render_tiles_into(ctx: *mut rc_ctx, params: *const rc_params, d_image: *mut f32, cancel: *const i32) -> c_int;
+    pub fn rc_shared_alloc(ctx: *mut rc_ctx, bytes: u64, d_ptr: *mut *mut c_void, handle: *mut u8) -> c_int;
+    pub fn rc_shared_open(ctx: *mut rc_ctx, handle: *const u8, d_ptr: *mut *mut c_void) -> c_int;
+    pub fn rc_shared_close(ctx: *mut rc_ctx, d_ptr: *mut c_void) -> c_int;
     pub fn rc_render_accumulate(ctx: *mut rc_ctx, params: *const rc_params, d_accum: *mut f32, cancel: *const i32) -> c_int;
     pub fn rc_finalize(ctx: *mut rc_ctx, d_accum: *const f32, width: i32, height: i32, samples: i32, d_rgb: *mut f32) -> c_int;
     pub fn rc_primary_aov(ctx: *mut rc_ctx, params: *const rc_params, precision: i32, id: *mut u32, t: *mut f64,
