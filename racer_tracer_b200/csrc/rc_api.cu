@@ -186,6 +186,7 @@ int validate_scene(const rc_scene* s) {
 inline float4 f4(double x, double y, double z, float w) { return make_float4((float)x, (float)y, (float)z, w); }
 inline float bits(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline float ubits(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline int ibits(float f) { int v; std::memcpy(&v, &f, 4); return v; }
 
 // next float toward -inf / +inf, then a relative pad: the fp32 boxes must
 // contain the f64 boxes and tolerate fp32 slab arithmetic
@@ -607,8 +608,36 @@ static void build_tables(const rc_scene* s, HostTables& t) {
     prims_lin.reserve(s->n_prims);
     for (int type = 0; type < 4; ++type) {
         for (int i = 0; i < s->n_prims; ++i)   // moving spheres (kind 4) share group 0 with the static ones
-            if ((kinds[i] == RC_PRIM_MOVING_SPHERE ? 0 : kinds[i]) == type) prims_lin.push_back(prims[i]);
+            if (t.prim_inst[i] < 0 && (kinds[i] == RC_PRIM_MOVING_SPHERE ? 0 : kinds[i]) == type) prims_lin.push_back(prims[i]);
         kp.lin_end[type] = (int)prims_lin.size();
+    }
+    // instanced top-level objects follow, each a run of primitives sharing object id, instance and stored Aabb
+    kp.n_cobj = 0;
+    bool objs_fit = s->n_instances <= RT_MAX_CONST_OBJS && (!any_instance || s->prim_aabb != nullptr);
+    for (int i = 0; i < s->n_instances && i < RT_MAX_CONST_OBJS; ++i) kp.cinst[i] = t.instances[i];
+    for (int i = 0; i < s->n_prims && objs_fit; ++i) {
+        if (t.prim_inst[i] < 0) continue;
+        const double* b = s->prim_aabb + 6 * (size_t)i;
+        bool same = false;
+        if (kp.n_cobj > 0 && i > 0 && t.prim_inst[i - 1] == t.prim_inst[i] && (s->prim_id[i - 1] >> 3) == (s->prim_id[i] >> 3) &&
+            std::memcmp(s->prim_aabb + 6 * (size_t)(i - 1), b, 6 * sizeof(double)) == 0) {
+            const int meta = ibits(kp.cobj_hi[kp.n_cobj - 1].w);
+            if ((meta & 255) < 255) { kp.cobj_hi[kp.n_cobj - 1].w = bits(meta + 1); same = true; }
+        }
+        if (!same) {
+            if (kp.n_cobj == RT_MAX_CONST_OBJS) { objs_fit = false; break; }
+            // the cull volume in fp32: rounded OUTWARD by one ulp-scale pad so it contains the f64 box
+            double ext = 0;
+            for (int a = 0; a < 3; ++a) ext = std::fmax(ext, b[3 + a] - b[a]);
+            kp.cobj_lo[kp.n_cobj] = make_float4(pad_lo(b[0], ext), pad_lo(b[1], ext), pad_lo(b[2], ext), bits((int)prims_lin.size()));
+            kp.cobj_hi[kp.n_cobj] = make_float4(pad_hi(b[3], ext), pad_hi(b[4], ext), pad_hi(b[5], ext), bits(1 | (t.prim_inst[i] << 8)));
+            ++kp.n_cobj;
+        }
+        prims_lin.push_back(prims[i]);
+    }
+    if (!objs_fit) {   // too many instanced objects for the linear modes: they traverse the BVH
+        kp.n_cobj = 0;
+        for (int i = 0; i < s->n_prims; ++i) if (t.prim_inst[i] >= 0 && (int)prims_lin.size() < s->n_prims) prims_lin.push_back(prims[i]);
     }
     for (int i = 0; i < RT_MAX_CONST_PRIMS; ++i)
         if (i < s->n_prims) kp.cprims[i] = prims_lin[i]; else std::memset(&kp.cprims[i], 0, sizeof(DevPrim));
@@ -629,7 +658,7 @@ static void build_tables(const rc_scene* s, HostTables& t) {
         kp.image_w[i] = i < s->n_images ? s->images[i].width : 0;
         kp.image_h[i] = i < s->n_images ? s->images[i].height : 0;
     }
-    t.mode = pick_mode(s, rects_fit && !any_instance, any_instance, t.smem_bytes);
+    t.mode = pick_mode(s, rects_fit && objs_fit, any_instance && !objs_fit, t.smem_bytes);
     t.has_textures = any_textured;
     t.mats_mask = 0;
     for (int i = 0; i < s->n_prims; ++i) t.mats_mask |= 1 << s->materials[s->prim_material[i]].type;
@@ -728,6 +757,8 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     if (rc != RC_OK) return rc;
     HostTables t;
     build_tables(s, t);
+    if (!t.instances.empty() && t.kp.n_cobj == 0 && s->n_nodes == 0)
+        return fail(RC_ERR_INVALID, "a scene with more than 8 instanced objects (or without prim_aabb) needs BVH nodes");
     {   // keep the camera / launch fields already stored in ctx->kp
         DevCamera<float> cam = ctx->kp.cam;
         int lens = ctx->kp.lens_enabled;

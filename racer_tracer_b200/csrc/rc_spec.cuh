@@ -104,12 +104,15 @@ inline std::string spec_float(float v) {
 inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
     std::ostringstream o;
     // primitive kinds present, background, regeneration batching: known before the headers are read
-    int prims_mask = 0;
-    if (kp.lin_end[0] > 0) prims_mask |= 1;
-    for (int g = 0; g < 3; ++g) if (kp.lin_end[g + 1] > kp.lin_end[g]) prims_mask |= 2 << g;
+    int prims_mask = 0;   // bit RT_PRIM_* (moving spheres count as spheres), instanced primitives included
+    for (int i = 0; i < kp.n_prims && i < RT_MAX_CONST_PRIMS; ++i) {
+        const int type = __float_as_int_host(kp.cprims[i].b.z) & 15;
+        prims_mask |= 1 << (type == RT_PRIM_MOVING ? RT_PRIM_SPHERE : type);
+    }
     o << "#define RT_SPEC_PRIMS " << prims_mask << "\n";
     const bool black = __float_as_int_host(kp.bg_a.w) != 0 && kp.bg_a.x == 0.f && kp.bg_a.y == 0.f && kp.bg_a.z == 0.f;
     o << "#define RT_SPEC_BG_BLACK " << (black ? 1 : 0) << "\n";
+    o << "#define RT_HAS_INSTANCES " << (kp.n_cobj > 0 ? 1 : 0) << "\n";
     if (const char* e = std::getenv("RC_REGEN_MIN")) o << "#define RT_REGEN_MIN " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
     o << "#include \"rt_scene.cuh\"\n";
@@ -173,6 +176,58 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
         for (int i = begin; i < end; ++i)
             o << "        { const bool hit = c" << i << " <= best_t; best_t = hit ? c" << i << " : best_t; best = hit ? " << i
               << " : best; }\n";
+        o << "    }\n";
+    }
+    // instanced objects: cull volume, ray into the object's space (constants spelled out), then its rectangles
+    for (int k = 0; k < kp.n_cobj; ++k) {
+        const float4 lo = kp.cobj_lo[k], hi = kp.cobj_hi[k];
+        const int first = __float_as_int_host(lo.w), meta = __float_as_int_host(hi.w), count = meta & 255;
+        const DevInstance& in = kp.cinst[meta >> 8];
+        o << "    if (aabb_hit_reference(make_float4(" << spec_float(lo.x) << ", " << spec_float(lo.y) << ", " << spec_float(lo.z)
+          << ", 0.0f), make_float4(" << spec_float(hi.x) << ", " << spec_float(hi.y) << ", " << spec_float(hi.z) << ", 0.0f), r, best_t)) {\n";
+        o << "        vec3f lo_ = r.o, ld_ = r.d;\n";
+        if (in.flags & 2) o << "        lo_ = mk3(lo_.x - " << spec_float(in.ox) << ", lo_.y - " << spec_float(in.oy) << ", lo_.z - " << spec_float(in.oz) << ");\n";
+        if (in.flags & 1) {
+            const std::string c = spec_float(in.cos_theta), sn = spec_float(in.sin_theta);
+            o << "        lo_ = mk3(" << c << " * lo_.x - " << sn << " * lo_.z, lo_.y, " << sn << " * lo_.x + " << c << " * lo_.z);\n";
+            o << "        ld_ = mk3(" << c << " * ld_.x - " << sn << " * ld_.z, ld_.y, " << sn << " * ld_.x + " << c << " * ld_.z);\n";
+        }
+        o << "        const RayT<float> lr = make_ray(lo_, ld_, r.time);\n";
+        // the object's primitives in order (Boxx::obj_hit, box.rs:82-101): rectangle candidates first
+        // (independent), spheres solved in place, then the ordered reduction.  The rectangle the ray leaves is
+        // skipped (its hit point went through a rotation and is not exactly on the plane any more).
+        const char* ln[3] = {"lr.o.z", "lr.o.y", "lr.o.x"};
+        const char* li[3] = {"lr.inv_d.z", "lr.inv_d.y", "lr.inv_d.x"};
+        const char* la[3] = {"lr.o.x", "lr.o.x", "lr.o.y"};
+        const char* lda[3] = {"lr.d.x", "lr.d.x", "lr.d.y"};
+        const char* lb[3] = {"lr.o.y", "lr.o.z", "lr.o.z"};
+        const char* ldb[3] = {"lr.d.y", "lr.d.z", "lr.d.z"};
+        for (int i = first; i < first + count; ++i) {
+            const DevPrim& p = kp.cprims[i];
+            const int type = __float_as_int_host(p.b.z) & 15;
+            if (type == RT_PRIM_SPHERE || type == RT_PRIM_MOVING) continue;
+            const int g = type - 1;
+            const double ca = 0.5 * ((double)p.a.x + p.a.y), ha = 0.5 * ((double)p.a.y - p.a.x);
+            const double cb = 0.5 * ((double)p.a.z + p.a.w), hb = 0.5 * ((double)p.a.w - p.a.z);
+            o << "        const float u" << i << " = (" << spec_float(p.b.x) << " - " << ln[g] << ") * " << li[g] << ";\n";
+            o << "        float e" << i << " = rect_candidate(u" << i << ", fmaf(u" << i << ", " << lda[g] << ", " << la[g] << " - " << spec_float((float)ca)
+              << "), fmaf(u" << i << ", " << ldb[g] << ", " << lb[g] << " - " << spec_float((float)cb) << "), " << spec_float((float)ha) << ", "
+              << spec_float((float)hb) << ");\n";
+            o << "        e" << i << " = last_prim == " << i << " ? __int_as_float(0x7f800000) : e" << i << ";\n";
+        }
+        for (int i = first; i < first + count; ++i) {
+            const DevPrim& p = kp.cprims[i];
+            const int type = __float_as_int_host(p.b.z) & 15;
+            if (type == RT_PRIM_SPHERE) {
+                o << "        { const float a_ = dot(lr.d, lr.d); const float t_ = sphere_hit<float>(lr.o, lr.d, a_, fast_rcp(a_), mk3(" << spec_float(p.a.x)
+                  << ", " << spec_float(p.a.y) << ", " << spec_float(p.a.z) << "), " << spec_float(p.a.w) << ", " << spec_float(p.b.x) << ", last_prim == " << i
+                  << ", (float)RT_T_MIN, best_t); if (t_ >= 0.0f) { best_t = t_; best = " << i << "; } }\n";
+            } else if (type == RT_PRIM_MOVING) {
+                o << "#error \"instanced moving spheres are rejected at upload\"\n";
+            } else {
+                o << "        { const bool hit = e" << i << " <= best_t; best_t = hit ? e" << i << " : best_t; best = hit ? " << i << " : best; }\n";
+            }
+        }
         o << "    }\n";
     }
     o << "    return best;\n}\n";

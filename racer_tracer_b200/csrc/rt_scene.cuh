@@ -39,6 +39,7 @@
 
 #define RT_MAX_CONST_PRIMS 40   // primitives kept in the kernel-parameter constant bank
 #define RT_MAX_CONST_RECTS 8    // per axis group, fully unrolled with constant-bank operands
+#define RT_MAX_CONST_OBJS 8     // instanced top-level objects (Box + RotateY / Translate) of the linear modes
 #define RT_MAX_IMAGES 8
 #define RT_T_MIN 0.001          // src/renderer.rs:58
 
@@ -126,6 +127,14 @@ struct KParams {
     // constant bank, no load instructions): group 0 = xy, 1 = xz, 2 = yz
     float4 crect_bounds[3][RT_MAX_CONST_RECTS];   // (centre a, half extent a, centre b, half extent b)
     float crect_k[3][RT_MAX_CONST_RECTS];
+    // Instanced top-level objects of the linear modes (the reference's default Sandbox scene: Cornell + two
+    // rotated, translated boxes).  Their primitives follow the four type groups in the linear table.  The
+    // stored Aabb is the object's cull volume (bvh_node.rs:119; RotateY's is not a bounding box, Q14), tested
+    // exactly as Aabb::hit does before the ray is taken into the object's space.
+    int n_cobj;
+    float4 cobj_lo[RT_MAX_CONST_OBJS];   // Aabb min, w = bits(first primitive in the linear table)
+    float4 cobj_hi[RT_MAX_CONST_OBJS];   // Aabb max, w = bits(primitive count | instance index << 8)
+    DevInstance cinst[RT_MAX_CONST_OBJS];
 };
 
 // ---------------------------------------------------------------------------
@@ -150,7 +159,7 @@ struct ConstScene {
     RT_D float4 pn(int i) const { return sh[i].n; }
     RT_D float4 nlo(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }  // no BVH in the constant bank
     RT_D float4 nhi(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
-    RT_D const DevInstance* instances() const { return nullptr; }            // instanced scenes never take this path
+    RT_D const DevInstance* instances() const { return P.cinst; }           // the scene's instance table (<= RT_MAX_CONST_OBJS)
     RT_D bool reference_aabb() const { return false; }
 };
 
@@ -413,6 +422,26 @@ RT_D void rect_group_const(const KParams& P, const RayT<float>& r, int last_prim
     }
 }
 
+RT_D bool aabb_hit_reference(float4 lo, float4 hi, const RayT<float>& r, float t_max);
+
+// The instanced objects of a linear scene, after its plain primitives: cull volume (Aabb::hit verbatim),
+// then the object's primitives against the ray in the object's space — SceneObject::hit through the
+// Translate / RotateY wrappers (translate.rs:23-42, rotate_y.rs:29-66), Boxx::obj_hit (box.rs:82-101).
+template <class Scene>
+RT_D void linear_objects(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& best_t, int& best) {
+#pragma unroll 1
+    for (int k = 0; k < P.n_cobj; ++k) {
+        const float4 lo = P.cobj_lo[k], hi = P.cobj_hi[k];
+        if (!aabb_hit_reference(lo, hi, r, best_t)) continue;
+        const int first = __float_as_int(lo.w), meta = __float_as_int(hi.w);
+        const RayT<float> lr = to_local(P.cinst[meta >> 8], r);
+        for (int p = first; p < first + (meta & 255); ++p) {
+            const float t = prim_test_local(S, p, S.ua(p), S.ub(p), lr, p == last_prim, true, best_t);
+            if (t >= 0.0f) { best_t = t; best = p; }
+        }
+    }
+}
+
 template <bool CONST_RECTS, class Scene>
 RT_D int closest_hit_linear(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& best_t) {
     int best = -1;
@@ -441,6 +470,7 @@ RT_D int closest_hit_linear(const KParams& P, const Scene& S, const RayT<float>&
         rect_group<1>(S, P.lin_end[1], P.lin_end[2], r, last_prim, best_t, best);
         rect_group<0>(S, P.lin_end[2], P.lin_end[3], r, last_prim, best_t, best);
     }
+    linear_objects(P, S, r, last_prim, best_t, best);
     return best;
 }
 
@@ -627,6 +657,9 @@ struct Hit {
 #ifndef RT_SPEC_PRIMS
 #define RT_SPEC_PRIMS 0xF
 #endif
+#ifndef RT_HAS_INSTANCES
+#define RT_HAS_INSTANCES 1    /* a scene-specialised kernel sets 0 when nothing is rotated / translated */
+#endif
 #define RT_HAS_SPHERES (RT_SPEC_PRIMS & 1)
 #define RT_HAS_RECTS (RT_SPEC_PRIMS & 0xE)
 
@@ -669,7 +702,7 @@ template <class Scene>
 RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t) {
     float4 a = S.pa(prim), b = S.pb(prim);
     const int inst = kinds_inst(b.z);
-    if (inst < 0) return make_hit_local(S, prim, a, b, r, t);
+    if (!RT_HAS_INSTANCES || inst < 0) return make_hit_local(S, prim, a, b, r, t);
     const DevInstance in = S.instances()[inst];
     const RayT<float> lr = to_local(in, r);
     Hit h = make_hit_local(S, prim, a, b, lr, t);

@@ -479,3 +479,34 @@ def test_processes_store_their_tiles_into_one_shared_frame(cfg):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29571", os.path.join(root, "tools", "ipc_tiles_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "IPC_TILES_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_instanced_scene_linear_path_equals_the_bvh_path(renderer, oracle, cfg):
+    """The reference's default Sandbox scene (Cornell + two rotated, translated boxes) fits the linear modes:
+    plain rectangles, then per instanced object the stored Aabb as cull volume (Aabb::hit verbatim, Q11/Q14)
+    and its sides in the object's space.  Same primary hits and the same paths as the BVH traversal of the
+    same scene, precompiled and scene-specialised."""
+    w, h = 300, 300
+    job = job_for("sandbox_boxes", cfg, w, h)
+    p = harness.make_params(w, h, 1, 20, fixed_jitter=1)
+    q = harness.make_params(w, h, 8, 20, seed=6)
+    renderer.upload(job)
+    ids_lin = renderer.primary_aov(p, 32)[0]
+    img_lin = renderer.render(q)
+    img_spec = renderer.render(harness.make_params(w, h, 8, 20, seed=6, specialize=1))
+    os.environ["RC_SCENE_MODE"] = "smem"
+    try:
+        renderer.upload(job)
+        ids_bvh = renderer.primary_aov(p, 32)[0]
+        img_bvh = renderer.render(q)
+        with pytest.raises(capi.RacerCudaError):      # the BVH modes have no scene-specialised kernel
+            renderer.render(harness.make_params(w, h, 8, 20, seed=6, specialize=1))
+    finally:
+        del os.environ["RC_SCENE_MODE"]
+    assert (ids_lin != ids_bvh).mean() < 1e-3          # exact ties only: the two paths order primitives differently
+    for name, img in (("precompiled", img_lin), ("specialised", img_spec)):
+        err = np.abs(img - img_bvh).max(axis=2)
+        # different kernels: rounding differences flip a few long paths (measured: 0.01 % of the pixels)
+        assert np.median(err) < 1e-6 and float((err > 2e-3).mean()) < 0.01, name
+    ref = oracle.render(job, q)
+    assert float((np.abs(img_spec - ref).max(axis=2) > 2e-3).mean()) < 0.01
