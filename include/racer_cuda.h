@@ -117,7 +117,9 @@ typedef struct rc_instance {
  * = number of consecutive primitives (1, or 6 for the sides of a Box, tested
  * in order like Boxx::obj_hit, src/geometry/box.rs:82-101).  Node 0 is the
  * root.  n_nodes == 0 selects the linear closest-hit loop over all primitives
- * in index order (the reference's src/shared_scene.rs:37-53 semantics).
+ * in index order (the reference's src/shared_scene.rs:37-53 semantics) — for
+ * scenes whose table fits a CTA's staging budget (a few hundred primitives);
+ * larger ones get a BVH built on the GPU from prim_aabb (rc_build_lbvh).
  * Primitives must be stored in the tree's depth-first (left-to-right) leaf
  * order so that "later visited wins an exact tie" (bvh_node.rs:124-129,
  * sphere.rs:53) reduces to "higher index wins". */

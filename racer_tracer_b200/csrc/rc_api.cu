@@ -839,6 +839,18 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     }
     CUDA_TRY(cudaSetDevice(ctx->devs[0].device));
     ctx->has_scene = true;
+    // A scene uploaded WITHOUT a BVH whose linear table would not fit the shared-memory staging budget gets one
+    // built on the device (the linear loop stays what small scenes use; a large one would be O(N) per ray and
+    // its table would not fit a CTA).  Results differ from the linear order only on exact ties (Q13).
+    if (s->n_nodes == 0 && ctx->mode == RT_MODE_SMEM_LINEAR && (size_t)s->n_prims * sizeof(DevPrim) > RC_SMEM_STAGE_LIMIT) {
+        if (ctx->objects.empty()) {
+            if ((size_t)s->n_prims * sizeof(DevPrim) > 200 * 1024)
+                return fail(RC_ERR_INVALID, "a scene this large needs BVH nodes, or prim_aabb so that rc_upload_scene can build them on the GPU");
+        } else {
+            int rc2 = rc_build_lbvh(ctx);
+            if (rc2 != RC_OK) return rc2;
+        }
+    }
     return RC_OK;
 }
 

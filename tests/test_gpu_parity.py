@@ -510,3 +510,61 @@ def test_instanced_scene_linear_path_equals_the_bvh_path(renderer, oracle, cfg):
         assert np.median(err) < 1e-6 and float((err > 2e-3).mean()) < 0.01, name
     ref = oracle.render(job, q)
     assert float((np.abs(img_spec - ref).max(axis=2) > 2e-3).mean()) < 0.01
+
+
+def many_spheres_job(cfg, n, w, h, seed=5):
+    """n small lambertian / metal spheres in a slab, no host BVH (n_nodes = 0), default sky."""
+    rng = np.random.default_rng(seed)
+    fs = harness.FlatScene()
+    textures, materials, objects = [], [], {}
+    for k in range(8):
+        t = capi.rc_texture()
+        t.type = capi.RC_TEX_SOLID
+        t.color[:] = rng.uniform(0.2, 0.9, 3).tolist()
+        textures.append(t)
+        m = capi.rc_material()
+        m.type, m.texture, m.param = (capi.RC_MAT_METAL if k == 7 else capi.RC_MAT_LAMBERTIAN), k, 0.1
+        materials.append(m)
+    centres = rng.uniform([-30, -8, -30], [30, 8, 30], size=(n, 3))
+    radii = rng.uniform(0.15, 0.45, n)
+    for i in range(n):
+        c, r = centres[i].tolist(), float(radii[i])
+        lo, hi = [c[a] - r for a in range(3)], [c[a] + r for a in range(3)]
+        key = f"s{i:06d}"
+        objects[key] = harness.TopObject(key, [harness.Prim(capi.RC_PRIM_SPHERE, c + [r, 0.0], i % 8, 0)], lo, hi, c)
+    harness._flatten(fs, objects, textures, materials, [], [], use_bvh=False)
+    fs.c.bg_type = capi.RC_BG_SKY
+    fs.c.bg_a[:] = [1.0, 1.0, 1.0]
+    fs.c.bg_b[:] = [0.5, 0.7, 1.0]
+    cam = harness.make_camera({"vfov": 40.0, "aperture": 0.0, "focus_distance": 10.0, "pos": [0.0, 25.0, 70.0],
+                               "look_at": [0.0, 0.0, 0.0]}, w, h)
+    return harness.Job(fs, cam, harness.make_tone_map("none"), cfg, w, h)
+
+
+def test_large_scene_gets_a_gpu_built_bvh(renderer, oracle, cfg):
+    """9 000 spheres uploaded without nodes: too many for the linear loop, so rc_upload_scene builds the LBVH
+    on the device — the multi-pass (global-memory) bitonic sort and the global-memory traversal mode, which
+    the small scenes never reach.  Valid tree; f64 primary hits bit-exact against the oracle on the same tree;
+    same-stream image within tolerance."""
+    n, w, h = 9000, 200, 150
+    job = many_spheres_job(cfg, n, w, h)
+    assert job.scene.c.n_nodes == 0
+    renderer.upload(job)
+    nodes, order = renderer.get_bvh(n)
+    assert len(nodes) == 2 * n - 1
+    check_tree(nodes, order, n, job.scene.np["prim_aabb"])
+    same_tree = harness.with_bvh(job, nodes, order)
+    p = harness.make_params(w, h, 1, 20, fixed_jitter=1)
+    ids, t, nrm, pt = renderer.primary_aov(p, 64)
+    oids, ot, onrm, opt = oracle.primary_aov(same_tree, p)
+    assert (oids != 0).mean() > 0.2
+    assert np.array_equal(ids, oids) and np.array_equal(t, ot) and np.array_equal(nrm, onrm)
+    assert (renderer.primary_aov(p, 32)[0] != oids).mean() < 2e-3
+    q = harness.make_params(w, h, 4, 20, seed=2)
+    img, ref = renderer.render(q), oracle.render(same_tree, q)
+    err = np.abs(img - ref).max(axis=2)
+    # thousands of sub-unit spheres seen from 70 units away: an fp32 rounding flips a secondary ray onto a
+    # neighbouring sphere far more often than in the BASELINE scenes (7.7 % of the pixels at 4 spp, measured);
+    # most pixels still agree to 1e-5 and the images agree in the mean
+    assert float((err > 2e-3).mean()) < 0.12 and np.median(err) < 1e-5
+    assert np.abs(img.mean(axis=(0, 1)) - ref.mean(axis=(0, 1))).max() < 2e-3
