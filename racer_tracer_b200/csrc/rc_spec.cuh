@@ -166,16 +166,28 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
             vb[i - begin] = rel_origin(ob[g], c.z);
         }
         o << "    {\n";
+        const bool chain = std::getenv("RC_SPEC_SELECT") == nullptr;   // predicate chain (default) or candidate + select reduction
         for (int i = begin; i < end; ++i) {
             const DevPrim& p = kp.cprims[i];
             const float4 c = kp.crect_bounds[g][i - begin];
             o << "        const float t" << i << " = (" << spec_float(p.b.x) << " - " << on[g] << ") * " << in[g] << ";\n";
+            if (chain) {
+                o << "        const float xa" << i << " = fmaf(t" << i << ", " << da[g] << ", " << va[i - begin] << "), xb" << i << " = fmaf(t" << i
+                  << ", " << db[g] << ", " << vb[i - begin] << ");\n";
+                continue;
+            }
             o << "        const float c" << i << " = rect_candidate(t" << i << ", fmaf(t" << i << ", " << da[g] << ", " << va[i - begin]
               << "), fmaf(t" << i << ", " << db[g] << ", " << vb[i - begin] << "), " << spec_float(c.y) << ", " << spec_float(c.w) << ");\n";
         }
-        for (int i = begin; i < end; ++i)
-            o << "        { const bool hit = c" << i << " <= best_t; best_t = hit ? c" << i << " : best_t; best = hit ? " << i
-              << " : best; }\n";
+        for (int i = begin; i < end; ++i) {
+            const float4 c = kp.crect_bounds[g][i - begin];
+            if (chain)
+                o << "        rect_closest(t" << i << ", xa" << i << ", xb" << i << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", " << i
+                  << ", best_t, best);\n";
+            else
+                o << "        { const bool hit = c" << i << " <= best_t; best_t = hit ? c" << i << " : best_t; best = hit ? " << i
+                  << " : best; }\n";
+        }
         o << "    }\n";
     }
     // instanced objects: cull volume, ray into the object's space (constants spelled out), then its rectangles
@@ -209,11 +221,10 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
             const int g = type - 1;
             const double ca = 0.5 * ((double)p.a.x + p.a.y), ha = 0.5 * ((double)p.a.y - p.a.x);
             const double cb = 0.5 * ((double)p.a.z + p.a.w), hb = 0.5 * ((double)p.a.w - p.a.z);
-            o << "        const float u" << i << " = (" << spec_float(p.b.x) << " - " << ln[g] << ") * " << li[g] << ";\n";
-            o << "        float e" << i << " = rect_candidate(u" << i << ", fmaf(u" << i << ", " << lda[g] << ", " << la[g] << " - " << spec_float((float)ca)
-              << "), fmaf(u" << i << ", " << ldb[g] << ", " << lb[g] << " - " << spec_float((float)cb) << "), " << spec_float((float)ha) << ", "
-              << spec_float((float)hb) << ");\n";
-            o << "        e" << i << " = last_prim == " << i << " ? __int_as_float(0x7f800000) : e" << i << ";\n";
+            // the rectangle the ray leaves gets t = -1, which fails t >= t_min
+            o << "        const float u" << i << " = last_prim == " << i << " ? -1.0f : (" << spec_float(p.b.x) << " - " << ln[g] << ") * " << li[g] << ";\n";
+            o << "        const float ea" << i << " = fmaf(u" << i << ", " << lda[g] << ", " << la[g] << " - " << spec_float((float)ca) << "), eb" << i
+              << " = fmaf(u" << i << ", " << ldb[g] << ", " << lb[g] << " - " << spec_float((float)cb) << ");\n";
         }
         for (int i = first; i < first + count; ++i) {
             const DevPrim& p = kp.cprims[i];
@@ -225,7 +236,9 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
             } else if (type == RT_PRIM_MOVING) {
                 o << "#error \"instanced moving spheres are rejected at upload\"\n";
             } else {
-                o << "        { const bool hit = e" << i << " <= best_t; best_t = hit ? e" << i << " : best_t; best = hit ? " << i << " : best; }\n";
+                const double ha = 0.5 * ((double)p.a.y - p.a.x), hb = 0.5 * ((double)p.a.w - p.a.z);
+                o << "        rect_closest(u" << i << ", ea" << i << ", eb" << i << ", " << spec_float((float)ha) << ", " << spec_float((float)hb) << ", " << i
+                  << ", best_t, best);\n";
             }
         }
         o << "    }\n";

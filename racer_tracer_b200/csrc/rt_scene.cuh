@@ -357,6 +357,23 @@ RT_D float rect_candidate(float t, float xa, float xb, float ha, float hb) {
     return t;
 }
 
+// rect_candidate() and the closest-hit update in one predicate chain (scene-specialised kernels): if the
+// rectangle is hit (bounds, t >= t_min) and t <= best_t, it becomes the best hit — `<=`: a later rectangle
+// wins an exact tie (sphere.rs:53 / shared_scene.rs:37-53).  Four compares and two predicated moves per
+// rectangle (ptxas turns the moves into selects: 6 instructions against 7 for rect_candidate + the select
+// reduction).  Packing the index into the low mantissa bits of t would make the update one predicated FMNMX
+// (5 instructions) at the price of 3 bits of t; not taken.
+RT_D void rect_closest(float t, float xa, float xb, float ha, float hb, int index, float& best_t, int& best) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.f32 p, %2, %4;\n\t"
+        "setp.le.and.f32 p, %3, %5, p;\n\t"
+        "setp.ge.and.f32 p, %6, 0f3A83126F, p;\n\t"   /* t >= 0.001f */
+        "setp.le.and.f32 p, %6, %0, p;\n\t"
+        "@p mov.f32 %0, %6;\n\t"
+        "@p mov.s32 %1, %7;\n\t}"
+        : "+f"(best_t), "+r"(best) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "r"(index));
+}
+
 // Linear closest hit over the TYPE-SORTED table (spheres, xy, xz, yz rects):
 // one tight loop per primitive kind with the axes hard-wired, no per-primitive
 // type decode and no early exits — every rectangle is a fixed sequence of
