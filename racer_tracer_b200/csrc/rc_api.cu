@@ -345,6 +345,8 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         for (size_t i = 0; i < d.tex.size(); ++i) kp.images[i] = d.tex[i];
         kp.segment_counter = d.counter.p;
         partition(kp, p, p->rank * n_dev + k, parts);
+        // tile culling needs one ray origin per tile (no lens), primitives that stay where they are, and a linear mode
+        kp.tile_cull = (!kp.lens_enabled && !kp.has_motion && !p->fixed_jitter && std::getenv("RC_NO_TILE_CULL") == nullptr) ? 1 : 0;
         if (ctx->preview_sw > 0) {   // scaled preview: p->width/height is the block grid, u and v refer to the screen
             kp.px_scale_x = ctx->preview_sw; kp.px_scale_y = ctx->preview_sh;
             kp.wm1 = (float)(ctx->preview_w - 1);

@@ -143,6 +143,75 @@ RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float
 }
 
 // ---------------------------------------------------------------------------
+// Tile culling.  With a pinhole camera every primary ray of a tile leaves the same point inside the frustum
+// spanned by the tile's corner rays (jitter included).  A primitive (or an instanced object's cull box) that
+// lies entirely outside one of the four side planes cannot be hit by any of them; if that holds for EVERY
+// primitive, each sample of the tile is one segment that ends in the background, and the CTA adds the
+// background radiance sample by sample (same order, same values as the general loop: bit-identical sums)
+// without intersecting anything.  Conservative by construction (bounding spheres / corner tests with a
+// margin); half of the Cornell frame and most of the clown frame are such tiles.
+// Returns true if something may be hit.  All threads of the CTA must call it.
+// ---------------------------------------------------------------------------
+RT_D bool tile_may_hit(const KParams& P, const DevPrim* prims, int tx, int ty) {
+    // corner directions: u in [x0, x1 + 1) / (W - 1), v in [y0, y1 + 1) / (H - 1), padded by a hundredth of a pixel
+    const float u0 = ((float)(tx * RT_TILE_W * P.px_scale_x) - 0.01f) / P.wm1;
+    const float u1 = ((float)((tx * RT_TILE_W + RT_TILE_W - 1) * P.px_scale_x) + 1.01f) / P.wm1;
+    const float v0 = ((float)(ty * RT_TILE_H * P.px_scale_y) - 0.01f) * P.inv_hm1;
+    const float v1 = ((float)((ty * RT_TILE_H + RT_TILE_H - 1) * P.px_scale_y) + 1.01f) * P.inv_hm1;
+    const vec3f c = P.cam.upper_left_corner, hx = P.cam.horizontal, vy = P.cam.vertical;
+    const vec3f d00 = c + u0 * hx - v0 * vy, d10 = c + u1 * hx - v0 * vy, d01 = c + u0 * hx - v1 * vy, d11 = c + u1 * hx - v1 * vy;
+    const vec3f dc = c + (0.5f * (u0 + u1)) * hx - (0.5f * (v0 + v1)) * vy;
+    auto cross3 = [](vec3f a, vec3f b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); };
+    vec3f n[4] = {cross3(d00, d01), cross3(d10, d11), cross3(d00, d10), cross3(d01, d11)};   // left, right, top, bottom
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        n[k] = unit_vector(n[k]);
+        if (dot(n[k], dc) < 0.0f) n[k] = -n[k];   // inward
+    }
+    const vec3f o = P.cam.origin;
+    // is the point set {q_j} (+ radius) entirely outside one side plane?
+    auto outside = [&](const vec3f* q, int nq, float radius) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bool all_out = true;
+            for (int j = 0; j < nq; ++j) {
+                const vec3f rel = q[j] - o;
+                const float margin = radius + 1e-5f * (fabsf(rel.x) + fabsf(rel.y) + fabsf(rel.z)) + 1e-6f;
+                if (dot(n[k], rel) >= -margin) all_out = false;
+            }
+            if (all_out) return true;
+        }
+        return false;
+    };
+    bool may = false;
+    for (int i = threadIdx.x; i < P.n_prims; i += blockDim.x) {
+        const float4 a = prims[i].a, b = prims[i].b;
+        if (kinds_inst(b.z) >= 0) continue;               // instanced: decided by the object's cull box below
+        const int type = kinds_prim(b.z);
+        if (RT_IS_SPHERE(type)) {
+            const vec3f ctr = mk3(a.x, a.y, a.z);
+            if (!outside(&ctr, 1, fabsf(a.w))) may = true;
+        } else {
+            vec3f q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float pa = (j & 1) ? a.y : a.x, pb = (j & 2) ? a.w : a.z;
+                q[j] = type == RT_PRIM_XY ? mk3(pa, pb, b.x) : (type == RT_PRIM_XZ ? mk3(pa, b.x, pb) : mk3(b.x, pa, pb));
+            }
+            if (!outside(q, 4, 0.0f)) may = true;
+        }
+    }
+    for (int k = threadIdx.x; k < P.n_cobj; k += blockDim.x) {
+        const float4 lo = P.cobj_lo[k], hi = P.cobj_hi[k];
+        vec3f q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = mk3((j & 1) ? hi.x : lo.x, (j & 2) ? hi.y : lo.y, (j & 4) ? hi.z : lo.z);
+        if (!outside(q, 8, 0.0f)) may = true;
+    }
+    return __syncthreads_or(may ? 1 : 0) != 0;
+}
+
+// ---------------------------------------------------------------------------
 // Shade one hit: emission + scatter (src/renderer.rs:59-69, src/material/*.rs).
 // Returns true if the path continues with (o, d) and throughput T updated;
 // `emit` receives the emitted radiance.
@@ -262,6 +331,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     // ray_color's `emitted + attenuation * recurse` collapses to throughput x terminal radiance.
     vec3f sum = mk3(0.0f, 0.0f, 0.0f);
     vec3f o = mk3(0.0f, 0.0f, 0.0f), d = o, T = o;
+    const vec3f T_ONE = mk3(1.0f, 1.0f, 1.0f);
     float time = 0.0f;         // Ray::time of the path (scattered rays inherit it, lambertian.rs:36 etc.)
     int s = valid ? s_first : s_last;
     int depth_left = 0;        // > 0: this lane is on a path that may still trace that many segments; 0: no path
@@ -272,6 +342,28 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         const float n = (float)(s_last - s);
         sum = mk3(n, n, n);
         s = s_last;
+    }
+
+    if (P.tile_cull && (MODE == RT_MODE_CONST_LINEAR || MODE == RT_MODE_SMEM_LINEAR) && P.max_depth > 0) {
+        if (!tile_may_hit(P, L.prims, tx, ty)) {
+            // every sample of this tile is one segment into the background (renderer.rs:78-88), T = 1
+            if (valid) {
+                nseg += (unsigned)(s_last - s);
+#pragma unroll 1
+                for (; s < s_last; ++s) {
+                    if (RT_SPEC_BG_BLACK) { s = s_last; break; }
+                    vec3f bg;
+                    if (__float_as_int(P.bg_a.w) == 0) {   // Sky: depends on the sample's direction
+                        const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1((uint32_t)s, 0u, RT_TAG_PATH), P.ks);
+                        const float vjit = P.fixed_jitter ? 0.5f : u16lo(rnd);
+                        camera_ray<SAMPLER, ROUNDS>(P, pc, (uint32_t)s, vjit, o, d, time);
+                        bg = background_color(P, d);
+                    } else bg = mk3(P.bg_a.x, P.bg_a.y, P.bg_a.z);
+                    sum = sum + T_ONE * bg;
+                }
+            }
+            s = s_last;
+        }
     }
 
 #pragma unroll 1

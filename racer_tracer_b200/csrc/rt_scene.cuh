@@ -109,6 +109,8 @@ struct KParams {
     int lin_end[4];             // type-sorted linear table: [0,lin_end[0]) spheres, then xy, xz, yz rects
     int n_perlin;
     int lens_enabled;
+    int tile_cull;              // 1: a CTA first asks whether its tile's primary rays can hit anything at all (pinhole
+                                // camera, nothing moves, linear modes); if not, its samples are background only
     int has_motion;             // the scene has a moving sphere: primary rays carry a time (camera.rs:335)
     int ref_aabb;               // scenes with RotateY: BVH culling uses the reference's per-axis Aabb::hit
     const DevPrim* prims;       // all primitives, BVH depth-first order (global memory)

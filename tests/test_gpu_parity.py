@@ -568,3 +568,36 @@ def test_large_scene_gets_a_gpu_built_bvh(renderer, oracle, cfg):
     # most pixels still agree to 1e-5 and the images agree in the mean
     assert float((err > 2e-3).mean()) < 0.12 and np.median(err) < 1e-5
     assert np.abs(img.mean(axis=(0, 1)) - ref.mean(axis=(0, 1))).max() < 2e-3
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "three_balls", "clown", "noise_and_textures", "sandbox_boxes"])
+def test_tile_culling_changes_nothing(renderer, cfg, name):
+    """Tiles whose primary rays cannot hit anything (frustum test against every primitive / object cull box)
+    skip the intersection and add the background sample by sample: the image and the segment count are
+    bit-identical to a render with the test switched off, precompiled and scene-specialised."""
+    w, h, spp = 400, 225, 8
+    job = job_for(name, cfg, w, h)
+    if job.camera.lens_radius != 0.0:
+        pytest.skip("culling needs a pinhole camera")
+    renderer.upload(job)
+    for spec in (0, 2):
+        p = harness.make_params(w, h, spp, 20, seed=12, specialize=spec)
+        a = renderer.render(p)
+        seg_a = renderer.stats().segments
+        os.environ["RC_NO_TILE_CULL"] = "1"
+        try:
+            b = renderer.render(p)
+            seg_b = renderer.stats().segments
+        finally:
+            del os.environ["RC_NO_TILE_CULL"]
+        assert np.array_equal(a, b) and seg_a == seg_b, (name, spec)
+    # the preview renderer goes through the same test with scaled pixel coordinates
+    sw, sh = harness.preview_scales(cfg, w, h)
+    pv = harness.make_params(w, h, 8, 10, seed=3)
+    a = renderer.render_preview(pv, sw, sh)
+    os.environ["RC_NO_TILE_CULL"] = "1"
+    try:
+        b = renderer.render_preview(pv, sw, sh)
+    finally:
+        del os.environ["RC_NO_TILE_CULL"]
+    assert np.array_equal(a, b)
