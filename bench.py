@@ -47,6 +47,11 @@ WORKLOADS = {
 }
 
 
+# HBM traffic of the dominant kernel per launch, from the committed ncu capture (bytes); the megakernel reads the
+# accumulation buffer once and its stores stay in L2 until evicted, independent of spp
+NCU_DRAM_BYTES_PER_LAUNCH = {"cornell_box_1080p_1024spp": 24907520 + 256}
+
+
 def scene_file(scene):
     return scene if scene == "random" else os.path.join(ROOT, "tests", "golden", "scenes", scene + ".yml")
 
@@ -356,6 +361,7 @@ def main():
                        "rng": f"philox2x32-{args.rng_rounds}", "split": split_name,
                        "kernel": "scene-specialised (NVRTC)" if spec else "precompiled",
                        "bvh": "gpu-lbvh" if args.lbvh else ("host" if job.scene.c.n_nodes else "none"),
+                       "tile_culling": "off" if os.environ.get("RC_NO_TILE_CULL") or job.camera.lens_radius != 0.0 else "on (bit-identical images)",
                        "l2": "256 MiB buffer written between timed iterations (flush)",
                        "parallelism": f"tiles{world}" if split_name == "tiles" else f"samples{world}",
                        "exchange": ("none" if world == 1 else ("in-kernel peer stores into rank 0's frame buffer (CUDA IPC, NVLink) + 1-element all-reduce"
@@ -392,7 +398,9 @@ def main():
             A_used = A_lin if job.scene.c.n_prims <= 8 else A
             achieved = value / world * A_used / 1e12
             line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": fp32_tflops, "unit": "TFLOP/s",
-                                "frac": achieved / fp32_tflops, "traffic": None,
+                                "frac": achieved / fp32_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
+                                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the megakernel launch, ncu --set full "
+                                                  "(profiles/r01_megakernel_v11_specialised_ncu.md): the accumulation buffer, once",
                                 "peak_source": "FFMA micro-benchmark in this run (rc_fp32_peak), per GPU",
                                 "flops_per_sample": A_used, "lane_ginstr_per_s_peak": lane_ginstr,
                                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_kind,
