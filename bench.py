@@ -261,35 +261,36 @@ def main():
         if shared is not None:
             frame = shared[step_no[0] & 1]
             step_no[0] += 1
-            r.render_tiles_into(p, frame)
-            launches[0] += int(r.stats().kernel_launches)
+            r.render_tiles_into(p, frame)     # enqueues only: the library does not drain the stream
             dist.all_reduce(join)             # stream-ordered join; the pixels already travelled inside the kernel
             if rank == 0:
                 r.finalize(frame, w, h, spp, rgb.data_ptr())
-                launches[0] += 1
             return
         accum.zero_()
         r.render_accumulate(p, accum.data_ptr())
-        launches[0] += int(r.stats().kernel_launches) + 1
         if world > 1:
             # exchange step: partial sample sums (or, with RC_BENCH_NCCL_GATHER, disjoint tiles) summed onto rank 0
             dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0:
             r.finalize(accum.data_ptr(), w, h, spp, rgb.data_ptr())
-            launches[0] += 1
+
+    def launches_per_step():
+        """Our kernels per step: the render call's own launches (read back after a step), + the zero-fill of the
+        accumulation buffer when there is one, + finalize on rank 0."""
+        return int(r.stats().kernel_launches) + (0 if shared is not None else 1) + (1 if rank == 0 else 0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):     # (W = 0 still runs one: the launch count is read after a step)
         step()
     barrier()
     sampler_thread = ClockSampler(local_rank) if rank == 0 else None
     if sampler_thread:
         sampler_thread.start()
-    launches[0] = 0
+    per_step = launches_per_step()      # after the warm-up steps; the timed loop itself never reads statistics back
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     barrier()
@@ -299,8 +300,9 @@ def main():
         ev[i][0].record(stream)
         step()
         ev[i][1].record(stream)
-        kernel_ms.append(r.stats().gpu_ms)
     barrier()
+    kernel_ms.append(r.stats().gpu_ms)   # of the last step
+    launches[0] = per_step * args.steps
     wall = time.perf_counter() - wall0
     if sampler_thread:
         sampler_thread.stop_flag.set()

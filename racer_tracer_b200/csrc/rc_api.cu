@@ -107,6 +107,7 @@ struct rc_ctx {
     std::vector<int> prim_order;       // device primitive i = uploaded primitive prim_order[i] (empty: identity)
     bool lbvh = false;
     bool overwrite = false;            // set for the duration of rc_render_tiles_into
+    bool stats_pending = false;        // the last render's time / counters have not been read back yet
     std::vector<void*> shared_owned, shared_opened;   // rc_shared_alloc / rc_shared_open
     int n_prims = 0, n_perlin = 0;
     bool instanced = false;
@@ -431,10 +432,23 @@ int ensure_accum(rc_ctx* ctx, const rc_params* p, bool device0_too) {
     return RC_OK;
 }
 
+// End of a render call: the stop event is recorded, nothing is waited for.  Time and segment counters are
+// resolved when somebody asks (rc_get_stats), so that a caller who only enqueues work — bench.py's timed
+// loop, a multi-rank job — never has its stream drained by the library.
 int finish_stats(rc_ctx* ctx, const rc_params* p) {
     DeviceState& d0 = ctx->devs[0];
     CUDA_TRY(cudaSetDevice(d0.device));
     CUDA_TRY(cudaEventRecord(d0.ev1, d0.stream));
+    const int world = p->world > 0 ? p->world : 1;
+    ctx->stats.samples = (uint64_t)p->width * p->height * p->samples / world;
+    ctx->stats_pending = true;
+    return RC_OK;
+}
+
+int resolve_stats(rc_ctx* ctx) {
+    if (!ctx->stats_pending) return RC_OK;
+    DeviceState& d0 = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d0.device));
     CUDA_TRY(cudaEventSynchronize(d0.ev1));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, d0.ev0, d0.ev1));
@@ -443,12 +457,12 @@ int finish_stats(rc_ctx* ctx, const rc_params* p) {
     for (auto& d : ctx->devs) {
         unsigned long long v = 0;
         CUDA_TRY(cudaSetDevice(d.device));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
         CUDA_TRY(cudaMemcpy(&v, d.counter.p, sizeof(v), cudaMemcpyDeviceToHost));
         segs += v;
     }
     ctx->stats.segments = segs;
-    const int world = p->world > 0 ? p->world : 1;
-    ctx->stats.samples = (uint64_t)p->width * p->height * p->samples / world;
+    ctx->stats_pending = false;
     CUDA_TRY(cudaSetDevice(d0.device));
     return RC_OK;
 }
@@ -1317,6 +1331,8 @@ int64_t rc_spec_source(const rc_scene* scene, char* out, int64_t capacity) {
 
 int rc_get_stats(rc_ctx* ctx, rc_stats* out) {
     if (!ctx || !out) return fail(RC_ERR_INVALID, "ctx or out is NULL");
+    int rc = resolve_stats(ctx);
+    if (rc != RC_OK) return rc;
     *out = ctx->stats;
     return RC_OK;
 }
