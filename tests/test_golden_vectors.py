@@ -1,0 +1,65 @@
+"""Golden vectors (tests/golden/vectors/*.npz, written by tools/make_golden_vectors.py from the CPU oracle).
+
+The reference has no golden outputs of its own and cannot be run here (parity unpinned), so
+these pin OUR restatement: the CPU test fails if the oracle's arithmetic or the RNG stream specification
+drifts; the GPU test compares the CUDA path with the committed vectors directly, without the oracle in the
+loop."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SCENES_X
+from racer_tracer_b200 import harness
+
+VEC = os.path.join(ROOT, "tests", "golden", "vectors")
+spec = importlib.util.spec_from_file_location("make_golden_vectors", os.path.join(ROOT, "tools", "make_golden_vectors.py"))
+gen = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(gen)
+
+
+@pytest.mark.parametrize("name", SCENES_X)
+def test_oracle_reproduces_the_golden_vectors(cfg, name):
+    want = np.load(os.path.join(VEC, name + ".npz"))
+    got = gen.vectors(name, cfg)
+    assert sorted(want.files) == sorted(got)
+    assert np.array_equal(got["aov_ids"], want["aov_ids"])
+    hit = want["aov_ids"] != 0
+    assert hit.any() and np.array_equal(got["aov_t"][~hit], want["aov_t"][~hit])
+    # f64 arithmetic is deterministic; libm (sin / cos / acos / cbrt / pow) may differ by an ulp between hosts
+    assert np.allclose(got["aov_t"][hit], want["aov_t"][hit], rtol=1e-13, atol=0)
+    assert np.allclose(got["aov_normal"], want["aov_normal"], rtol=0, atol=1e-13)
+    assert np.allclose(got["image"], want["image"], rtol=0, atol=1e-9)
+    if "preview" in want.files:
+        assert np.allclose(got["preview"], want["preview"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SCENES_X)
+def test_cuda_path_matches_the_golden_vectors(renderer, cfg, name):
+    want = np.load(os.path.join(VEC, name + ".npz"))
+    path = name if name == "random" else os.path.join(ROOT, "tests", "golden", "scenes", name + ".yml")
+    job = harness.prepare_job(path, cfg, 64, 48, seed=0, image_dirs=[gen.IMAGES])
+    renderer.upload(job)
+    p = harness.make_params(64, 48, 1, 20, fixed_jitter=1)
+    ids, t, nrm, _ = renderer.primary_aov(p, 64)        # the reference's f64 operation order: bit-exact ids
+    assert np.array_equal(ids.reshape(48, 64), want["aov_ids"])
+    hit = want["aov_ids"] != 0
+    assert np.allclose(t.reshape(48, 64)[hit], want["aov_t"][hit], rtol=1e-13, atol=0)
+    ids32, t32, _, _ = renderer.primary_aov(p, 32)      # the renderer's fp32 intersectors
+    same = (ids32.reshape(48, 64) == want["aov_ids"])
+    assert same.mean() > 0.998
+    both = hit & same
+    rel = np.abs(t32.reshape(48, 64)[both] - want["aov_t"][both]) / want["aov_t"][both]
+    assert np.quantile(rel, 0.999) < 1e-5               # north_star: hit t within 1e-5 relative
+    job2 = harness.prepare_job(path, cfg, 48, 36, seed=0, image_dirs=[gen.IMAGES])
+    renderer.upload(job2)
+    for spec_mode in (0, 2):
+        img = renderer.render(harness.make_params(48, 36, 4, 20, seed=1, specialize=spec_mode))
+        err = np.abs(img - want["image"]).max(axis=2)
+        assert float((err > 2e-3).mean()) < 0.04 and np.median(err) < 1e-5, (name, spec_mode)
+    if "preview" in want.files:
+        sw, sh = (int(v) for v in want["preview_scale"])
+        pv = renderer.render_preview(harness.make_params(48, 36, 6, 10, seed=1), sw, sh)
+        assert float((np.abs(pv - want["preview"]).max(axis=2) > 2e-3).mean()) < 0.04
