@@ -184,8 +184,9 @@ def main():
     ap.add_argument("--sampler", default="direct", choices=["direct", "rejection"])
     ap.add_argument("--rng-rounds", type=int, default=10)
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling runs only)")
-    ap.add_argument("--specialize", type=int, default=int(os.environ.get("RC_SPECIALIZE", "1")), choices=[0, 1, 2],
-                    help="1: scene compiled into the megakernel with NVRTC (default); 0: precompiled kernels")
+    ap.add_argument("--specialize", type=int, default=int(os.environ.get("RC_SPECIALIZE", "2")), choices=[0, 1, 2],
+                    help="2 (default): scene compiled into the megakernel with NVRTC, precompiled kernel if that is impossible "
+                         "(which one ran is reported in config.kernel); 1: the same but fail instead; 0: precompiled kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lbvh", action="store_true", help="rebuild the BVH on the GPU (rc_build_lbvh) after the upload")
     args = ap.parse_args()
@@ -218,8 +219,7 @@ def main():
     variant = capi.RC_VARIANT_MEGAKERNEL if args.variant == "megakernel" else capi.RC_VARIANT_WAVEFRONT
     sampler = capi.RC_SAMPLER_DIRECT if args.sampler == "direct" else capi.RC_SAMPLER_REJECTION
     spec = args.specialize if (args.variant == "megakernel" and args.sampler == "direct" and args.rng_rounds == 10) else 0
-    if spec == 1 and args.workload.startswith("random"):
-        spec = 2     # ~480 primitives do not fit the constant-bank path: precompiled BVH kernels
+
     params = harness.make_params(w, h, spp, depth, seed=0, variant=variant, sampler=sampler, split=split,
                                  rank=rank, world=world, rng_rounds=args.rng_rounds, specialize=spec)
 
@@ -291,6 +291,7 @@ def main():
     if sampler_thread:
         sampler_thread.start()
     per_step = launches_per_step()      # after the warm-up steps; the timed loop itself never reads statistics back
+    used_specialised = bool(r.stats().specialized)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     barrier()
@@ -361,7 +362,7 @@ def main():
             "config": {"workload": args.workload, "scene": scene + ".yml", "width": w, "height": h, "spp": spp,
                        "max_depth": depth, "variant": args.variant, "sampler": args.sampler,
                        "rng": f"philox2x32-{args.rng_rounds}", "split": split_name,
-                       "kernel": "scene-specialised (NVRTC)" if spec else "precompiled",
+                       "kernel": "scene-specialised (NVRTC)" if used_specialised else "precompiled",
                        "bvh": "gpu-lbvh" if args.lbvh else ("host" if job.scene.c.n_nodes else "none"),
                        "tile_culling": "off" if os.environ.get("RC_NO_TILE_CULL") or job.camera.lens_radius != 0.0 else "on (bit-identical images)",
                        "l2": "256 MiB buffer written between timed iterations (flush)",

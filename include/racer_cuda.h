@@ -240,7 +240,8 @@ typedef struct rc_stats {
     int32_t  n_devices;
     int32_t  sm_count;        /* of device 0                                */
     int32_t  sm_clock_khz;    /* max SM clock of device 0                   */
-    int32_t  reserved;
+    int32_t  specialized;     /* 1: the last render ran the scene-specialised
+                                 (NVRTC) megakernel, 0: a precompiled kernel */
 } rc_stats;
 
 typedef struct rc_ctx rc_ctx;

@@ -101,7 +101,7 @@ class rc_tone_map(C.Structure):
 class rc_stats(C.Structure):
     _fields_ = [("gpu_ms", C.c_double), ("samples", C.c_uint64), ("segments", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("n_devices", C.c_int32), ("sm_count", C.c_int32),
-                ("sm_clock_khz", C.c_int32), ("reserved", C.c_int32)]
+                ("sm_clock_khz", C.c_int32), ("specialized", C.c_int32)]
 
 
 # every symbol include/racer_cuda.h declares

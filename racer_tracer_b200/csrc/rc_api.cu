@@ -327,6 +327,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
     const int parts = world * n_dev;
     const int rounds = p->rng_rounds ? p->rng_rounds : 10;
     uint64_t launches = 0;
+    bool used_spec = false;
     for (int k = 0; k < n_dev; ++k) {
         DeviceState& d = ctx->devs[k];
         CUDA_TRY(cudaSetDevice(d.device));
@@ -399,6 +400,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
             kp.s_begin = s; kp.s_end = s + step < s1 ? s + step : s1;
             int rc;
             if (spec) {
+                used_spec = true;
                 rc = spec_launch(spec, kp, accum, kp.n_tiles * kp.slices, ctx->smem_bytes, d.stream) == 0 ? RC_OK : RC_ERR_CUDA;
                 if (rc != RC_OK) return fail(rc, "launch of the scene-specialised kernel failed");
             } else {
@@ -418,6 +420,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         }
     }
     ctx->stats.kernel_launches = launches;
+    ctx->stats.specialized = used_spec ? 1 : 0;
     return RC_OK;
 }
 

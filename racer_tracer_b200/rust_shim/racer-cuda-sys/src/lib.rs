@@ -90,7 +90,7 @@ pub struct rc_params {
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rc_stats {
     pub gpu_ms: f64, pub samples: u64, pub segments: u64, pub kernel_launches: u64,
-    pub n_devices: i32, pub sm_count: i32, pub sm_clock_khz: i32, pub reserved: i32,
+    pub n_devices: i32, pub sm_count: i32, pub sm_clock_khz: i32, pub specialized: i32,
 }
 
 #[repr(C)] pub struct rc_ctx { _private: [u8; 0] }
