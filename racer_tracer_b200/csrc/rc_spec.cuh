@@ -167,9 +167,30 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
         }
         o << "    {\n";
         const bool chain = std::getenv("RC_SPEC_SELECT") == nullptr;   // predicate chain (default) or candidate + select reduction
+        const bool packed = chain && std::getenv("RC_SPEC_SCALAR") == nullptr;   // FFMA2 pairs (default) or scalar arithmetic
         for (int i = begin; i < end; ++i) {
             const DevPrim& p = kp.cprims[i];
             const float4 c = kp.crect_bounds[g][i - begin];
+            if (packed && i + 1 < end) {   // two rectangles of this axis group per packed instruction
+                const DevPrim& q = kp.cprims[i + 1];
+                const float4 c2 = kp.crect_bounds[g][i + 1 - begin];
+                const int j = i + 1;
+                o << "        float t" << i << ", t" << j << ", xa" << i << ", xa" << j << ", xb" << i << ", xb" << j << ";\n";
+                o << "        pair_t(" << spec_float(p.b.x) << ", " << spec_float(q.b.x) << ", " << on[g] << ", " << in[g] << ", t" << i << ", t" << j << ");\n";
+                auto centres = [&](const char* axis, float ca1, float ca2, const std::string& v1, const std::string& v2, const char* tag) {
+                    if (ca1 == ca2) return std::make_pair(v1, v2);      // one shared scalar, broadcast
+                    const std::string n1 = std::string(tag) + std::to_string(i), n2 = std::string(tag) + std::to_string(j);
+                    o << "        float " << n1 << ", " << n2 << ";\n";
+                    o << "        pair_oc(" << axis << ", " << spec_float(ca1) << ", " << spec_float(ca2) << ", " << n1 << ", " << n2 << ");\n";
+                    return std::make_pair(n1, n2);
+                };
+                const auto pa = centres(oa[g], c.x, c2.x, va[i - begin], va[j - begin], "pa");
+                const auto pb = centres(ob[g], c.z, c2.z, vb[i - begin], vb[j - begin], "pb");
+                o << "        pair_x(t" << i << ", t" << j << ", " << da[g] << ", " << pa.first << ", " << pa.second << ", xa" << i << ", xa" << j << ");\n";
+                o << "        pair_x(t" << i << ", t" << j << ", " << db[g] << ", " << pb.first << ", " << pb.second << ", xb" << i << ", xb" << j << ");\n";
+                ++i;
+                continue;
+            }
             o << "        const float t" << i << " = (" << spec_float(p.b.x) << " - " << on[g] << ") * " << in[g] << ";\n";
             if (chain) {
                 o << "        const float xa" << i << " = fmaf(t" << i << ", " << da[g] << ", " << va[i - begin] << "), xb" << i << " = fmaf(t" << i

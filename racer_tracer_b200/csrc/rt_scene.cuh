@@ -376,6 +376,34 @@ RT_D void rect_closest(float t, float xa, float xb, float ha, float hb, int inde
         : "+f"(best_t), "+r"(best) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "r"(index));
 }
 
+// Packed FP32 (sm_100a FFMA2 / FADD2 / FMUL2: two fp32 lanes per instruction, one issue slot, scalar operands
+// broadcast).  The pipe spends two cycles on them, so the FP32 peak is unchanged (tools/micro/ffma2_bench.cu:
+// 71 vs 73 TFLOP/s) — but this kernel is bound by ISSUE slots, not by the FMA pipe (34 % busy), and two
+// rectangles on the same axis need the same three operations with the same ray operands:
+//   pair_t   (k1, k2) - o_n, times 1/d_n                       -> the two plane distances
+//   pair_oc  o_a - (c1, c2)                                    -> origins relative to the two centres
+//   pair_x   (t1, t2) * d_a + (oc1, oc2)                       -> the two in-plane coordinates
+// Each is one instruction for two rectangles; the arithmetic (round-to-nearest sub, mul, fused fma) is what
+// the scalar code does, so results are bit-identical.
+RT_D void pair_t(float k1, float k2, float on, float inv, float& t1, float& t2) {
+    asm("{\n\t.reg .b64 kk, oo, ii, tt;\n\t"
+        "mov.b64 kk, {%2, %3};\n\tmov.b64 oo, {%4, %4};\n\tmov.b64 ii, {%5, %5};\n\t"
+        "sub.f32x2 tt, kk, oo;\n\tmul.f32x2 tt, tt, ii;\n\t"
+        "mov.b64 {%0, %1}, tt;\n\t}" : "=f"(t1), "=f"(t2) : "f"(k1), "f"(k2), "f"(on), "f"(inv));
+}
+RT_D void pair_oc(float oa, float c1, float c2, float& oc1, float& oc2) {
+    asm("{\n\t.reg .b64 oo, cc, rr;\n\t"
+        "mov.b64 oo, {%2, %2};\n\tmov.b64 cc, {%3, %4};\n\t"
+        "sub.f32x2 rr, oo, cc;\n\t"
+        "mov.b64 {%0, %1}, rr;\n\t}" : "=f"(oc1), "=f"(oc2) : "f"(oa), "f"(c1), "f"(c2));
+}
+RT_D void pair_x(float t1, float t2, float d, float oc1, float oc2, float& x1, float& x2) {
+    asm("{\n\t.reg .b64 tt, dd, cc, xx;\n\t"
+        "mov.b64 tt, {%2, %3};\n\tmov.b64 dd, {%4, %4};\n\tmov.b64 cc, {%5, %6};\n\t"
+        "fma.rn.f32x2 xx, tt, dd, cc;\n\t"
+        "mov.b64 {%0, %1}, xx;\n\t}" : "=f"(x1), "=f"(x2) : "f"(t1), "f"(t2), "f"(d), "f"(oc1), "f"(oc2));
+}
+
 // Linear closest hit over the TYPE-SORTED table (spheres, xy, xz, yz rects):
 // one tight loop per primitive kind with the axes hard-wired, no per-primitive
 // type decode and no early exits — every rectangle is a fixed sequence of
