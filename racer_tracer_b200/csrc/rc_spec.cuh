@@ -242,6 +242,25 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
             const int g = type - 1;
             const double ca = 0.5 * ((double)p.a.x + p.a.y), ha = 0.5 * ((double)p.a.y - p.a.x);
             const double cb = 0.5 * ((double)p.a.z + p.a.w), hb = 0.5 * ((double)p.a.w - p.a.z);
+            // two consecutive sides on the same axis (a Box's opposite faces): packed arithmetic, as for the plain groups
+            if (std::getenv("RC_SPEC_SCALAR") == nullptr && i + 1 < first + count && (__float_as_int_host(kp.cprims[i + 1].b.z) & 15) == type) {
+                const DevPrim& q = kp.cprims[i + 1];
+                const int j = i + 1;
+                const double ca2 = 0.5 * ((double)q.a.x + q.a.y), cb2 = 0.5 * ((double)q.a.z + q.a.w);
+                o << "        float u" << i << ", u" << j << ", ea" << i << ", ea" << j << ", eb" << i << ", eb" << j << ", ca" << i << ", ca" << j
+                  << ", cb" << i << ", cb" << j << ";\n";
+                o << "        pair_t(" << spec_float(p.b.x) << ", " << spec_float(q.b.x) << ", " << ln[g] << ", " << li[g] << ", u" << i << ", u" << j << ");\n";
+                if ((float)ca == (float)ca2) o << "        ca" << i << " = ca" << j << " = " << la[g] << " - " << spec_float((float)ca) << ";\n";
+                else o << "        pair_oc(" << la[g] << ", " << spec_float((float)ca) << ", " << spec_float((float)ca2) << ", ca" << i << ", ca" << j << ");\n";
+                if ((float)cb == (float)cb2) o << "        cb" << i << " = cb" << j << " = " << lb[g] << " - " << spec_float((float)cb) << ";\n";
+                else o << "        pair_oc(" << lb[g] << ", " << spec_float((float)cb) << ", " << spec_float((float)cb2) << ", cb" << i << ", cb" << j << ");\n";
+                o << "        pair_x(u" << i << ", u" << j << ", " << lda[g] << ", ca" << i << ", ca" << j << ", ea" << i << ", ea" << j << ");\n";
+                o << "        pair_x(u" << i << ", u" << j << ", " << ldb[g] << ", cb" << i << ", cb" << j << ", eb" << i << ", eb" << j << ");\n";
+                // the rectangle the ray leaves gets t = -1, which fails t >= t_min
+                o << "        u" << i << " = last_prim == " << i << " ? -1.0f : u" << i << "; u" << j << " = last_prim == " << j << " ? -1.0f : u" << j << ";\n";
+                ++i;
+                continue;
+            }
             // the rectangle the ray leaves gets t = -1, which fails t >= t_min
             o << "        const float u" << i << " = last_prim == " << i << " ? -1.0f : (" << spec_float(p.b.x) << " - " << ln[g] << ") * " << li[g] << ";\n";
             o << "        const float ea" << i << " = fmaf(u" << i << ", " << lda[g] << ", " << la[g] << " - " << spec_float((float)ca) << "), eb" << i
