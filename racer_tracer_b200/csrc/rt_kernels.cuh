@@ -307,9 +307,11 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
 
     // CTA -> (tile, slice of the sample range).  With one GPU there are thousands of tiles and
     // slices == 1; when the tiles are shared out over several GPUs each tile's samples are cut
-    // into `slices` CTAs so the grid still fills the machine many times over (no long tail).
-    const int tile_k = P.slices > 1 ? (int)blockIdx.x / P.slices : (int)blockIdx.x;
-    const int slice = P.slices > 1 ? (int)blockIdx.x - tile_k * P.slices : 0;
+    // into `slices` CTAs so the grid still fills the machine many times over.
+    // Slice-major order with DECREASING slice lengths (weights S, S-1, .., 1): the CTAs scheduled last — the ones
+    // that form the tail of the grid — are the short ones.
+    const int slice = P.slices > 1 ? (int)blockIdx.x / P.n_tiles : 0;
+    const int tile_k = P.slices > 1 ? (int)blockIdx.x - slice * P.n_tiles : (int)blockIdx.x;
     const int tile = P.tile_first + tile_k * P.tile_stride;
     const int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -318,9 +320,11 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     const bool valid = px < P.width && py < P.height;
     int s_first = P.s_begin, s_last = P.s_end;
     if (P.slices > 1) {
-        const int n = P.s_end - P.s_begin;
-        s_first = P.s_begin + (int)(((long long)n * slice) / P.slices);
-        s_last = P.s_begin + (int)(((long long)n * (slice + 1)) / P.slices);
+        const long long n = P.s_end - P.s_begin, S = P.slices, total = S * (S + 1) / 2;
+        const long long c0 = (long long)slice * S - (long long)slice * (slice - 1) / 2;       // weights of the slices before this one
+        const long long c1 = c0 + (S - slice);
+        s_first = P.s_begin + (int)(n * c0 / total);
+        s_last = P.s_begin + (int)(n * c1 / total);
     }
 
     PixelCtx pc = pixel_setup<ROUNDS>(P, valid ? px : 0, valid ? py : 0);
