@@ -251,7 +251,27 @@ def _flatten(fs: "FlatScene", objects: dict, textures, materials, images, perlin
 
 
 
-def load_scene(path: str, seed: int = 0, use_bvh: bool | None = None, image_dirs=()) -> FlatScene:
+def sandbox_additions(doc: dict):
+    """Sandbox::load_cornell_box (src/scene/sandbox.rs:39-81) on top of the parsed cornell_box.yml: two white
+    Lambertian boxes, each rotated about y and then translated (create_box / create_rotate_y / create_translate),
+    black background, the Cornell camera.  Expressed as additions to the (lower-cased) YAML document, so that the
+    ordinary YAML pathway (yml.rs:292-439) flattens them."""
+    doc["textures"]["sandbox_white"] = {"solidcolor": {"color": {"color": [0.63, 0.63, 0.63]}}}
+    doc["materials"]["sandbox_white"] = {"lambertian": {"texture": "sandbox_white"}}
+    g = doc["geometry"]
+    g["sandbox_box1"] = {"box": {"min": {"pos": [0.0, 0.0, 0.0]}, "max": {"pos": [165.0, 330.0, 165.0]}, "material": "sandbox_white"}}
+    g["sandbox_box1_rotate"] = {"rotatey": {"key": "sandbox_box1", "degrees": 15.0}}
+    g["sandbox_box1_translate"] = {"translate": {"key": "sandbox_box1", "pos": [265.0, 0.0, 295.0]}}
+    g["sandbox_box2"] = {"box": {"min": {"pos": [0.0, 0.0, 0.0]}, "max": {"pos": [165.0, 165.0, 165.0]}, "material": "sandbox_white"}}
+    g["sandbox_box2_rotate"] = {"rotatey": {"key": "sandbox_box2", "degrees": -18.0}}
+    g["sandbox_box2_translate"] = {"translate": {"key": "sandbox_box2", "pos": [130.0, 0.0, 65.0]}}
+    doc["background"] = {"solidcolor": {"pos": [0.0, 0.0, 0.0]}}
+    doc["camera"] = {"vfov": 40.0, "aperture": 0.0, "focus_distance": 10000.0, "pos": {"pos": [278.0, 278.0, -800.0]},
+                     "look_at": {"pos": [278.0, 278.0, 0.0]}}
+    doc.pop("tone_map", None)
+
+
+def load_scene(path: str, seed: int = 0, use_bvh: bool | None = None, image_dirs=(), additions=None) -> FlatScene:
     """YmlLoader::load + TryInto<SceneLoadData> (src/scene/yml.rs:43-47,173-458),
     followed by the flattening the Rust shim performs before rc_upload_scene."""
     with open(path, "r") as f:
@@ -262,6 +282,8 @@ def load_scene(path: str, seed: int = 0, use_bvh: bool | None = None, image_dirs
     if not isinstance(doc, dict):
         raise SceneLoadError(f"Configuration({path}): not a mapping")
     doc = _lower_keys(doc)
+    if additions is not None:
+        additions(doc)
     for req in ("textures", "materials", "geometry"):
         if req not in doc or not isinstance(doc[req], dict):
             raise SceneLoadError(f"Configuration({path}): missing field `{req}`")
@@ -796,6 +818,8 @@ def prepare_job(scene_path: str, config: Config | None = None, width=None, heigh
     w, h = width or cfg.width, height or cfg.height
     if scene_path == "random":      # SceneLoaderConfig::Random, config.rs:84-93
         fs = random_scene(seed=seed, use_bvh=use_bvh)
+    elif scene_path.startswith("sandbox:"):   # SceneLoaderConfig::Sandbox over the given cornell_box.yml (sandbox.rs:41-42)
+        fs = load_scene(scene_path[len("sandbox:"):], seed=seed, use_bvh=use_bvh, image_dirs=image_dirs, additions=sandbox_additions)
     else:
         fs = load_scene(scene_path, seed=seed, use_bvh=use_bvh, image_dirs=image_dirs)
     cam = make_camera(merged_camera(fs.camera_cfg, cfg.camera), w, h)

@@ -52,12 +52,15 @@ int main(int argc, char** argv) {
         if (have_seed) config.gpu.seed = seed;
         if (scene_path.empty() && config.loader.kind == SceneLoaderConfig::Yml) scene_path = config.loader.path;
         if (scene_path.empty() && config.loader.kind == SceneLoaderConfig::Random) scene_path = "random";
+        if (scene_path.empty() && config.loader.kind == SceneLoaderConfig::Sandbox) scene_path = "sandbox:../resources/scenes/cornell_box.yml";   // sandbox.rs:41-42
         if (scene_path.empty()) throw TracerError(TracerError::ArgumentParsingError, "Argument parsing Error: --scene (or loader: Yml) is required");
         if (config.screen.width < 2 || config.screen.height < 2)
             throw TracerError(TracerError::Configuration, "Config Error (screen): width and height must be >= 2");
 
-        std::unique_ptr<SceneData> scene = scene_path == "random" ? SceneData::load_random(config.gpu.seed)   // SceneLoaderConfig::Random
-                                                                  : SceneData::load_yml(scene_path, config.gpu.seed, image_dirs);
+        // SceneLoaderConfig::{Random, Sandbox, Yml} (config.rs:84-93); "sandbox:<path of cornell_box.yml>"
+        std::unique_ptr<SceneData> scene = scene_path == "random" ? SceneData::load_random(config.gpu.seed)
+                                           : scene_path.rfind("sandbox:", 0) == 0 ? SceneData::load_sandbox(scene_path.substr(8), config.gpu.seed)
+                                                                                  : SceneData::load_yml(scene_path, config.gpu.seed, image_dirs);
         const Image image(config.screen.width, config.screen.height);
         const rc_camera camera = make_camera(merge_camera(scene->camera, config.camera), image);   // main.rs:95-111
         const rc_tone_map tone_map = scene->has_tone_map ? scene->tone_map : config.tone_map;       // main.rs:84-86

@@ -406,7 +406,44 @@ SceneData::SceneData() {
     tone_map = make_tone_map_default();
 }
 
-std::unique_ptr<SceneData> SceneData::load_yml(const std::string& path, uint64_t seed, const std::vector<std::string>& image_dirs) {
+namespace {
+// Sandbox::load_cornell_box (scene/sandbox.rs:39-81) as additions to the parsed, lower-cased cornell_box.yml: two
+// white Lambertian boxes, each rotated about y and then translated, black background, the Cornell camera.
+void sandbox_additions(Node& doc) {
+    const Node extra = yaml_lite::parse(
+        "textures:\n"
+        "  sandbox_white: {solidcolor: {color: {color: [0.63, 0.63, 0.63]}}}\n"
+        "materials:\n"
+        "  sandbox_white: {lambertian: {texture: sandbox_white}}\n"
+        "geometry:\n"
+        "  sandbox_box1: {box: {min: {pos: [0.0, 0.0, 0.0]}, max: {pos: [165.0, 330.0, 165.0]}, material: sandbox_white}}\n"
+        "  sandbox_box1_rotate: {rotatey: {key: sandbox_box1, degrees: 15.0}}\n"
+        "  sandbox_box1_translate: {translate: {key: sandbox_box1, pos: [265.0, 0.0, 295.0]}}\n"
+        "  sandbox_box2: {box: {min: {pos: [0.0, 0.0, 0.0]}, max: {pos: [165.0, 165.0, 165.0]}, material: sandbox_white}}\n"
+        "  sandbox_box2_rotate: {rotatey: {key: sandbox_box2, degrees: -18.0}}\n"
+        "  sandbox_box2_translate: {translate: {key: sandbox_box2, pos: [130.0, 0.0, 65.0]}}\n"
+        "background: {solidcolor: {pos: [0.0, 0.0, 0.0]}}\n"
+        "camera: {vfov: 40.0, aperture: 0.0, focus_distance: 10000.0, pos: {pos: [278.0, 278.0, -800.0]}, look_at: {pos: [278.0, 278.0, 0.0]}}\n");
+    auto section = [&](const std::string& name) -> Node& {
+        for (auto& kv : doc.map) if (kv.first == name) return kv.second;
+        doc.map.emplace_back(name, Node());
+        doc.map.back().second.kind = Node::Map;
+        return doc.map.back().second;
+    };
+    for (const char* name : {"textures", "materials", "geometry"})
+        for (auto& kv : extra.at(name).map) section(name).map.push_back(kv);
+    section("background") = extra.at("background");
+    section("camera") = extra.at("camera");
+    for (size_t i = 0; i < doc.map.size(); ++i)
+        if (doc.map[i].first == "tone_map") { doc.map.erase(doc.map.begin() + i); break; }
+}
+}  // namespace
+
+std::unique_ptr<SceneData> SceneData::load_sandbox(const std::string& cornell_box_yml, uint64_t seed) {
+    return load_yml(cornell_box_yml, seed, {}, true);
+}
+
+std::unique_ptr<SceneData> SceneData::load_yml(const std::string& path, uint64_t seed, const std::vector<std::string>& image_dirs, bool sandbox) {
     bool ok = false;
     const std::string text = read_file(path, ok);
     auto cfg_err = [&](const std::string& m) { return TracerError(TracerError::Configuration, "Config Error (" + path + "): " + m); };
@@ -418,6 +455,7 @@ std::unique_ptr<SceneData> SceneData::load_yml(const std::string& path, uint64_t
     } catch (const yaml_lite::ParseError& e) { throw cfg_err(e.what()); }
     if (!doc.is_map()) throw cfg_err("not a mapping");
     yaml_lite::lower_keys(doc);
+    if (sandbox) sandbox_additions(doc);
     for (const char* req : {"textures", "materials", "geometry"})
         if (!doc.find(req) || !doc.at(req).is_map()) throw cfg_err(std::string("missing field `") + req + "`");
     try {

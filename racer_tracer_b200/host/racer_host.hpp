@@ -133,7 +133,10 @@ struct SceneData {
     // YmlLoader::load (yml.rs:43-47,173-458): throws Configuration / SceneLoad / UnknownMaterial /
     // FailedToOpenImage exactly where the reference returns them.
     static std::unique_ptr<SceneData> load_yml(const std::string& path, uint64_t seed = 0,
-                                               const std::vector<std::string>& image_dirs = {});
+                                               const std::vector<std::string>& image_dirs = {}, bool sandbox = false);
+    // Sandbox::load (scene/sandbox.rs:39-81), the loader racer-tracer/config.yml selects: cornell_box.yml (the
+    // reference reads ../resources/scenes/cornell_box.yml) plus two rotated, translated boxes.
+    static std::unique_ptr<SceneData> load_sandbox(const std::string& cornell_box_yml, uint64_t seed = 0);
     // Random::load (scene/random.rs:25-95): checkered ground, 22 x 22 small spheres (diffuse ones move), three
     // large spheres; its own camera (vfov 20, aperture 0.1, focus 10).  Deterministic in `seed`.
     static std::unique_ptr<SceneData> load_random(uint64_t seed = 0);

@@ -11,7 +11,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 SCENES = ["three_balls", "emissive", "noise_and_textures", "cornell_box", "clown"]   # the BASELINE configs
 # + the reference's Sandbox scene (Box / RotateY / Translate instances) in YAML form
 # + the reference's Random scene (scene/random.rs: ~480 spheres, moving spheres + ray time, lens), §8(f)-4
-SCENES_X = SCENES + ["sandbox_boxes", "random"]
+# + the reference's Sandbox LOADER (scene/sandbox.rs: cornell_box.yml + two rotated, translated boxes), the scene
+#   racer-tracer/config.yml selects by default
+SCENES_X = SCENES + ["sandbox_boxes", "random", "sandbox"]
 
 
 def pytest_configure(config):
@@ -21,6 +23,8 @@ def pytest_configure(config):
 def scene_path(name):
     if name == "random":      # SceneLoaderConfig::Random: generated, not a file
         return name
+    if name == "sandbox":     # SceneLoaderConfig::Sandbox: cornell_box.yml + programmatic additions
+        return "sandbox:" + os.path.join(GOLDEN, "scenes", "cornell_box.yml")
     return os.path.join(GOLDEN, "scenes", name + ".yml")
 
 

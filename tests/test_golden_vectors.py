@@ -39,7 +39,7 @@ def test_oracle_reproduces_the_golden_vectors(cfg, name):
 @pytest.mark.parametrize("name", SCENES_X)
 def test_cuda_path_matches_the_golden_vectors(renderer, cfg, name):
     want = np.load(os.path.join(VEC, name + ".npz"))
-    path = name if name == "random" else os.path.join(ROOT, "tests", "golden", "scenes", name + ".yml")
+    path = gen.scene_path(name)
     job = harness.prepare_job(path, cfg, 64, 48, seed=0, image_dirs=[gen.IMAGES])
     renderer.upload(job)
     p = harness.make_params(64, 48, 1, 20, fixed_jitter=1)

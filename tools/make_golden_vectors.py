@@ -19,13 +19,21 @@ sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 from racer_tracer_b200 import harness  # noqa: E402
 
-SCENES = ["three_balls", "emissive", "noise_and_textures", "cornell_box", "clown", "sandbox_boxes", "random"]
+SCENES = ["three_balls", "emissive", "noise_and_textures", "cornell_box", "clown", "sandbox_boxes", "random", "sandbox"]
 OUT = os.path.join(ROOT, "tests", "golden", "vectors")
 IMAGES = os.path.join(ROOT, "tests", "golden", "resources", "images")
 
 
+def scene_path(name):
+    if name == "random":
+        return name
+    if name == "sandbox":
+        return "sandbox:" + os.path.join(ROOT, "tests", "golden", "scenes", "cornell_box.yml")
+    return os.path.join(ROOT, "tests", "golden", "scenes", name + ".yml")
+
+
 def vectors(name, cfg):
-    path = name if name == "random" else os.path.join(ROOT, "tests", "golden", "scenes", name + ".yml")
+    path = scene_path(name)
     job = harness.prepare_job(path, cfg, 64, 48, seed=0, image_dirs=[IMAGES])
     ids, t, nrm, _ = O.primary_aov(job, harness.make_params(64, 48, 1, 20, fixed_jitter=1))
     job2 = harness.prepare_job(path, cfg, 48, 36, seed=0, image_dirs=[IMAGES])
