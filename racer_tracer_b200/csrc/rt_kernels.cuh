@@ -272,7 +272,8 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
         }
         col = mk3(1.0f, 1.0f, 1.0f);
     }
-    T = T * col;
+    mul2(T.x, T.y, col.x, col.y, T.x, T.y);
+    T.z = T.z * col.z;
     o = h.p;
     d = nd;
     return true;

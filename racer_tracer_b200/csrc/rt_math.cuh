@@ -45,6 +45,28 @@ RT_D float fast_rsqrt(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "
 RT_D float rt_rcp(float v) { return fast_rcp(v); }
 RT_D double rt_rcp(double v) { return 1.0 / v; }
 
+// Packed FP32 (sm_100a: FFMA2 / FMUL2, two fp32 lanes per instruction and per issue slot; a scalar operand is
+// broadcast).  Same rounding as the scalar instructions (RN, fused), so results do not change; what changes is
+// the number of issue slots, which is what bounds the render kernel (profiles/).
+RT_D void fma2_bcast(float s, float a0, float a1, float b0, float b1, float& r0, float& r1) {   // s * (a0, a1) + (b0, b1)
+    asm("{\n\t.reg .b64 ss, aa, bb, rr;\n\t"
+        "mov.b64 ss, {%2, %2};\n\tmov.b64 aa, {%3, %4};\n\tmov.b64 bb, {%5, %6};\n\t"
+        "fma.rn.f32x2 rr, ss, aa, bb;\n\t"
+        "mov.b64 {%0, %1}, rr;\n\t}" : "=f"(r0), "=f"(r1) : "f"(s), "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+RT_D void mul2_bcast(float s, float a0, float a1, float& r0, float& r1) {   // s * (a0, a1)
+    asm("{\n\t.reg .b64 ss, aa, rr;\n\t"
+        "mov.b64 ss, {%2, %2};\n\tmov.b64 aa, {%3, %4};\n\t"
+        "mul.f32x2 rr, ss, aa;\n\t"
+        "mov.b64 {%0, %1}, rr;\n\t}" : "=f"(r0), "=f"(r1) : "f"(s), "f"(a0), "f"(a1));
+}
+RT_D void mul2(float a0, float a1, float b0, float b1, float& r0, float& r1) {   // (a0, a1) * (b0, b1)
+    asm("{\n\t.reg .b64 aa, bb, rr;\n\t"
+        "mov.b64 aa, {%2, %3};\n\tmov.b64 bb, {%4, %5};\n\t"
+        "mul.f32x2 rr, aa, bb;\n\t"
+        "mov.b64 {%0, %1}, rr;\n\t}" : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 template <typename T> RT_D Vec3T<T> unit_vector(Vec3T<T> a) { return a * rt_rsqrt(length_squared(a)); }
 
 // vec3.rs:412-414

@@ -713,7 +713,8 @@ struct Hit {
 template <class Scene>
 RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT<float>& r, float t) {
     Hit h;
-    h.p = r.o + t * r.d;  // Ray::at
+    fma2_bcast(t, r.d.x, r.d.y, r.o.x, r.o.y, h.p.x, h.p.y);   // Ray::at
+    h.p.z = fmaf(t, r.d.z, r.o.z);
     if (RT_HAS_SPHERES && (!RT_HAS_RECTS || RT_IS_SPHERE(kinds_prim(b.z)))) {
         vec3f ctr = kinds_prim(b.z) == RT_PRIM_MOVING ? sphere_centre(a, S.pn(prim), r.time) : mk3(a.x, a.y, a.z);
         const float aa = dot(r.d, r.d);
@@ -729,13 +730,15 @@ RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT
         const float4 n4 = S.pn(prim);
         const vec3f N = mk3(n4.x, n4.y, n4.z);
         const float e = b.x - dot(h.p, N);
-        h.p = mk3(fmaf(e, N.x, h.p.x), fmaf(e, N.y, h.p.y), fmaf(e, N.z, h.p.z));
+        fma2_bcast(e, N.x, N.y, h.p.x, h.p.y, h.p.x, h.p.y);
+        h.p.z = fmaf(e, N.z, h.p.z);
         const float dn = dot(r.d, N);
         h.front_face = dn < 0.0f;   // dot(d, axis) < 0, geometry.rs:49-56
         // +1 if dn < 0 else -1: the inverted sign bit of dn over the bits of 1.0f (one LOP3)
         const float sgn = __int_as_float((~__float_as_int(dn) & 0x80000000) | 0x3f800000);
         h.outward = N;
-        h.n = mk3(sgn * N.x, sgn * N.y, sgn * N.z);
+        mul2_bcast(sgn, N.x, N.y, h.n.x, h.n.y);
+        h.n.z = sgn * N.z;
     }
     h.lp = h.p;
     return h;
@@ -902,8 +905,8 @@ RT_D vec3f sphere_direct(float u1, float u2) {
 // sphere_direct(u24(wx), u24(wy)) with the integer -> uniform scalings folded into the
 // multiply-adds (same values: u24 is exact in fp32 and the scale factors are powers of two)
 RT_D vec3f sphere_direct_w(uint32_t wx, uint32_t wy) {
-    const float z = fmaf((float)(wx >> 8), -1.0f / 8388608.0f, 1.0f);                 // 1 - 2 u1
-    const float r = fast_sqrt(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
+    const float z = fmaf((float)(wx >> 8), -1.0f / 8388608.0f, 1.0f);                 // 1 - 2 u1, in [-1 + 2^-23, 1]
+    const float r = fast_sqrt(fmaf(-z, z, 1.0f));                                       // |z| <= 1 exactly: never negative
     const float phi = fmaf((float)(wy >> 8), 6.283185307179586f / 16777216.0f, -3.14159265358979323846f);
     return mk3(-r * __cosf(phi), -r * __sinf(phi), z);
 }
