@@ -342,6 +342,9 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     int depth_left = 0;        // > 0: this lane is on a path that may still trace that many segments; 0: no path
     int last_prim = -1;
     uint32_t seg = 0;          // index of the segment about to be traced (0 = primary ray)
+    uint32_t ctr1 = 0;         // Philox counter word of that segment's block: sample | seg << 24 (tag PATH = 0), kept incrementally
+    unsigned sh_prims = (unsigned)__cvta_generic_to_shared(L.prims);   // (meaningful in the staged modes only)
+    asm volatile("" : "+r"(sh_prims));   // opaque: kept in a register instead of being rebuilt (S2UR + 2 uniform ops) at every use
     unsigned nseg = 0;
     if (P.max_depth <= 0) {    // renderer.rs:48-56: depth 0 is white, for every sample
         const float n = (float)(s_last - s);
@@ -384,13 +387,14 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         }
         if (fresh) {
             R.sample = (uint32_t)s++;
+            ctr1 = R.sample;
             seg = 0; last_prim = -1;
             T = mk3(1.0f, 1.0f, 1.0f);
             depth_left = P.max_depth;
         }
         if (depth_left != 0) {
             // ---- the segment's random block: drawn here, by all lanes together ----
-            const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(R.sample, seg, RT_TAG_PATH), P.ks);
+            const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, ctr1, P.ks);   // == rt_ctr1(R.sample, seg, RT_TAG_PATH)
             if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337
                 const float vjit = P.fixed_jitter ? 0.5f : u16lo(rnd);
                 camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d, time);
@@ -398,7 +402,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             RayT<float> r = make_ray(o, d, time);
             float t;
             int prim;
-            if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, L.prims); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
+            if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, sh_prims); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
             else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t); }
             ++nseg;
             if (prim < 0) {  // renderer.rs:78-88
@@ -406,9 +410,10 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                 depth_left = 0;
             } else {
                 ++seg;   // hit number along the path (1 = primary hit)
+                ctr1 += 1u << 24;
                 vec3f X_end;   // radiance that ends the path
                 bool cont;
-                if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, L.prims); cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
+                if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, sh_prims); cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
                 else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
                 if (!cont) {                 // absorbed (X_end = 0) or a light (X_end = emission)
                     sum = sum + T * X_end;

@@ -145,20 +145,29 @@ struct KParams {
 // instructions); SmemScene reads primitives and nodes staged in shared
 // memory; GlobalScene reads them through the read-only path.
 // ---------------------------------------------------------------------------
+// 16-byte load from a 32-bit shared-memory address (computed once per kernel: the generic-to-shared
+// conversion otherwise costs three uniform instructions at every use inside the path loop)
+RT_D float4 lds128(unsigned addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 struct ConstScene {
     const KParams& P;
-    const DevPrim* sh;   // the same type-sorted table staged in shared memory: per-lane (divergent) indices
-    RT_D ConstScene(const KParams& p, const DevPrim* staged) : P(p), sh(staged) {}
+    unsigned sh;   // shared-memory address of the same type-sorted table, staged per CTA: per-lane (divergent) indices
+    RT_D ConstScene(const KParams& p, const DevPrim* staged) : P(p), sh((unsigned)__cvta_generic_to_shared(staged)) {}
+    RT_D ConstScene(const KParams& p, unsigned staged_addr) : P(p), sh(staged_addr) {}
     // uniform index (the intersection loops): constant-bank operands
     RT_D float4 ua(int i) const { return P.cprims[i].a; }
     RT_D float4 ub(int i) const { return P.cprims[i].b; }
     RT_D float4 un(int i) const { return P.cprims[i].n; }
     // per-lane index (hit record, shading): shared memory — an indexed constant load replays
     // once per distinct address in the warp
-    RT_D float4 pa(int i) const { return sh[i].a; }
-    RT_D float4 pb(int i) const { return sh[i].b; }
-    RT_D float4 pc(int i) const { return sh[i].c; }
-    RT_D float4 pn(int i) const { return sh[i].n; }
+    RT_D float4 pa(int i) const { return lds128(sh + 64u * (unsigned)i); }
+    RT_D float4 pb(int i) const { return lds128(sh + 64u * (unsigned)i + 16u); }
+    RT_D float4 pc(int i) const { return lds128(sh + 64u * (unsigned)i + 32u); }
+    RT_D float4 pn(int i) const { return lds128(sh + 64u * (unsigned)i + 48u); }
     RT_D float4 nlo(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }  // no BVH in the constant bank
     RT_D float4 nhi(int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
     RT_D const DevInstance* instances() const { return P.cinst; }           // the scene's instance table (<= RT_MAX_CONST_OBJS)
