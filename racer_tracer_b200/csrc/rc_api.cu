@@ -886,6 +886,7 @@ int rc_set_camera(rc_ctx* ctx, const rc_camera* c) {
     f.origin = v3f(c->origin); f.upper_left_corner = v3f(rel); f.right = v3f(c->right); f.up = v3f(c->up);
     f.horizontal = v3f(c->horizontal); f.vertical = v3f(c->vertical);
     f.lens_radius = (float)c->lens_radius; f.time_a = (float)c->time_a; f.time_b = (float)c->time_b;
+    if (ctx->kp.lens_enabled != (c->lens_radius != 0.0 ? 1 : 0)) ctx->spec_source.clear();   // the specialised kernel knows whether there is a lens
     ctx->kp.lens_enabled = c->lens_radius != 0.0;
     DevCamera<double>& g = ctx->aov.cam;
     g.origin = v3d(c->origin); g.upper_left_corner = v3d(c->upper_left_corner); g.right = v3d(c->right); g.up = v3d(c->up);

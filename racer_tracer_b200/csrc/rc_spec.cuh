@@ -113,6 +113,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
     const bool black = __float_as_int_host(kp.bg_a.w) != 0 && kp.bg_a.x == 0.f && kp.bg_a.y == 0.f && kp.bg_a.z == 0.f;
     o << "#define RT_SPEC_BG_BLACK " << (black ? 1 : 0) << "\n";
     o << "#define RT_HAS_INSTANCES " << (kp.n_cobj > 0 ? 1 : 0) << "\n";
+    o << "#define RT_HAS_LENS " << (kp.lens_enabled ? 1 : 0) << "\n";   // part of the source, hence of the cache key
     if (const char* e = std::getenv("RC_REGEN_MIN")) o << "#define RT_REGEN_MIN " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
     o << "#include \"rt_scene.cuh\"\n";

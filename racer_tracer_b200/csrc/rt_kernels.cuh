@@ -75,6 +75,9 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
 #ifndef RT_HAS_MOTION
 #define RT_HAS_MOTION 1     /* a scene-specialised kernel sets 0 when no sphere moves */
 #endif
+#ifndef RT_HAS_LENS
+#define RT_HAS_LENS 1       /* ... and 0 when the camera it was compiled for is a pinhole (lens_radius == 0) */
+#endif
 
 template <int MODE, class Scene>
 RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& t) {
@@ -121,7 +124,7 @@ RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float
         const uint2 w = philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.ks);
         time = fmaf(P.cam.time_b - P.cam.time_a, u16lo(w), P.cam.time_a);
     }
-    if (P.lens_enabled && !P.fixed_jitter) {  // camera.rs:327-328; skipped when lens_radius == 0 (offset = 0)
+    if (RT_HAS_LENS && P.lens_enabled && !P.fixed_jitter) {  // camera.rs:327-328; skipped when lens_radius == 0 (offset = 0)
         float dx, dy;
         if (SAMPLER == 1) {  // random_in_unit_disk, util.rs:25-39
             for (uint32_t j = 1;; ++j) {
@@ -238,8 +241,12 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
         if (SAMPLER == 1) rv = unit_vector(reject_in_unit_sphere<ROUNDS>(R, bounce));
         else rv = sphere_direct_w(rnd.x, rnd.y);
         nd = h.n + rv;
-        // near_zero, vec3.rs:127-130: all three components below 1e-8 (rv = -n; one draw in 2^24)
-        if (fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z)) < 1e-8f) nd = h.n;
+        // near_zero, vec3.rs:127-130: all three components below 1e-8 (rv = -n; one draw in 2^24) -> the normal.
+        // As arithmetic (nd + k n, k = 1 in that case: what is left of nd vanishes against the unit normal)
+        // instead of three selects: the ALU pipe is the saturated one.
+        const float k0 = fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z)) < 1e-8f ? 1.0f : 0.0f;
+        fma2_bcast(k0, h.n.x, h.n.y, nd.x, nd.y, nd.x, nd.y);
+        nd.z = fmaf(k0, h.n.z, nd.z);
     } else if (RT_HAS_MAT(RT_MAT_METAL) && (mat == RT_MAT_METAL || !RT_HAS_MAT(RT_MAT_DIELECTRIC))) {  // metal.rs:25-44
         vec3f rv;
         if (SAMPLER == 1) rv = reject_in_unit_sphere<ROUNDS>(R, bounce);
@@ -367,7 +374,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                         camera_ray<SAMPLER, ROUNDS>(P, pc, (uint32_t)s, vjit, o, d, time);
                         bg = background_color(P, d);
                     } else bg = mk3(P.bg_a.x, P.bg_a.y, P.bg_a.z);
-                    sum = sum + T_ONE * bg;
+                    sum = mk3(fmaf(T_ONE.x, bg.x, sum.x), fmaf(T_ONE.y, bg.y, sum.y), fmaf(T_ONE.z, bg.z, sum.z));
                 }
             }
             s = s_last;
@@ -386,12 +393,13 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             if (!__any_sync(0xffffffffu, (depth_left != 0) | (s < s_last))) break;
         }
         if (fresh) {
-            R.sample = (uint32_t)s++;
+            R.sample = (uint32_t)s;
             ctr1 = R.sample;
             seg = 0; last_prim = -1;
             T = mk3(1.0f, 1.0f, 1.0f);
             depth_left = P.max_depth;
         }
+        s += fresh ? 1 : 0;
         if (depth_left != 0) {
             // ---- the segment's random block: drawn here, by all lanes together ----
             const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, ctr1, P.ks);   // == rt_ctr1(R.sample, seg, RT_TAG_PATH)
@@ -406,7 +414,10 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t); }
             ++nseg;
             if (prim < 0) {  // renderer.rs:78-88
-                if (!RT_SPEC_BG_BLACK) sum = sum + T * background_color(P, d);
+                if (!RT_SPEC_BG_BLACK) {
+                    const vec3f bg = background_color(P, d);
+                    sum = mk3(fmaf(T.x, bg.x, sum.x), fmaf(T.y, bg.y, sum.y), fmaf(T.z, bg.z, sum.z));
+                }
                 depth_left = 0;
             } else {
                 ++seg;   // hit number along the path (1 = primary hit)
@@ -420,7 +431,10 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                     depth_left = 0;
                 } else {
                     last_prim = prim;
-                    if (--depth_left == 0) sum = sum + T;   // white at depth 0, renderer.rs:48-56
+                    // white at depth 0 (renderer.rs:48-56): sum += w T with w = 1 when the budget is spent, as arithmetic
+                    const float w = --depth_left == 0 ? 1.0f : 0.0f;
+                    fma2_bcast(w, T.x, T.y, sum.x, sum.y, sum.x, sum.y);
+                    sum.z = fmaf(w, T.z, sum.z);
                 }
             }
         }

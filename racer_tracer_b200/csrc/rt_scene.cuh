@@ -878,9 +878,10 @@ RT_D vec3f texture_value(const KParams& P, const TexCtx& X, const Scene& S, int 
 // BackgroundColor::color, src/background_color.rs:27-48
 RT_D vec3f background_color(const KParams& P, vec3f d) {
     if (__float_as_int(P.bg_a.w) == 0) {  // Sky
-        float t = 0.5f * (d.y * rsqrtf(dot(d, d)) + 1.0f);
-        return mk3((1.0f - t) * P.bg_a.x + t * P.bg_b.x, (1.0f - t) * P.bg_a.y + t * P.bg_b.y,
-                   (1.0f - t) * P.bg_a.z + t * P.bg_b.z);
+        // explicit fused operations: this function is inlined in several places (general loop, culled tiles,
+        // wavefront) and every copy has to round identically, whatever the compiler would contract around it
+        const float t = 0.5f * fmaf(d.y, rsqrtf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x))), 1.0f), u = 1.0f - t;
+        return mk3(fmaf(t, P.bg_b.x, u * P.bg_a.x), fmaf(t, P.bg_b.y, u * P.bg_a.y), fmaf(t, P.bg_b.z, u * P.bg_a.z));
     }
     return mk3(P.bg_a.x, P.bg_a.y, P.bg_a.z);
 }

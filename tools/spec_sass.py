@@ -51,6 +51,16 @@ for l in lines:
 print(f"{len(ops)} static instructions")
 mix = collections.Counter(o[1].split(".")[0] for o in ops)
 print(", ".join(f"{k} {v}" for k, v in mix.most_common(24)))
+# the path loop: from the target of the last backward branch after a VOTE.ANY to that branch
+ALU = {"FSETP", "LOP3", "FSEL", "SEL", "ISETP", "SHF", "I2FP", "PRMT", "FMNMX", "FMNMX3", "IADD3", "VOTE", "PLOP3", "LEA", "VIADD", "MOV",
+       "IABS", "FSET"}
+for i, o in enumerate(ops[:-1]):
+    if o[1].startswith("VOTE") and "BRA" in ops[i + 1][1]:
+        m = re.search(r"BRA 0x([0-9a-f]+)", ops[i + 1][2])
+        if m and int(m.group(1), 16) < o[0]:
+            body = [q for q in ops if int(m.group(1), 16) <= q[0] <= ops[i + 1][0]]
+            n_alu = sum(1 for q in body if q[1].split(".")[0] in ALU)
+            print(f"path loop: {len(body)} static instructions, {n_alu} on the ALU pipe (compares, selects, logic, moves, conversions)")
 if args.dump:
     open(args.dump, "w").write("\n".join(o[2] for o in ops))
     print("SASS ->", args.dump)
