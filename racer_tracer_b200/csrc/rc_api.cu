@@ -551,6 +551,7 @@ static void build_tables(const rc_scene* s, HostTables& t) {
         // a sphere: the centre's velocity per unit of ray time (0 when it does not move)
         p.n = make_float4(type == RC_PRIM_YZ_RECT ? 1.f : 0.f, type == RC_PRIM_XZ_RECT ? 1.f : 0.f, type == RC_PRIM_XY_RECT ? 1.f : 0.f, 0.f);
         if (type == RC_PRIM_MOVING_SPHERE) p.n = make_float4((float)vel[0], (float)vel[1], (float)vel[2], 0.f);
+        p.n.w = (float)m.type;   // RT_MAT_* as a float: shade_hit tests it with one float compare
         kinds[i] = type;
         ids[i] = s->prim_id[i];
         if (s->prim_aabb)

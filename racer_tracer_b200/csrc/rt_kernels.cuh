@@ -225,18 +225,19 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
                     vec3f& T, vec3f& emit) {
     Hit h = make_hit(S, prim, r, t);
     float4 pb = S.pb(prim), pc = S.pc(prim);
-    int mat = kinds_mat(pb.z);
+    // the material kind as a float (n.w of the table): one float compare instead of mask + integer compare
+    const float mat = S.pn(prim).w;
     vec3f col = mk3(pc.x, pc.y, pc.z);
     if (TEX) {  // compiled out for scenes whose textures are all solid colours
         if (kinds_tex(pb.z) != RT_TEX_SOLID) col = texture_value(P, X, S, __float_as_int(pb.w), prim, h);
     }
     emit = mk3(0.0f, 0.0f, 0.0f);
-    if (RT_HAS_MAT(RT_MAT_LIGHT) && mat == RT_MAT_LIGHT) {  // diffuse_light.rs:25-36
+    if (RT_HAS_MAT(RT_MAT_LIGHT) && mat == (float)RT_MAT_LIGHT) {  // diffuse_light.rs:25-36
         emit = col;
         return false;
     }
     vec3f nd;
-    if (RT_HAS_MAT(RT_MAT_LAMBERTIAN) && (mat == RT_MAT_LAMBERTIAN || !(RT_HAS_MAT(RT_MAT_METAL) || RT_HAS_MAT(RT_MAT_DIELECTRIC)))) {  // lambertian.rs:25-39
+    if (RT_HAS_MAT(RT_MAT_LAMBERTIAN) && (mat == (float)RT_MAT_LAMBERTIAN || !(RT_HAS_MAT(RT_MAT_METAL) || RT_HAS_MAT(RT_MAT_DIELECTRIC)))) {  // lambertian.rs:25-39
         vec3f rv;
         if (SAMPLER == 1) rv = unit_vector(reject_in_unit_sphere<ROUNDS>(R, bounce));
         else rv = sphere_direct_w(rnd.x, rnd.y);
@@ -247,7 +248,7 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
         const float k0 = fmaxf(fmaxf(fabsf(nd.x), fabsf(nd.y)), fabsf(nd.z)) < 1e-8f ? 1.0f : 0.0f;
         fma2_bcast(k0, h.n.x, h.n.y, nd.x, nd.y, nd.x, nd.y);
         nd.z = fmaf(k0, h.n.z, nd.z);
-    } else if (RT_HAS_MAT(RT_MAT_METAL) && (mat == RT_MAT_METAL || !RT_HAS_MAT(RT_MAT_DIELECTRIC))) {  // metal.rs:25-44
+    } else if (RT_HAS_MAT(RT_MAT_METAL) && (mat == (float)RT_MAT_METAL || !RT_HAS_MAT(RT_MAT_DIELECTRIC))) {  // metal.rs:25-44
         vec3f rv;
         if (SAMPLER == 1) rv = reject_in_unit_sphere<ROUNDS>(R, bounce);
         else {
@@ -346,7 +347,10 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     const vec3f T_ONE = mk3(1.0f, 1.0f, 1.0f);
     float time = 0.0f;         // Ray::time of the path (scattered rays inherit it, lambertian.rs:36 etc.)
     int s = valid ? s_first : s_last;
-    int depth_left = 0;        // > 0: this lane is on a path that may still trace that many segments; 0: no path
+    // > 0: this lane is on a path that may still trace that many segments; 0: no path.  A float (max_depth <= 63
+    // is exact): counting down and the "budget spent" weight are then FADD / FADD.SAT on the FMA pipe instead
+    // of integer add + compare + select on the ALU pipe, which is the saturated one in this kernel.
+    float depth_left = 0.0f;
     int last_prim = -1;
     uint32_t seg = 0;          // index of the segment about to be traced (0 = primary ray)
     uint32_t ctr1 = 0;         // Philox counter word of that segment's block: sample | seg << 24 (tag PATH = 0), kept incrementally
@@ -384,23 +388,23 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
 #pragma unroll 1
     while (true) {
         // ---- lanes whose path ended take the next sample of their pixel (bookkeeping only) ----
-        bool fresh = depth_left == 0 && s < s_last;
+        bool fresh = depth_left == 0.0f && s < s_last;
         if (RT_REGEN_MIN > 1) {
-            const unsigned want = __ballot_sync(0xffffffffu, fresh), live = __ballot_sync(0xffffffffu, depth_left != 0);
+            const unsigned want = __ballot_sync(0xffffffffu, fresh), live = __ballot_sync(0xffffffffu, depth_left != 0.0f);
             if ((want | live) == 0u) break;
             if (live != 0u && __popc(want) < RT_REGEN_MIN) fresh = false;
         } else {
-            if (!__any_sync(0xffffffffu, (depth_left != 0) | (s < s_last))) break;
+            if (!__any_sync(0xffffffffu, (depth_left != 0.0f) | (s < s_last))) break;
         }
         if (fresh) {
             R.sample = (uint32_t)s;
             ctr1 = R.sample;
             seg = 0; last_prim = -1;
             T = mk3(1.0f, 1.0f, 1.0f);
-            depth_left = P.max_depth;
+            depth_left = (float)P.max_depth;
         }
         s += fresh ? 1 : 0;
-        if (depth_left != 0) {
+        if (depth_left != 0.0f) {
             // ---- the segment's random block: drawn here, by all lanes together ----
             const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, ctr1, P.ks);   // == rt_ctr1(R.sample, seg, RT_TAG_PATH)
             if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337
@@ -418,7 +422,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                     const vec3f bg = background_color(P, d);
                     sum = mk3(fmaf(T.x, bg.x, sum.x), fmaf(T.y, bg.y, sum.y), fmaf(T.z, bg.z, sum.z));
                 }
-                depth_left = 0;
+                depth_left = 0.0f;
             } else {
                 ++seg;   // hit number along the path (1 = primary hit)
                 ctr1 += 1u << 24;
@@ -428,11 +432,12 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                 else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
                 if (!cont) {                 // absorbed (X_end = 0) or a light (X_end = emission)
                     sum = sum + T * X_end;
-                    depth_left = 0;
+                    depth_left = 0.0f;
                 } else {
                     last_prim = prim;
                     // white at depth 0 (renderer.rs:48-56): sum += w T with w = 1 when the budget is spent, as arithmetic
-                    const float w = --depth_left == 0 ? 1.0f : 0.0f;
+                    depth_left -= 1.0f;
+                    const float w = __saturatef(1.0f - depth_left);   // 1 when the budget is spent (depth_left == 0), else 0
                     fma2_bcast(w, T.x, T.y, sum.x, sum.y, sum.x, sum.y);
                     sum.z = fmaf(w, T.z, sum.z);
                 }

@@ -17,7 +17,7 @@
 //   n: rect: the +axis unit normal (xy_rect.rs:45 etc.), so that the hit record
 //      is formed with multiply-adds instead of per-type selects;  sphere: the
 //      centre's velocity per unit of ray time, centre(time) = a.xyz + time * n.xyz
-//      (MovingSphere::pos, moving_sphere.rs:37-39; 0 for a static sphere)
+//      (MovingSphere::pos, moving_sphere.rs:37-39; 0 for a static sphere); n.w = material kind as a float
 // packed kinds (b.z bits): [0:4) prim type, [4:8) material type, [8:12)
 // texture type, [12:32) instance index + 1 (0 = none)
 // ---------------------------------------------------------------------------
@@ -743,8 +743,9 @@ RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT
         h.p.z = fmaf(e, N.z, h.p.z);
         const float dn = dot(r.d, N);
         h.front_face = dn < 0.0f;   // dot(d, axis) < 0, geometry.rs:49-56
-        // +1 if dn < 0 else -1: the inverted sign bit of dn over the bits of 1.0f (one LOP3)
-        const float sgn = __int_as_float((~__float_as_int(dn) & 0x80000000) | 0x3f800000);
+        // +1 if dn < 0 else -1, on the FMA pipe: sat(-dn * 3e38) is 1 or 0 (|dn| below 3e-39 — an fp32 subnormal —
+        // would give a fraction; a ray that parallel to the plane has no hit to shade)
+        const float sgn = fmaf(2.0f, __saturatef(dn * -3.0e38f), -1.0f);
         h.outward = N;
         mul2_bcast(sgn, N.x, N.y, h.n.x, h.n.y);
         h.n.z = sgn * N.z;
