@@ -117,8 +117,13 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
     if (const char* e = std::getenv("RC_REGEN_MIN")) o << "#define RT_REGEN_MIN " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
     o << "#include \"rt_scene.cuh\"\n";
+    // rectangle-only scenes keep the index of the best hit as a FLOAT, so that both conditional moves of the
+    // closest-hit update are predicated FFMAs on the FMA pipe (rect_closest_fma); with spheres around, the
+    // index stays an integer (rect_closest)
+    const bool fidx = (prims_mask & 1) == 0 && std::getenv("RC_SPEC_SELECT") == nullptr && std::getenv("RC_SPEC_INT_INDEX") == nullptr;
     o << "RT_D int spec_closest_hit(const RayT<float>& r, int last_prim, float& best_t) {\n";
     o << "    int best = -1;\n    best_t = RT_NO_HIT;\n    (void)last_prim;\n";
+    if (fidx) o << "    float bestf = -1.0f;\n";
     const int n_sph = kp.lin_end[0];
     bool any_motion = false;
     if (n_sph > 0) {
@@ -203,7 +208,10 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
         }
         for (int i = begin; i < end; ++i) {
             const float4 c = kp.crect_bounds[g][i - begin];
-            if (chain)
+            if (chain && fidx)
+                o << "        rect_closest_fma(t" << i << ", xa" << i << ", xb" << i << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", "
+                  << spec_float((float)i) << ", best_t, bestf);\n";
+            else if (chain)
                 o << "        rect_closest(t" << i << ", xa" << i << ", xb" << i << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", " << i
                   << ", best_t, best);\n";
             else
@@ -278,12 +286,17 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
                 o << "#error \"instanced moving spheres are rejected at upload\"\n";
             } else {
                 const double ha = 0.5 * ((double)p.a.y - p.a.x), hb = 0.5 * ((double)p.a.w - p.a.z);
+                if (fidx)
+                    o << "        rect_closest_fma(u" << i << ", ea" << i << ", eb" << i << ", " << spec_float((float)ha) << ", " << spec_float((float)hb) << ", "
+                      << spec_float((float)i) << ", best_t, bestf);\n";
+                else
                 o << "        rect_closest(u" << i << ", ea" << i << ", eb" << i << ", " << spec_float((float)ha) << ", " << spec_float((float)hb) << ", " << i
                   << ", best_t, best);\n";
             }
         }
         o << "    }\n";
     }
+    if (fidx) o << "    best = __float2int_rn(bestf);\n";
     o << "    return best;\n}\n";
     o << "#define RT_SPECIALIZED 1\n";
     o << "#define RT_SPEC_MATS " << mats_mask << "\n";

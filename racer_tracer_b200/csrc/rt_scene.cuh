@@ -385,6 +385,21 @@ RT_D void rect_closest(float t, float xa, float xb, float ha, float hb, int inde
         : "+f"(best_t), "+r"(best) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "r"(index));
 }
 
+// The same update with the two conditional moves done by PREDICATED FFMAs (best = t * 1 + 0, index = index * 0 +
+// i as a float): four compares on the ALU pipe and two instructions on the FMA pipe, which has room, instead of
+// four compares + two selects on the ALU pipe, which is the saturated one.  `best_index` carries the index as a
+// float (-1 = none).  t > 0 here, so t * 1 + 0 is t exactly.
+RT_D void rect_closest_fma(float t, float xa, float xb, float ha, float hb, float index, float& best_t, float& best_index) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.f32 p, %2, %4;\n\t"
+        "setp.le.and.f32 p, %3, %5, p;\n\t"
+        "setp.ge.and.f32 p, %6, 0f3A83126F, p;\n\t"   /* t >= 0.001f */
+        "setp.le.and.f32 p, %6, %0, p;\n\t"
+        "@p fma.rn.f32 %0, %6, 0f3F800000, 0f00000000;\n\t"
+        "@p fma.rn.f32 %1, %1, 0f00000000, %7;\n\t}"
+        : "+f"(best_t), "+f"(best_index) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "f"(index));
+}
+
 // Packed FP32 (sm_100a FFMA2 / FADD2 / FMUL2: two fp32 lanes per instruction, one issue slot, scalar operands
 // broadcast).  The pipe spends two cycles on them, so the FP32 peak is unchanged (tools/micro/ffma2_bench.cu:
 // 71 vs 73 TFLOP/s) — but this kernel is bound by ISSUE slots, not by the FMA pipe (34 % busy), and two
