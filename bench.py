@@ -49,7 +49,7 @@ WORKLOADS = {
 
 # HBM traffic of the dominant kernel per launch, from the committed ncu capture (bytes); the megakernel reads the
 # accumulation buffer once and its stores stay in L2 until evicted, independent of spp
-NCU_DRAM_BYTES_PER_LAUNCH = {"cornell_box_1080p_1024spp": 24906752}
+NCU_DRAM_BYTES_PER_LAUNCH = {"cornell_box_1080p_1024spp": 24906496 + 768}
 
 
 def scene_file(scene):
@@ -403,7 +403,7 @@ def main():
             line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": fp32_tflops, "unit": "TFLOP/s",
                                 "frac": achieved / fp32_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the megakernel launch, ncu --set full "
-                                                  "(profiles/r01_megakernel_v17_specialised_ncu.md): the accumulation buffer, once",
+                                                  "(profiles/r01_megakernel_v19_specialised_ncu.md): the accumulation buffer, once",
                                 "peak_source": "FFMA micro-benchmark in this run (rc_fp32_peak), per GPU",
                                 "flops_per_sample": A_used, "lane_ginstr_per_s_peak": lane_ginstr,
                                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_kind,

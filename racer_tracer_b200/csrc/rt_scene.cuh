@@ -931,9 +931,13 @@ RT_D vec3f sphere_direct(float u1, float u2) {
 // sphere_direct(u24(wx), u24(wy)) with the integer -> uniform scalings folded into the
 // multiply-adds (same values: u24 is exact in fp32 and the scale factors are powers of two)
 RT_D vec3f sphere_direct_w(uint32_t wx, uint32_t wy) {
-    const float z = fmaf((float)(wx >> 8), -1.0f / 8388608.0f, 1.0f);                 // 1 - 2 u1, in [-1 + 2^-23, 1]
+    // (w >> 8 as the high word of w * 2^24: an IMAD.HI on the FMA pipe instead of a shift on the ALU pipe)
+    wx = __umulhi(wx, 1u << 24); wy = __umulhi(wy, 1u << 24);
+    // 1 - 2 u1, in [-1 + 2^-23, 1]; as multiply (exact: a power of two) + add with immediates, so that no constant
+    // has to be put into a register with a MOV on the ALU pipe
+    const float z = __fadd_rn(1.0f, __fmul_rn((float)wx, -1.0f / 8388608.0f));
     const float r = fast_sqrt(fmaf(-z, z, 1.0f));                                       // |z| <= 1 exactly: never negative
-    const float phi = fmaf((float)(wy >> 8), 6.283185307179586f / 16777216.0f, -3.14159265358979323846f);
+    const float phi = fmaf((float)wy, 6.283185307179586f / 16777216.0f, -3.14159265358979323846f);
     return mk3(-r * __cosf(phi), -r * __sinf(phi), z);
 }
 
