@@ -108,3 +108,22 @@ def test_specialised_source_compiles_for_sm_100a(cuda_lib, cfg, tmp_path):
                    check=True)
     big = harness.prepare_job(scene_path("clown"), cfg, 64, 64)
     assert cuda_lib.rc_spec_source(big.scene.ptr, None, 0) > 0          # 23 spheres still fit the constant bank
+
+
+@pytest.mark.parametrize("name,needle", [("sandbox", "rect_closest_fma"), ("sandbox_boxes", "aabb_hit_reference"),
+                                         ("clown", "sphere_hit<float>"), ("emissive", "#define RT_SPEC_BG_BLACK 1")])
+def test_specialised_source_of_every_scene_kind_compiles(cuda_lib, cfg, tmp_path, name, needle):
+    """The generator's other branches — instanced objects (cull box + ray transform + packed box faces), the
+    float-index closest hit of rectangle-only scenes, spheres, textures — produce code nvcc accepts for sm_100a."""
+    from conftest import scene_path
+    job = harness.prepare_job(scene_path(name), cfg, 64, 64)
+    n = cuda_lib.rc_spec_source(job.scene.ptr, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    assert cuda_lib.rc_spec_source(job.scene.ptr, buf, n + 1) == n
+    src = buf.value.decode()
+    assert needle in src
+    cu = tmp_path / "spec.cu"
+    cu.write_text(src)
+    subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I",
+                    os.path.join(ROOT, "racer_tracer_b200", "csrc"), "-cubin", "-o", str(tmp_path / "spec.cubin"), str(cu)],
+                   check=True)
