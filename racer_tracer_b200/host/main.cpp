@@ -15,8 +15,30 @@
 #include <string>
 
 #include "racer_host.hpp"
+#include "yaml_lite.hpp"
 
 using namespace racer;
+
+// --dump-yaml: the parsed tree of one YAML file as JSON (keys lower-cased as the loaders see them, scalars as
+// strings); tests compare it with PyYAML on the reference's own files.
+static void yaml_to_json(const yaml_lite::Node& n, std::string& out) {
+    auto quote = [&](const std::string& s) {
+        out += '"';
+        for (char c : s) { if (c == '"' || c == '\\') out += '\\'; out += c; }
+        out += '"';
+    };
+    if (n.is_null()) out += "null";
+    else if (n.is_scalar()) quote(n.scalar);
+    else if (n.is_seq()) {
+        out += '[';
+        for (size_t i = 0; i < n.seq.size(); ++i) { if (i) out += ','; yaml_to_json(n.seq[i], out); }
+        out += ']';
+    } else {
+        out += '{';
+        for (size_t i = 0; i < n.map.size(); ++i) { if (i) out += ','; quote(n.map[i].first); out += ':'; yaml_to_json(n.map[i].second, out); }
+        out += '}';
+    }
+}
 
 int main(int argc, char** argv) {
     std::string config_path, scene_path, out_path, dump_path;
@@ -35,6 +57,22 @@ int main(int argc, char** argv) {
             else if (a == "--scene") scene_path = next();
             else if (a == "--out") out_path = next();
             else if (a == "--dump-flat") dump_path = next();
+            else if (a == "--dump-yaml") {
+                const std::string file = next();
+                std::ifstream f(file.c_str());
+                if (!f) throw TracerError(TracerError::Configuration, "Config Error (" + file + "): configuration file \"" + file + "\" not found");
+                std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+                try {
+                    yaml_lite::Node doc = yaml_lite::parse(text);
+                    yaml_lite::lower_keys(doc);
+                    std::string out;
+                    yaml_to_json(doc, out);
+                    std::printf("%s\n", out.c_str());
+                } catch (const yaml_lite::ParseError& e) {
+                    throw TracerError(TracerError::Configuration, "Config Error (" + file + "): " + e.what());
+                }
+                return 0;
+            }
             else if (a == "--image-dir") image_dirs.push_back(next());
             else if (a == "--width") width = std::atol(next().c_str());
             else if (a == "--height") height = std::atol(next().c_str());

@@ -228,3 +228,86 @@ def test_racer_render_png_equals_the_harness_path(racer_render, tmp_path, cfg, r
     renderer.upload(job)
     pv = renderer.render_preview(harness.make_params(120, 80, cfg.preview.samples, cfg.preview.max_depth, seed=5), sw, sh)
     assert np.array_equal(body, renderer.postprocess(job.tone_map, pv)[0])
+
+
+def _canon(v):
+    """PyYAML value -> the shape --dump-yaml prints: lower-cased keys, scalars by numeric value or text."""
+    if isinstance(v, dict):
+        return {str(k).lower(): _canon(x) for k, x in v.items()}
+    if isinstance(v, list):
+        return [_canon(x) for x in v]
+    return _scalar(v)
+
+
+def _scalar(v):
+    if v is None:
+        return None
+    if isinstance(v, bool):
+        return str(v).lower()
+    if isinstance(v, (int, float)):
+        return float(v)
+    try:
+        return float(v)
+    except ValueError:
+        return str(v)
+
+
+def _canon_cpp(v):
+    if isinstance(v, dict):
+        return {k: _canon_cpp(x) for k, x in v.items()}
+    if isinstance(v, list):
+        return [_canon_cpp(x) for x in v]
+    return _scalar(v)
+
+
+BLOCK_STYLE = """\
+# block style, as the reference's own scene files are written (resources/scenes/*.yml)
+materials:
+  Ground:
+    Lambertian:
+      texture: ground   # trailing comment
+  "quoted name":
+    Metal:
+      texture: 'single quoted'
+      fuzz: 1.0e-1
+geometry:
+  floor:
+    XzRect:
+      x0: -1000
+      x1: +1000.5
+      z0: 0
+      z1: 1
+      k: 0
+      material: Ground
+  list_block:
+    Sphere:
+      pos:
+        - 0
+        - -1.5
+        - 2
+      radius: 0.5
+      material: "quoted name"
+  nested_flow: {Box: {min: {pos: [0, 0, 0]}, max: {pos: [1, 2, 3]}, material: Ground}}
+empty_map: {}
+empty_seq: []
+flag: true
+"""
+
+
+@pytest.mark.parametrize("name", ["config.yml"] + ["scenes/" + s + ".yml" for s in
+                                                     ("clown", "cornell_box", "emissive", "noise_and_textures", "sandbox_boxes",
+                                                      "three_balls", "two_balls")] + ["<block>"])
+def test_yaml_reader_agrees_with_pyyaml(racer_render, tmp_path, name):
+    """yaml_lite.hpp (the C++ host's reader for config.yml / scene files, replacing the reference's serde_yaml
+    use at src/config.rs:306 and src/scene/yml.rs:213) parses every fixture, and a block-style document in the
+    style of the reference's own files, to the same tree as PyYAML."""
+    yaml = pytest.importorskip("yaml")
+    if name == "<block>":
+        path = tmp_path / "block.yml"
+        path.write_text(BLOCK_STYLE)
+    else:
+        path = os.path.join(ROOT, "tests", "golden", name)
+    out = run(racer_render, "--dump-yaml", str(path)).stdout
+    got = _canon_cpp(json.loads(out))
+    want = _canon(yaml.safe_load(open(path).read()))
+    assert got == want
