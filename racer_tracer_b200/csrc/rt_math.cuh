@@ -66,6 +66,12 @@ RT_D void mul2(float a0, float a1, float b0, float b1, float& r0, float& r1) {  
         "mul.f32x2 rr, aa, bb;\n\t"
         "mov.b64 {%0, %1}, rr;\n\t}" : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+RT_D void fma2(float a0, float a1, float b0, float b1, float c0, float c1, float& r0, float& r1) {   // (a0, a1) * (b0, b1) + (c0, c1)
+    asm("{\n\t.reg .b64 aa, bb, cc, rr;\n\t"
+        "mov.b64 aa, {%2, %3};\n\tmov.b64 bb, {%4, %5};\n\tmov.b64 cc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rr, aa, bb, cc;\n\t"
+        "mov.b64 {%0, %1}, rr;\n\t}" : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
 
 template <typename T> RT_D Vec3T<T> unit_vector(Vec3T<T> a) { return a * rt_rsqrt(length_squared(a)); }
 
