@@ -102,6 +102,7 @@ struct rc_ctx {
     bool has_scene = false, has_camera = false;
     bool has_textures = false;   // any primitive whose texture is not a solid colour
     int mats_mask = 0xF;         // material kinds the scene uses
+    int prims_mask = 0xF;        // primitive kinds the scene uses (bit RT_PRIM_*; moving spheres count as spheres)
     std::string spec_source;     // generated source of the scene-specialised kernel ("" = not generated yet)
     std::vector<LbvhObject> objects, objects_next;   // top-level objects of the uploaded scene (rc_build_lbvh)
     std::vector<int> prim_order;       // device primitive i = uploaded primitive prim_order[i] (empty: identity)
@@ -367,17 +368,22 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         }
         // scene-specialised kernel (NVRTC), cached per scene and device
         SpecKernel* spec = nullptr;
-        if (p->specialize && ctx->mode == RT_MODE_CONST_LINEAR && p->sampler == RC_SAMPLER_DIRECT && rounds == 10) {
+        // (the constant-table path gets its primitives as immediates; the BVH paths get the scene's kinds of
+        // primitive, material and wrapper compiled in or out — 48 KB of dynamic shared memory without opt-in)
+        const bool spec_mode_ok = ctx->mode == RT_MODE_CONST_LINEAR ||
+                                  ((ctx->mode == RT_MODE_SMEM_BVH || ctx->mode == RT_MODE_GLOBAL_BVH) && ctx->smem_bytes <= 48 * 1024 &&
+                                   std::getenv("RC_NO_BVH_SPEC") == nullptr);
+        if (p->specialize && spec_mode_ok && p->sampler == RC_SAMPLER_DIRECT && rounds == 10) {
             std::string err;
             if (!spec_load_api((const void*)&rc_abi_version)) err = spec_api().err;
             else {
-                if (ctx->spec_source.empty()) ctx->spec_source = spec_generate(ctx->kp, ctx->has_textures, ctx->mats_mask);
+                if (ctx->spec_source.empty())
+                    ctx->spec_source = spec_generate(ctx->kp, ctx->has_textures, ctx->mats_mask, ctx->mode, ctx->prims_mask, ctx->instanced);
                 spec = spec_build(d.spec_cache, ctx->spec_source, err);
             }
             if (!spec && p->specialize == 1) return fail(RC_ERR_STATE, "scene specialisation failed: " + err);
         } else if (p->specialize == 1) {
-            return fail(RC_ERR_INVALID, "specialize = 1 needs the megakernel, the direct sampler, 10 Philox rounds and a scene "
-                                        "that fits the constant-bank path");
+            return fail(RC_ERR_INVALID, "specialize = 1 needs the megakernel, the direct sampler and 10 Philox rounds");
         }
         const int s0 = kp.s_begin, s1 = kp.s_end;
         const int step = cancel ? 32 : (s1 - s0);
@@ -490,6 +496,7 @@ struct HostTables {   // everything rc_upload_scene derives from an rc_scene, be
     size_t smem_bytes = 0;
     bool has_textures = false;
     int mats_mask = 0xF;
+    int prims_mask = 0xF;
 };
 
 // f64 host scene -> fp32 device tables (pure host arithmetic)
@@ -681,7 +688,11 @@ static void build_tables(const rc_scene* s, HostTables& t) {
     t.mode = pick_mode(s, rects_fit && objs_fit, any_instance && !objs_fit, t.smem_bytes);
     t.has_textures = any_textured;
     t.mats_mask = 0;
-    for (int i = 0; i < s->n_prims; ++i) t.mats_mask |= 1 << s->materials[s->prim_material[i]].type;
+    t.prims_mask = 0;
+    for (int i = 0; i < s->n_prims; ++i) {
+        t.mats_mask |= 1 << s->materials[s->prim_material[i]].type;
+        t.prims_mask |= 1 << (s->prim_type[i] == RC_PRIM_MOVING_SPHERE ? RC_PRIM_SPHERE : s->prim_type[i]);
+    }
 
 }
 
@@ -790,6 +801,7 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     ctx->smem_bytes = t.smem_bytes;
     ctx->has_textures = t.has_textures;
     ctx->mats_mask = t.mats_mask;
+    ctx->prims_mask = t.prims_mask;
     ctx->spec_source.clear();
     ctx->aov.n_prims = s->n_prims; ctx->aov.n_nodes = s->n_nodes;
     // top-level objects = runs of primitives that share an object id (id >> 3; a Box's six sides) and a stored Aabb
@@ -1324,8 +1336,8 @@ int64_t rc_spec_source(const rc_scene* scene, char* out, int64_t capacity) {
     if (validate_scene(scene) != RC_OK) return -1;
     HostTables t;
     build_tables(scene, t);
-    if (t.mode != RT_MODE_CONST_LINEAR) return fail(RC_ERR_INVALID, "scene does not fit the constant-bank path");
-    std::string src = spec_generate(t.kp, t.has_textures, t.mats_mask);
+    if (t.mode == RT_MODE_SMEM_LINEAR) return fail(RC_ERR_INVALID, "a node-less scene beyond the constant table has no specialised kernel (it gets a BVH at upload)");
+    std::string src = spec_generate(t.kp, t.has_textures, t.mats_mask, t.mode, t.prims_mask, !t.instances.empty());
     if (out && capacity > 0) {
         size_t n = src.size() < (size_t)capacity - 1 ? src.size() : (size_t)capacity - 1;
         std::memcpy(out, src.data(), n);

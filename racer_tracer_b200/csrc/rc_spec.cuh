@@ -30,6 +30,7 @@ struct SpecKernel {
     void* module = nullptr;     // CUmodule
     void* function = nullptr;   // CUfunction
     std::string source;
+    std::string error;          // non-empty: this source failed to compile / load (remembered, not retried per render)
 };
 
 struct SpecApi {
@@ -101,8 +102,31 @@ inline std::string spec_float(float v) {
 
 // Source of the specialised translation unit for a scene already laid out in KParams
 // (type-sorted constant-bank table).
-inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask) {
+inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int mode = RT_MODE_CONST_LINEAR, int prims_mask_all = 0xF,
+                                 bool instanced = false) {
     std::ostringstream o;
+    if (mode != RT_MODE_CONST_LINEAR) {
+        // BVH paths: the tables stay in memory; what is compiled in is which kinds of primitive, material, wrapper,
+        // lens and motion the scene has — the leaf test and the shading lose the branches of everything absent.
+        const bool black = __float_as_int_host(kp.bg_a.w) != 0 && kp.bg_a.x == 0.f && kp.bg_a.y == 0.f && kp.bg_a.z == 0.f;
+        o << "#define RT_SPEC_PRIMS " << prims_mask_all << "\n";
+        o << "#define RT_SPEC_BG_BLACK " << (black ? 1 : 0) << "\n";
+        o << "#define RT_HAS_INSTANCES " << (instanced ? 1 : 0) << "\n";
+        o << "#define RT_HAS_LENS " << (kp.lens_enabled ? 1 : 0) << "\n";
+        o << "#define RT_HAS_MOTION " << (kp.has_motion ? 1 : 0) << "\n";
+        if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
+        o << "#include \"rt_scene.cuh\"\n";
+        o << "RT_D int spec_closest_hit(const RayT<float>&, int, float&) { return -1; }   // constant-table scenes only\n";
+        o << "#define RT_SPECIALIZED 1\n";
+        o << "#define RT_SPEC_MATS " << mats_mask << "\n";
+        o << "#include \"rt_kernels.cuh\"\n";
+        o << "extern \"C\" __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)\n"
+             "spec_megakernel(const __grid_constant__ KParams P, float* __restrict__ accum) {\n"
+             "    extern __shared__ __align__(16) unsigned char smem[];\n"
+             "    megakernel_body<" << (mode == RT_MODE_SMEM_BVH ? "RT_MODE_SMEM_BVH" : "RT_MODE_GLOBAL_BVH") << ", 0, 10, "
+          << (tex ? "true" : "false") << ">(P, accum, smem);\n}\n";
+        return o.str();
+    }
     // primitive kinds present, background, regeneration batching: known before the headers are read
     int prims_mask = 0;   // bit RT_PRIM_* (moving spheres count as spheres), instanced primitives included
     for (int i = 0; i < kp.n_prims && i < RT_MAX_CONST_PRIMS; ++i) {
@@ -321,7 +345,16 @@ inline bool spec_read(const std::string& path, std::string& out) {
 // Compile + load; returns nullptr and sets err on failure.
 inline SpecKernel* spec_build(std::map<std::string, SpecKernel>& cache, const std::string& source, std::string& err) {
     auto it = cache.find(source);
-    if (it != cache.end()) return &it->second;
+    if (it != cache.end()) {
+        if (!it->second.error.empty()) { err = it->second.error; return nullptr; }
+        return &it->second;
+    }
+    auto remember_failure = [&]() {
+        SpecKernel bad;
+        bad.error = err;
+        cache.emplace(source, bad);
+        return (SpecKernel*)nullptr;
+    };
     SpecApi& a = spec_api();
     std::string h_math, h_scene, h_kernels;
     if (!spec_read(a.header_dir + "rt_math.cuh", h_math) || !spec_read(a.header_dir + "rt_scene.cuh", h_scene) ||
@@ -342,7 +375,7 @@ inline SpecKernel* spec_build(std::map<std::string, SpecKernel>& cache, const st
         if (n) a.GetProgramLog(prog, &log[0]);
         err = "nvrtc compile failed: " + log.substr(0, 1500);
         a.DestroyProgram(&prog);
-        return nullptr;
+        return remember_failure();
     }
     size_t n = 0;
     a.GetCUBINSize(prog, &n);
@@ -351,8 +384,8 @@ inline SpecKernel* spec_build(std::map<std::string, SpecKernel>& cache, const st
     a.DestroyProgram(&prog);
     SpecKernel k;
     k.source = source;
-    if (a.cuModuleLoadData(&k.module, cubin.data()) != 0) { err = "cuModuleLoadData failed"; return nullptr; }
-    if (a.cuModuleGetFunction(&k.function, k.module, "spec_megakernel") != 0) { err = "spec_megakernel not found in module"; return nullptr; }
+    if (a.cuModuleLoadData(&k.module, cubin.data()) != 0) { err = "cuModuleLoadData failed"; return remember_failure(); }
+    if (a.cuModuleGetFunction(&k.function, k.module, "spec_megakernel") != 0) { err = "spec_megakernel not found in module"; return remember_failure(); }
     auto res = cache.emplace(source, k);
     return &res.first->second;
 }

@@ -37,6 +37,17 @@
 #define RT_TEX_IMAGE 2
 #define RT_TEX_NOISE 3
 
+// Which primitive kinds a scene contains (bit RT_PRIM_*).  A scene-specialised translation unit
+// defines it; the precompiled kernels keep every kind.
+#ifndef RT_SPEC_PRIMS
+#define RT_SPEC_PRIMS 0xF
+#endif
+#ifndef RT_HAS_INSTANCES
+#define RT_HAS_INSTANCES 1    /* a scene-specialised kernel sets 0 when nothing is rotated / translated */
+#endif
+#define RT_HAS_SPHERES (RT_SPEC_PRIMS & 1)
+#define RT_HAS_RECTS (RT_SPEC_PRIMS & 0xE)
+
 #define RT_MAX_CONST_PRIMS 40   // primitives kept in the kernel-parameter constant bank
 #define RT_MAX_CONST_RECTS 8    // per axis group, fully unrolled with constant-bank operands
 #define RT_MAX_CONST_OBJS 8     // instanced top-level objects (Box + RotateY / Translate) of the linear modes
@@ -322,7 +333,7 @@ RT_D vec3f sphere_centre(float4 a, float4 n, float time) {
 template <class Scene>
 RT_D float prim_test_local(const Scene& S, int i, float4 a, float4 b, const RayT<float>& r, bool self, bool instanced, float t_max) {
     int type = kinds_prim(b.z);
-    if (RT_IS_SPHERE(type)) {
+    if (RT_HAS_SPHERES && (!RT_HAS_RECTS || RT_IS_SPHERE(type))) {
         const float aa = dot(r.d, r.d);
         const bool moving = type == RT_PRIM_MOVING;
         const vec3f ctr = moving ? sphere_centre(a, S.pn(i), r.time) : mk3(a.x, a.y, a.z);
@@ -620,8 +631,8 @@ RT_D float aabb_entry(float4 lo, float4 hi, const RayT<float>& r, float t_max) {
 template <bool ORDERED, class Scene>
 RT_D void leaf_test(const Scene& S, int leaf, const RayT<float>& r, int last_prim, float& best_t, int& best) {
     const int first = leaf & 0xffffff, count = leaf >> 24;
-    const int inst = kinds_inst(S.pb(first).z);
-    if (inst >= 0) {
+    const int inst = RT_HAS_INSTANCES ? kinds_inst(S.pb(first).z) : -1;
+    if (RT_HAS_INSTANCES && inst >= 0) {
         const RayT<float> lr = to_local(S.instances()[inst], r);
         for (int p = first; p < first + count; ++p) {
             const float t = prim_test_local(S, p, S.pa(p), S.pb(p), lr, p == last_prim, true, best_t);
@@ -753,17 +764,6 @@ struct Hit {
     vec3f lp;          // hit point in the primitive's own space (rectangle uv)
     bool front_face;
 };
-
-// Which primitive kinds a scene contains (bit RT_PRIM_*).  A scene-specialised translation unit
-// defines it; the precompiled kernels keep every kind.
-#ifndef RT_SPEC_PRIMS
-#define RT_SPEC_PRIMS 0xF
-#endif
-#ifndef RT_HAS_INSTANCES
-#define RT_HAS_INSTANCES 1    /* a scene-specialised kernel sets 0 when nothing is rotated / translated */
-#endif
-#define RT_HAS_SPHERES (RT_SPEC_PRIMS & 1)
-#define RT_HAS_RECTS (RT_SPEC_PRIMS & 0xE)
 
 template <class Scene>
 RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT<float>& r, float t) {

@@ -188,7 +188,10 @@ def _flatten(fs: "FlatScene", objects: dict, textures, materials, images, perlin
     nodes: list[rc_bvh_node] = []
     if use_bvh and ordered:
         order: list[TopObject] = []
-        _build_bvh(ordered, nodes, order)
+        if len(ordered) >= SAH_MIN_OBJECTS and not instances:
+            _build_bvh_sah(list(enumerate(ordered)), nodes, order)
+        else:
+            _build_bvh(ordered, nodes, order)
         ordered = order
         # fix leaf prim offsets now that the DFS order is known
         first = {}
@@ -574,6 +577,53 @@ def _build_bvh(objs, nodes, order):
     r = _build_bvh(objs[mid:], nodes, order)
     nd.left, nd.right = l, r
     for a in range(3):  # Aabb::from((&a, &b)), src/aabb.rs:95-114
+        nd.bmin[a] = min(nodes[l].bmin[a], nodes[r].bmin[a])
+        nd.bmax[a] = max(nodes[l].bmax[a], nodes[r].bmax[a])
+    return idx
+
+
+SAH_MIN_OBJECTS = 65   # smaller scenes keep the reference's median split (and with it their primitive order)
+
+
+def _area(lo, hi):
+    dx, dy, dz = hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]
+    return 2.0 * (dx * dy + dy * dz + dz * dx)
+
+
+def _build_bvh_sah(objs, nodes, order):
+    """Surface-area-heuristic tree over the same leaves as _build_bvh (one top-level object each), for scenes
+    large enough to be traced through the BVH: the closest hit does not depend on the tree (the images are
+    identical), the number of boxes a ray visits does — the Random scene's ground sphere inflates every
+    ancestor box of a median split.  `objs` = [(canonical index, object)].  Per node: for each axis, sort by
+    box centre (ties: canonical index), sweep every split k and keep the first minimum of
+    area(left) * k + area(right) * (m - k), axes in order x, y, z.  Same node / leaf-order output as
+    _build_bvh; racer_host.cpp::build_bvh_sah is the same algorithm in the same arithmetic."""
+    idx = len(nodes)
+    nd = rc_bvh_node()
+    nodes.append(nd)
+    if len(objs) == 1:
+        o = objs[0][1]
+        nd.bmin[:], nd.bmax[:] = o.aabb_min, o.aabb_max
+        nd.left, nd.right = ~len(order), 1
+        order.append(o)
+        return idx
+    m = len(objs)
+    best = None
+    for axis in range(3):
+        srt = sorted(objs, key=lambda e: (e[1].aabb_min[axis] + e[1].aabb_max[axis], e[0]))
+        lo = np.minimum.accumulate(np.array([e[1].aabb_min for e in srt], dtype=np.float64), axis=0)
+        hi = np.maximum.accumulate(np.array([e[1].aabb_max for e in srt], dtype=np.float64), axis=0)
+        rlo = np.minimum.accumulate(np.array([e[1].aabb_min for e in srt[::-1]], dtype=np.float64), axis=0)[::-1]
+        rhi = np.maximum.accumulate(np.array([e[1].aabb_max for e in srt[::-1]], dtype=np.float64), axis=0)[::-1]
+        for k in range(1, m):
+            cost = _area(lo[k - 1], hi[k - 1]) * k + _area(rlo[k], rhi[k]) * (m - k)
+            if best is None or cost < best[0]:
+                best = (cost, srt, k)
+    _, srt, k = best
+    l = _build_bvh_sah(srt[:k], nodes, order)
+    r = _build_bvh_sah(srt[k:], nodes, order)
+    nd.left, nd.right = l, r
+    for a in range(3):
         nd.bmin[a] = min(nodes[l].bmin[a], nodes[r].bmin[a])
         nd.bmax[a] = max(nodes[l].bmax[a], nodes[r].bmax[a])
     return idx

@@ -174,6 +174,69 @@ int build_bvh(std::vector<TopObject*> objs, std::vector<rc_bvh_node>& nodes, std
     return idx;
 }
 
+// Surface-area-heuristic tree over the same leaves (one top-level object each), for scenes large enough to be
+// traced through the BVH: the closest hit does not depend on the tree, the number of boxes a ray visits
+// does.  Per node: for each axis, sort by box centre (ties: canonical index), sweep every split k, keep the
+// first minimum of area(left) * k + area(right) * (m - k).  The same algorithm in the same f64 arithmetic as
+// harness.py::_build_bvh_sah (tests/test_host_cpp.py compares the trees).
+const size_t SAH_MIN_OBJECTS = 65;
+
+double box_area(const double lo[3], const double hi[3]) {
+    const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return 2.0 * (dx * dy + dy * dz + dz * dx);
+}
+
+int build_bvh_sah(const std::vector<std::pair<int, TopObject*>>& objs, std::vector<rc_bvh_node>& nodes, std::vector<TopObject*>& order) {
+    const int idx = (int)nodes.size();
+    nodes.push_back(rc_bvh_node());
+    if (objs.size() == 1) {
+        TopObject* o = objs[0].second;
+        for (int a = 0; a < 3; ++a) { nodes[idx].bmin[a] = o->lo[a]; nodes[idx].bmax[a] = o->hi[a]; }
+        nodes[idx].left = ~(int)order.size();
+        nodes[idx].right = 1;
+        order.push_back(o);
+        return idx;
+    }
+    const size_t m = objs.size();
+    bool have = false;
+    double best_cost = 0.0;
+    size_t best_k = 0;
+    std::vector<std::pair<int, TopObject*>> best_sorted;
+    std::vector<double> llo(3 * m), lhi(3 * m), rlo(3 * m), rhi(3 * m);
+    for (int axis = 0; axis < 3; ++axis) {
+        std::vector<std::pair<int, TopObject*>> srt(objs);
+        std::sort(srt.begin(), srt.end(), [axis](const std::pair<int, TopObject*>& x, const std::pair<int, TopObject*>& y) {
+            const double kx = x.second->lo[axis] + x.second->hi[axis], ky = y.second->lo[axis] + y.second->hi[axis];
+            return kx < ky || (kx == ky && x.first < y.first);
+        });
+        for (size_t i = 0; i < m; ++i)
+            for (int a = 0; a < 3; ++a) {
+                llo[3 * i + a] = i ? std::min(llo[3 * (i - 1) + a], srt[i].second->lo[a]) : srt[i].second->lo[a];
+                lhi[3 * i + a] = i ? std::max(lhi[3 * (i - 1) + a], srt[i].second->hi[a]) : srt[i].second->hi[a];
+            }
+        for (size_t i = m; i-- > 0;)
+            for (int a = 0; a < 3; ++a) {
+                rlo[3 * i + a] = i + 1 < m ? std::min(rlo[3 * (i + 1) + a], srt[i].second->lo[a]) : srt[i].second->lo[a];
+                rhi[3 * i + a] = i + 1 < m ? std::max(rhi[3 * (i + 1) + a], srt[i].second->hi[a]) : srt[i].second->hi[a];
+            }
+        for (size_t k = 1; k < m; ++k) {
+            const double left = box_area(&llo[3 * (k - 1)], &lhi[3 * (k - 1)]) * (double)k;
+            const double right = box_area(&rlo[3 * k], &rhi[3 * k]) * (double)(m - k);
+            const double cost = left + right;
+            if (!have || cost < best_cost) { have = true; best_cost = cost; best_k = k; best_sorted = srt; }
+        }
+    }
+    const std::vector<std::pair<int, TopObject*>> lhs(best_sorted.begin(), best_sorted.begin() + best_k), rhs(best_sorted.begin() + best_k, best_sorted.end());
+    const int l = build_bvh_sah(lhs, nodes, order);
+    const int r = build_bvh_sah(rhs, nodes, order);
+    nodes[idx].left = l; nodes[idx].right = r;
+    for (int a = 0; a < 3; ++a) {
+        nodes[idx].bmin[a] = std::min(nodes[l].bmin[a], nodes[r].bmin[a]);
+        nodes[idx].bmax[a] = std::max(nodes[l].bmax[a], nodes[r].bmax[a]);
+    }
+    return idx;
+}
+
 // Top-level objects (canonical order) -> structure-of-arrays primitives + host BVH: what the Rust shim
 // does before rc_upload_scene.
 void flatten_objects(SceneData& sd, std::vector<TopObject*> ordered) {
@@ -200,7 +263,13 @@ void flatten_objects(SceneData& sd, std::vector<TopObject*> ordered) {
     // ---- BVH over the top-level objects; primitives stored in its depth-first leaf order
     if (!ordered.empty()) {
         std::vector<TopObject*> order;
-        build_bvh(ordered, sd.nodes, order);
+        if (ordered.size() >= SAH_MIN_OBJECTS && sd.instances.empty()) {
+            std::vector<std::pair<int, TopObject*>> indexed;
+            for (size_t i = 0; i < ordered.size(); ++i) indexed.emplace_back((int)i, ordered[i]);
+            build_bvh_sah(indexed, sd.nodes, order);
+        } else {
+            build_bvh(ordered, sd.nodes, order);
+        }
         ordered = order;
         std::vector<int> first(ordered.size());
         int count = 0;

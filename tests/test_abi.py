@@ -110,20 +110,56 @@ def test_specialised_source_compiles_for_sm_100a(cuda_lib, cfg, tmp_path):
     assert cuda_lib.rc_spec_source(big.scene.ptr, None, 0) > 0          # 23 spheres still fit the constant bank
 
 
-@pytest.mark.parametrize("name,needle", [("sandbox", "rect_closest_fma"), ("sandbox_boxes", "aabb_hit_reference"),
-                                         ("clown", "sphere_hit<float>"), ("emissive", "#define RT_SPEC_BG_BLACK 1")])
-def test_specialised_source_of_every_scene_kind_compiles(cuda_lib, cfg, tmp_path, name, needle):
+def _compile_like_the_library(src: str, tmp_path):
+    """NVRTC with the headers and options rc_spec.cuh uses (it is stricter than nvcc about inline functions
+    that are declared but never defined); nvcc when the cuda-python bindings are not importable."""
+    csrc = os.path.join(ROOT, "racer_tracer_b200", "csrc")
+    try:
+        from cuda.bindings import nvrtc
+    except ImportError:
+        cu = tmp_path / "spec.cu"
+        cu.write_text(src)
+        subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I", csrc,
+                        "-cubin", "-o", str(tmp_path / "spec.cubin"), str(cu)], check=True)
+        return
+    names = [b"rt_math.cuh", b"rt_scene.cuh", b"rt_kernels.cuh"]
+    headers = [open(os.path.join(csrc, n.decode()), "rb").read() for n in names]
+    err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"spec_scene.cu", len(names), headers, names)
+    assert int(err) == 0
+    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-lineinfo", b"-default-device"]
+    err, = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
+    _, size = nvrtc.nvrtcGetProgramLogSize(prog)
+    log = b" " * size
+    nvrtc.nvrtcGetProgramLog(prog, log)
+    assert int(err) == 0, log.decode(errors="replace")[:3000]
+    _, size = nvrtc.nvrtcGetCUBINSize(prog)
+    assert size > 0
+
+
+@pytest.mark.parametrize("name,mode,needle", [
+    ("sandbox", None, "rect_closest_fma"), ("sandbox_boxes", None, "aabb_hit_reference"), ("clown", None, "sphere_hit<float>"),
+    ("emissive", None, "#define RT_SPEC_BG_BLACK 1"),
+    # the BVH paths: kinds of primitive / material / wrapper / motion as defines, tables stay in memory
+    ("random", None, "megakernel_body<RT_MODE_GLOBAL_BVH, 0, 10, true>"),
+    ("sandbox_boxes", "smem", "megakernel_body<RT_MODE_SMEM_BVH, 0, 10, false>"),
+    ("noise_and_textures", "global", "#define RT_SPEC_PRIMS 1\n"),
+])
+def test_specialised_source_of_every_scene_kind_compiles(cuda_lib, cfg, tmp_path, name, mode, needle):
     """The generator's other branches — instanced objects (cull box + ray transform + packed box faces), the
-    float-index closest hit of rectangle-only scenes, spheres, textures — produce code nvcc accepts for sm_100a."""
+    float-index closest hit of rectangle-only scenes, spheres, textures, and the BVH paths — produce code the
+    run-time compiler accepts for sm_100a."""
     from conftest import scene_path
     job = harness.prepare_job(scene_path(name), cfg, 64, 64)
-    n = cuda_lib.rc_spec_source(job.scene.ptr, None, 0)
-    buf = C.create_string_buffer(n + 1)
-    assert cuda_lib.rc_spec_source(job.scene.ptr, buf, n + 1) == n
+    if mode:
+        os.environ["RC_SCENE_MODE"] = mode
+    try:
+        n = cuda_lib.rc_spec_source(job.scene.ptr, None, 0)
+        assert n > 0, cuda_lib.rc_last_error()
+        buf = C.create_string_buffer(n + 1)
+        assert cuda_lib.rc_spec_source(job.scene.ptr, buf, n + 1) == n
+    finally:
+        if mode:
+            del os.environ["RC_SCENE_MODE"]
     src = buf.value.decode()
     assert needle in src
-    cu = tmp_path / "spec.cu"
-    cu.write_text(src)
-    subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I",
-                    os.path.join(ROOT, "racer_tracer_b200", "csrc"), "-cubin", "-o", str(tmp_path / "spec.cubin"), str(cu)],
-                   check=True)
+    _compile_like_the_library(src, tmp_path)

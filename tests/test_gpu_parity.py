@@ -499,10 +499,13 @@ def test_instanced_scene_linear_path_equals_the_bvh_path(renderer, oracle, cfg):
         renderer.upload(job)
         ids_bvh = renderer.primary_aov(p, 32)[0]
         img_bvh = renderer.render(q)
-        with pytest.raises(capi.RacerCudaError):      # the BVH modes have no scene-specialised kernel
-            renderer.render(harness.make_params(w, h, 8, 20, seed=6, specialize=1))
+        # the BVH paths' specialised kernel (kinds of primitive / material / wrapper compiled in or out)
+        img_bvh_spec = renderer.render(harness.make_params(w, h, 8, 20, seed=6, specialize=1))
+        assert renderer.stats().specialized == 1
     finally:
         del os.environ["RC_SCENE_MODE"]
+    err = np.abs(img_bvh_spec - img_bvh).max(axis=2)
+    assert np.median(err) < 1e-6 and float((err > 2e-3).mean()) < 0.01
     assert (ids_lin != ids_bvh).mean() < 1e-3          # exact ties only: the two paths order primitives differently
     for name, img in (("precompiled", img_lin), ("specialised", img_spec)):
         err = np.abs(img - img_bvh).max(axis=2)

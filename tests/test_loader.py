@@ -120,6 +120,51 @@ def test_bvh_is_a_valid_preorder_tree(name):
     assert seen == list(range(n))       # primitives are stored in DFS leaf order
 
 
+def _sah_cost(nodes):
+    """Expected boxes visited by a random ray: sum over nodes of area(node) / area(root)."""
+    root = harness._area(list(nodes[0].bmin), list(nodes[0].bmax))
+    return sum(harness._area(list(nd.bmin), list(nd.bmax)) for nd in nodes) / root
+
+
+def test_large_scenes_get_a_sah_tree():
+    """Scenes of SAH_MIN_OBJECTS objects or more (the Random scene: 484 spheres) are split by the surface-area
+    heuristic instead of the reference's median (bvh_node.rs:31-82): still a valid pre-order tree with one
+    object per leaf in DFS order, the ground sphere isolated directly under the root, and a lower expected
+    number of box visits than the median tree over the same objects."""
+    fs = harness.random_scene(seed=0)
+    nodes, n = fs.nodes, fs.c.n_prims
+    assert n >= harness.SAH_MIN_OBJECTS and len(nodes) == 2 * n - 1
+    seen = []
+
+    def walk(i):
+        nd = nodes[i]
+        if nd.left < 0:
+            seen.append(~nd.left)
+            box = fs.np["prim_aabb"][~nd.left]
+            assert nd.right == 1 and list(nd.bmin) == list(box[:3]) and list(nd.bmax) == list(box[3:])
+        else:
+            assert nd.left == i + 1 and nd.right > nd.left
+            walk(nd.left)
+            walk(nd.right)
+            for a in range(3):
+                assert nd.bmin[a] == min(nodes[nd.left].bmin[a], nodes[nd.right].bmin[a])
+                assert nd.bmax[a] == max(nodes[nd.left].bmax[a], nodes[nd.right].bmax[a])
+    walk(0)
+    assert seen == list(range(n))
+    ground = nodes[nodes[0].left] if nodes[nodes[0].left].left < 0 else nodes[nodes[0].right]
+    assert ground.left < 0 and ground.bmax[0] - ground.bmin[0] == 2000.0      # the radius-1000 sphere
+    # the median tree over the same objects
+    saved = harness.SAH_MIN_OBJECTS
+    try:
+        harness.SAH_MIN_OBJECTS = 1 << 30
+        median = harness.random_scene(seed=0)
+    finally:
+        harness.SAH_MIN_OBJECTS = saved
+    assert _sah_cost(nodes) < 0.75 * _sah_cost(median.nodes)
+    # small scenes keep the median split, and with it the primitive order the goldens were made with
+    assert load("clown").c.n_prims < harness.SAH_MIN_OBJECTS
+
+
 def test_rect_and_sphere_boxes():
     fs = load("cornell_box")
     i = [k for k in range(6) if fs.object_keys[(int(fs.np["prim_id"][k]) >> 3) - 1] == "light"][0]
