@@ -115,6 +115,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         o << "#define RT_HAS_LENS " << (kp.lens_enabled ? 1 : 0) << "\n";
         o << "#define RT_HAS_MOTION " << (kp.has_motion ? 1 : 0) << "\n";
         if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
+        else if (mode == RT_MODE_GLOBAL_BVH) o << "#define RT_MIN_BLOCKS RT_MIN_BLOCKS_GLOBAL_BVH\n";   // see rt_kernels.cuh
         o << "#include \"rt_scene.cuh\"\n";
         o << "RT_D int spec_closest_hit(const RayT<float>&, int, float&) { return -1; }   // constant-table scenes only\n";
         o << "#define RT_SPECIALIZED 1\n";

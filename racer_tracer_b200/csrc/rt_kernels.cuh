@@ -298,6 +298,11 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 6
 #endif
+// The global-memory BVH walk waits on loads, not on registers: 9 CTAs of 56 registers (a few spilled
+// values) run the Random scene 7 % faster than 6 CTAs of 80 (measured, tools/bvh_trees.py).
+#ifndef RT_MIN_BLOCKS_GLOBAL_BVH
+#define RT_MIN_BLOCKS_GLOBAL_BVH 9
+#endif
 // Lanes whose path ended wait until at least this many lanes of the warp want a new sample
 // (or nobody is alive): regeneration is the one part of the loop that runs at low lane
 // occupancy, so it is batched.  1 = regenerate immediately.
@@ -482,7 +487,7 @@ __global__ void reduce_slices_kernel(const __grid_constant__ KParams P, float* _
 }
 
 template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
-__global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)
+__global__ void __launch_bounds__(RT_BLOCK, MODE == RT_MODE_GLOBAL_BVH ? RT_MIN_BLOCKS_GLOBAL_BVH : RT_MIN_BLOCKS)
 megakernel_render(const __grid_constant__ KParams P, float* __restrict__ accum) {
     extern __shared__ __align__(16) unsigned char smem[];
     megakernel_body<MODE, SAMPLER, ROUNDS, TEX>(P, accum, smem);
