@@ -373,7 +373,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         const bool spec_mode_ok = ctx->mode == RT_MODE_CONST_LINEAR ||
                                   ((ctx->mode == RT_MODE_SMEM_BVH || ctx->mode == RT_MODE_GLOBAL_BVH) && ctx->smem_bytes <= 48 * 1024 &&
                                    std::getenv("RC_NO_BVH_SPEC") == nullptr);
-        if (p->specialize && spec_mode_ok && p->sampler == RC_SAMPLER_DIRECT && rounds == 10) {
+        if (p->specialize && spec_mode_ok && p->sampler == RC_SAMPLER_DIRECT && rounds == 10 && !p->fixed_jitter) {
             std::string err;
             if (!spec_load_api((const void*)&rc_abi_version)) err = spec_api().err;
             else {
@@ -383,7 +383,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
             }
             if (!spec && p->specialize == 1) return fail(RC_ERR_STATE, "scene specialisation failed: " + err);
         } else if (p->specialize == 1) {
-            return fail(RC_ERR_INVALID, "specialize = 1 needs the megakernel, the direct sampler and 10 Philox rounds");
+            return fail(RC_ERR_INVALID, "specialize = 1 needs the megakernel, the direct sampler, 10 Philox rounds and no fixed jitter");
         }
         const int s0 = kp.s_begin, s1 = kp.s_end;
         const int step = cancel ? 32 : (s1 - s0);

@@ -120,6 +120,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         o << "RT_D int spec_closest_hit(const RayT<float>&, int, float&) { return -1; }   // constant-table scenes only\n";
         o << "#define RT_SPECIALIZED 1\n";
         o << "#define RT_SPEC_MATS " << mats_mask << "\n";
+        o << "#define RT_FIXED_JITTER(P) 0\n";
         o << "#include \"rt_kernels.cuh\"\n";
         o << "extern \"C\" __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)\n"
              "spec_megakernel(const __grid_constant__ KParams P, float* __restrict__ accum) {\n"
@@ -326,6 +327,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     o << "#define RT_SPECIALIZED 1\n";
     o << "#define RT_SPEC_MATS " << mats_mask << "\n";
     o << "#define RT_HAS_MOTION " << (any_motion ? 1 : 0) << "\n";
+    o << "#define RT_FIXED_JITTER(P) 0\n";   // renders with fixed jitter (parity checks) use the precompiled kernels
     o << "#include \"rt_kernels.cuh\"\n";
     o << "extern \"C\" __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)\n"
          "spec_megakernel(const __grid_constant__ KParams P, float* __restrict__ accum) {\n"

@@ -75,6 +75,9 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
 #ifndef RT_HAS_MOTION
 #define RT_HAS_MOTION 1     /* a scene-specialised kernel sets 0 when no sphere moves */
 #endif
+#ifndef RT_FIXED_JITTER
+#define RT_FIXED_JITTER(P) ((P).fixed_jitter)   /* a scene-specialised kernel is never launched with fixed jitter: 0 there */
+#endif
 #ifndef RT_HAS_LENS
 #define RT_HAS_LENS 1       /* ... and 0 when the camera it was compiled for is a pinhole (lens_radius == 0) */
 #endif
@@ -105,7 +108,7 @@ RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
     c.px = px; c.py = py;
     c.pixel = (uint32_t)(py * P.width + px);
     float ujit = 0.5f;
-    if (!P.fixed_jitter) ujit = u24(philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.ks).x);
+    if (!RT_FIXED_JITTER(P)) ujit = u24(philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.ks).x);
     float u = ((float)(px * P.px_scale_x) + ujit) / P.wm1;  // once per pixel, cpu.rs:35-36 (cpu_scaled.rs:55-56)
     // cam.upper_left_corner holds (upper_left_corner - origin), formed in f64 on the host
     c.dir0 = P.cam.upper_left_corner + u * P.cam.horizontal;
@@ -114,17 +117,18 @@ RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
 
 // Primary ray of one sample.  `w` = the sample's start block (x -> v jitter).
 template <int SAMPLER, int ROUNDS>
-RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit, vec3f& o, vec3f& d, float& time) {
-    float v = ((float)(c.py * P.px_scale_y) + vjit) * P.inv_hm1;  // cpu.rs:39-40 (cpu_scaled.rs:59-60)
+RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit16, vec3f& o, vec3f& d, float& time) {
+    // vjit16 = the v jitter times 65536 (an integer: the scaling is exact, so the fused form rounds like add(py, jitter))
+    float v = fmaf(vjit16, 1.0f / 65536.0f, (float)(c.py * P.px_scale_y)) * P.inv_hm1;  // cpu.rs:39-40 (cpu_scaled.rs:59-60)
     d = c.dir0 - v * P.cam.vertical;
     o = P.cam.origin;
     time = P.cam.time_a;
-    if (RT_HAS_MOTION && P.has_motion && !P.fixed_jitter) {
+    if (RT_HAS_MOTION && P.has_motion && !RT_FIXED_JITTER(P)) {
         // camera.rs:335: random_double_range(time_a, time_b); the draw is the spare 16 bits of LENS block 0
         const uint2 w = philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(sample, 0u, RT_TAG_LENS), P.ks);
         time = fmaf(P.cam.time_b - P.cam.time_a, u16lo(w), P.cam.time_a);
     }
-    if (RT_HAS_LENS && P.lens_enabled && !P.fixed_jitter) {  // camera.rs:327-328; skipped when lens_radius == 0 (offset = 0)
+    if (RT_HAS_LENS && P.lens_enabled && !RT_FIXED_JITTER(P)) {  // camera.rs:327-328; skipped when lens_radius == 0 (offset = 0)
         float dx, dy;
         if (SAMPLER == 1) {  // random_in_unit_disk, util.rs:25-39
             for (uint32_t j = 1;; ++j) {
@@ -379,7 +383,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                     vec3f bg;
                     if (__float_as_int(P.bg_a.w) == 0) {   // Sky: depends on the sample's direction
                         const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1((uint32_t)s, 0u, RT_TAG_PATH), P.ks);
-                        const float vjit = P.fixed_jitter ? 0.5f : u16lo(rnd);
+                        const float vjit = RT_FIXED_JITTER(P) ? 32768.0f : u16lo_int(rnd);
                         camera_ray<SAMPLER, ROUNDS>(P, pc, (uint32_t)s, vjit, o, d, time);
                         bg = background_color(P, d);
                     } else bg = mk3(P.bg_a.x, P.bg_a.y, P.bg_a.z);
@@ -413,7 +417,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             // ---- the segment's random block: drawn here, by all lanes together ----
             const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, ctr1, P.ks);   // == rt_ctr1(R.sample, seg, RT_TAG_PATH)
             if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337
-                const float vjit = P.fixed_jitter ? 0.5f : u16lo(rnd);
+                const float vjit = RT_FIXED_JITTER(P) ? 32768.0f : u16lo_int(rnd);
                 camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d, time);
             }
             RayT<float> r = make_ray(o, d, time);
@@ -513,7 +517,7 @@ primary_aov_kernel(const __grid_constant__ KParams P, uint32_t* __restrict__ id,
     PixelCtx pc = pixel_setup<10>(P, px, py);
     vec3f o, d;
     float time;
-    camera_ray<0, 10>(P, pc, 0u, 0.5f, o, d, time);   // fixed jitter: time = time_a
+    camera_ray<0, 10>(P, pc, 0u, 32768.0f, o, d, time);   // fixed jitter: time = time_a
     RayT<float> r = make_ray(o, d, time);
     float t;
     int prim;

@@ -137,6 +137,8 @@ RT_HD void u21x3(uint2 w, float& a, float& b, float& c) {
 // 16-bit uniform from the spare low byte of each word of a PATH / LENS block (v jitter, ray time).
 // fp32 cannot hold more of the jitter anyway: (float)py + jitter keeps 2^-13 at py >= 1024.
 RT_HD float u16lo(uint2 w) { return (float)(((w.x & 0xFFu) << 8) | (w.y & 0xFFu)) * (1.0f / 65536.0f); }
+// the same 16 bits as a float integer in [0, 65536): one byte permute + one conversion
+RT_D float u16lo_int(uint2 w) { return (float)(unsigned short)__byte_perm(w.y, w.x, 0x0040); }
 // three 16-bit uniforms from the upper 24 bits of each word of a PATH block (metal fuzz, direct)
 RT_HD void u16x3(uint2 w, float& a, float& b, float& c) {
     a = (float)(w.x >> 16) * (1.0f / 65536.0f);
