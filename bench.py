@@ -403,7 +403,7 @@ def main():
             line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": fp32_tflops, "unit": "TFLOP/s",
                                 "frac": achieved / fp32_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the megakernel launch, ncu --set full "
-                                                  "(profiles/r01_megakernel_v19_specialised_ncu.md): the accumulation buffer, once",
+                                                  "(profiles/r01_megakernel_v21_specialised_ncu.md): the accumulation buffer, once",
                                 "peak_source": "FFMA micro-benchmark in this run (rc_fp32_peak), per GPU",
                                 "flops_per_sample": A_used, "lane_ginstr_per_s_peak": lane_ginstr,
                                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_kind,
