@@ -899,7 +899,9 @@ int rc_set_camera(rc_ctx* ctx, const rc_camera* c) {
     f.origin = v3f(c->origin); f.upper_left_corner = v3f(rel); f.right = v3f(c->right); f.up = v3f(c->up);
     f.horizontal = v3f(c->horizontal); f.vertical = v3f(c->vertical);
     f.lens_radius = (float)c->lens_radius; f.time_a = (float)c->time_a; f.time_b = (float)c->time_b;
-    if (ctx->kp.lens_enabled != (c->lens_radius != 0.0 ? 1 : 0)) ctx->spec_source.clear();   // the specialised kernel knows whether there is a lens
+    // the specialised source depends on the camera (lens or pinhole; which pairs of opposite walls enclose it):
+    // regenerate it — the text is the cache key, so an unchanged text costs no recompilation
+    ctx->spec_source.clear();
     ctx->kp.lens_enabled = c->lens_radius != 0.0;
     DevCamera<double>& g = ctx->aov.cam;
     g.origin = v3d(c->origin); g.upper_left_corner = v3d(c->upper_left_corner); g.right = v3d(c->right); g.up = v3d(c->up);
@@ -1337,6 +1339,12 @@ int64_t rc_spec_source(const rc_scene* scene, char* out, int64_t capacity) {
     HostTables t;
     build_tables(scene, t);
     if (t.mode == RT_MODE_SMEM_LINEAR) return fail(RC_ERR_INVALID, "a node-less scene beyond the constant table has no specialised kernel (it gets a BVH at upload)");
+    // host-only tooling: no camera has been set here, RC_SPEC_CAMERA="x,y,z" supplies the pinhole position
+    // the generator checks wall pairs against (tools/spec_sass.py passes the scene's camera)
+    if (const char* e = std::getenv("RC_SPEC_CAMERA")) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (std::sscanf(e, "%f,%f,%f", &x, &y, &z) == 3) { t.kp.cam.origin.x = x; t.kp.cam.origin.y = y; t.kp.cam.origin.z = z; }
+    }
     std::string src = spec_generate(t.kp, t.has_textures, t.mats_mask, t.mode, t.prims_mask, !t.instances.empty());
     if (out && capacity > 0) {
         size_t n = src.size() < (size_t)capacity - 1 ? src.size() : (size_t)capacity - 1;

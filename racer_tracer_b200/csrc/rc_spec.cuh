@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -188,6 +189,8 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         rel[key] = name;
         return name;
     };
+    // slab pairs (below) need every ray origin inside the slab: rectangles only, nothing instanced, a pinhole
+    const bool slab_scene_ok = kp.n_cobj == 0 && !kp.lens_enabled && std::getenv("RC_SPEC_NO_SLAB") == nullptr;
     for (int g = 0; g < 3; ++g) {
         const int begin = kp.lin_end[g], end = kp.lin_end[g + 1];
         if (end <= begin) continue;
@@ -200,13 +203,54 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         o << "    {\n";
         const bool chain = std::getenv("RC_SPEC_SELECT") == nullptr;   // predicate chain (default) or candidate + select reduction
         const bool packed = chain && std::getenv("RC_SPEC_SCALAR") == nullptr;   // FFMA2 pairs (default) or scalar arithmetic
-        for (int i = begin; i < end; ++i) {
+        // Slab pair: two rectangles of this group with the same bounds (opposite walls) between which every ray of
+        // the scene starts — all geometry and the pinhole lie inside the slab.  Exactly one of the two planes is
+        // then in front of a ray, max(t_i, t_j), and ONE rectangle test serves both walls.
+        int s0 = -1, s1 = -1;
+        if (packed && fidx && slab_scene_ok) {
+            const int n_axis = 2 - g;   // plane axis of the group: xy -> z, xz -> y, yz -> x
+            for (int i = begin; i < end && s0 < 0; ++i)
+                for (int j = i + 1; j < end && s0 < 0; ++j) {
+                    const float4 c = kp.crect_bounds[g][i - begin], c2 = kp.crect_bounds[g][j - begin];
+                    if (c.x != c2.x || c.y != c2.y || c.z != c2.z || c.w != c2.w) continue;
+                    const float k_lo = std::fmin(kp.cprims[i].b.x, kp.cprims[j].b.x), k_hi = std::fmax(kp.cprims[i].b.x, kp.cprims[j].b.x);
+                    if (!(k_lo < k_hi)) continue;
+                    const float cam_n = n_axis == 0 ? kp.cam.origin.x : (n_axis == 1 ? kp.cam.origin.y : kp.cam.origin.z);
+                    bool inside = cam_n > k_lo && cam_n < k_hi;
+                    for (int gg = 0; gg < 3 && inside; ++gg)
+                        for (int r = kp.lin_end[gg]; r < kp.lin_end[gg + 1] && inside; ++r) {
+                            const float4 b = kp.crect_bounds[gg][r - kp.lin_end[gg]];
+                            const int rn = 2 - gg, ra = gg == 2 ? 1 : 0, rb = gg == 0 ? 1 : 2;   // plane axis, in-plane axes
+                            float lo, hi;
+                            if (n_axis == rn) lo = hi = kp.cprims[r].b.x;
+                            else if (n_axis == ra) { lo = b.x - b.y; hi = b.x + b.y; }
+                            else { (void)rb; lo = b.z - b.w; hi = b.z + b.w; }
+                            inside = lo >= k_lo && hi <= k_hi;
+                        }
+                    if (inside) { s0 = kp.cprims[i].b.x < kp.cprims[j].b.x ? i : j; s1 = s0 == i ? j : i; }
+                }
+        }
+        std::vector<int> rest;
+        for (int i = begin; i < end; ++i)
+            if (i != s0 && i != s1) rest.push_back(i);
+        if (s0 >= 0) {
+            const DevPrim& p = kp.cprims[s0];
+            const DevPrim& q = kp.cprims[s1];
+            o << "        float t" << s0 << ", t" << s1 << ", xa" << s0 << ", xb" << s0 << ";\n";
+            o << "        pair_t(" << spec_float(p.b.x) << ", " << spec_float(q.b.x) << ", " << on[g] << ", " << in[g] << ", t" << s0 << ", t" << s1 << ");\n";
+            o << "        const float ts" << s0 << " = fmaxf(t" << s0 << ", t" << s1 << ");   // slab pair " << s0 << " / " << s1 << "\n";
+            o << "        fma2_bcast(ts" << s0 << ", " << da[g] << ", " << db[g] << ", " << va[s0 - begin] << ", " << vb[s0 - begin] << ", xa" << s0 << ", xb" << s0 << ");\n";
+            o << "        const float fi" << s0 << " = fmaf(t" << s1 << " > t" << s0 << " ? 1.0f : 0.0f, " << spec_float((float)(s1 - s0)) << ", "
+              << spec_float((float)s0) << ");\n";
+        }
+        for (size_t u = 0; u < rest.size(); ++u) {
+            const int i = rest[u];
             const DevPrim& p = kp.cprims[i];
             const float4 c = kp.crect_bounds[g][i - begin];
-            if (packed && i + 1 < end) {   // two rectangles of this axis group per packed instruction
-                const DevPrim& q = kp.cprims[i + 1];
-                const float4 c2 = kp.crect_bounds[g][i + 1 - begin];
-                const int j = i + 1;
+            if (packed && u + 1 < rest.size()) {   // two rectangles of this axis group per packed instruction
+                const int j = rest[u + 1];
+                const DevPrim& q = kp.cprims[j];
+                const float4 c2 = kp.crect_bounds[g][j - begin];
                 o << "        float t" << i << ", t" << j << ", xa" << i << ", xa" << j << ", xb" << i << ", xb" << j << ";\n";
                 o << "        pair_t(" << spec_float(p.b.x) << ", " << spec_float(q.b.x) << ", " << on[g] << ", " << in[g] << ", t" << i << ", t" << j << ");\n";
                 auto centres = [&](const char* axis, float ca1, float ca2, const std::string& v1, const std::string& v2, const char* tag) {
@@ -220,10 +264,15 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
                 const auto pb = centres(ob[g], c.z, c2.z, vb[i - begin], vb[j - begin], "pb");
                 o << "        pair_x(t" << i << ", t" << j << ", " << da[g] << ", " << pa.first << ", " << pa.second << ", xa" << i << ", xa" << j << ");\n";
                 o << "        pair_x(t" << i << ", t" << j << ", " << db[g] << ", " << pb.first << ", " << pb.second << ", xb" << i << ", xb" << j << ");\n";
-                ++i;
+                ++u;
                 continue;
             }
             o << "        const float t" << i << " = (" << spec_float(p.b.x) << " - " << on[g] << ") * " << in[g] << ";\n";
+            if (packed) {   // one rectangle: its two in-plane coordinates are the two lanes
+                o << "        float xa" << i << ", xb" << i << ";\n";
+                o << "        fma2_bcast(t" << i << ", " << da[g] << ", " << db[g] << ", " << va[i - begin] << ", " << vb[i - begin] << ", xa" << i << ", xb" << i << ");\n";
+                continue;
+            }
             if (chain) {
                 o << "        const float xa" << i << " = fmaf(t" << i << ", " << da[g] << ", " << va[i - begin] << "), xb" << i << " = fmaf(t" << i
                   << ", " << db[g] << ", " << vb[i - begin] << ");\n";
@@ -232,7 +281,12 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
             o << "        const float c" << i << " = rect_candidate(t" << i << ", fmaf(t" << i << ", " << da[g] << ", " << va[i - begin]
               << "), fmaf(t" << i << ", " << db[g] << ", " << vb[i - begin] << "), " << spec_float(c.y) << ", " << spec_float(c.w) << ");\n";
         }
-        for (int i = begin; i < end; ++i) {
+        if (s0 >= 0) {
+            const float4 c = kp.crect_bounds[g][s0 - begin];
+            o << "        rect_closest_fma(ts" << s0 << ", xa" << s0 << ", xb" << s0 << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", fi" << s0
+              << ", best_t, bestf);\n";
+        }
+        for (int i : rest) {
             const float4 c = kp.crect_bounds[g][i - begin];
             if (chain && fidx)
                 o << "        rect_closest_fma(t" << i << ", xa" << i << ", xb" << i << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", "

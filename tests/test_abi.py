@@ -163,3 +163,38 @@ def test_specialised_source_of_every_scene_kind_compiles(cuda_lib, cfg, tmp_path
     src = buf.value.decode()
     assert needle in src
     _compile_like_the_library(src, tmp_path)
+
+
+def _spec_source(cuda_lib, job, camera=None):
+    if camera is not None:
+        os.environ["RC_SPEC_CAMERA"] = ",".join(repr(float(v)) for v in camera)
+    try:
+        n = cuda_lib.rc_spec_source(job.scene.ptr, None, 0)
+        assert n > 0, cuda_lib.rc_last_error()
+        buf = C.create_string_buffer(n + 1)
+        assert cuda_lib.rc_spec_source(job.scene.ptr, buf, n + 1) == n
+    finally:
+        os.environ.pop("RC_SPEC_CAMERA", None)
+    return buf.value.decode()
+
+
+def test_opposite_walls_become_one_test_only_when_every_ray_starts_between_them(cuda_lib, cfg, tmp_path):
+    """Slab pairs of the specialised closest hit: two rectangles with the same bounds on parallel planes are
+    tested as max(t_i, t_j) — one rectangle test for both — iff all geometry and the pinhole lie between the
+    planes.  Cornell from its own camera: the side walls and floor / ceiling; from a camera left of the red wall
+    only floor / ceiling; with a lens, or in a scene with spheres or instanced boxes, none."""
+    from conftest import scene_path
+    job = harness.prepare_job(scene_path("cornell_box"), cfg, 64, 64)
+    inside = _spec_source(cuda_lib, job, camera=job.camera.origin)
+    assert inside.count("// slab pair") == 2 and inside.count("rect_closest_fma(") == 4
+    _compile_like_the_library(inside, tmp_path)
+    left_of_the_box = _spec_source(cuda_lib, job, camera=(-100.0, 278.0, -800.0))
+    assert left_of_the_box.count("// slab pair") == 1 and left_of_the_box.count("rect_closest_fma(") == 5
+    assert "pair_t(0.0f, 555.0f, r.o.y" in left_of_the_box and "fmaxf(t1, t2)" in left_of_the_box
+    above = _spec_source(cuda_lib, job, camera=(278.0, 900.0, 278.0))
+    assert above.count("// slab pair") == 1 and "pair_t(0.0f, 555.0f, r.o.x" in above
+    no_camera = _spec_source(cuda_lib, job)            # origin (0, 0, 0): on the walls, not between them
+    assert no_camera.count("// slab pair") == 0 and no_camera.count("rect_closest_fma(") == 6
+    for other in ("sandbox_boxes", "emissive"):
+        j = harness.prepare_job(scene_path(other), cfg, 64, 64)
+        assert "// slab pair" not in _spec_source(cuda_lib, j, camera=j.camera.origin)

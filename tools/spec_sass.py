@@ -26,6 +26,7 @@ args = ap.parse_args()
 lib = capi.load()
 cfg = harness.load_config(os.path.join(ROOT, "tests", "golden", "config.yml"))
 job = harness.prepare_job(os.path.join(ROOT, "tests", "golden", "scenes", args.scene + ".yml"), cfg, 64, 64)
+os.environ["RC_SPEC_CAMERA"] = ",".join(repr(float(v)) for v in job.camera.origin)   # rc_spec_source has no camera of its own
 n = lib.rc_spec_source(job.scene.ptr, None, 0)
 buf = C.create_string_buffer(n + 1)
 lib.rc_spec_source(job.scene.ptr, buf, n + 1)
