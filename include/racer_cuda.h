@@ -213,9 +213,13 @@ typedef struct rc_params {
     int32_t  rng_rounds;      /* Philox rounds; 0 = 10                      */
     int32_t  specialize;      /* 0: precompiled kernels.  1: compile the scene
                                  into the megakernel at run time (NVRTC, cached
-                                 per scene; small scenes only) and fail if that
-                                 is impossible.  2: the same, but fall back to
-                                 the precompiled kernel                     */
+                                 per scene: primitives as immediates for scenes
+                                 on the constant-table path, the kinds of
+                                 primitive / material / wrapper present for BVH
+                                 scenes) and fail if that is impossible.  2: the
+                                 same, but fall back to the precompiled kernel.
+                                 Needs the megakernel, the direct sampler, 10
+                                 Philox rounds and fixed_jitter = 0          */
 } rc_params;
 
 typedef struct rc_tone_map {
