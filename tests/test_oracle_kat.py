@@ -515,3 +515,24 @@ def test_moving_sphere_and_random_scene(cfg):
     p = harness.make_params(64, 48, 4, 5, seed=1)
     img = O.render(job, p)
     assert np.isfinite(img).all() and img.std() > 0.05
+
+
+def test_the_tree_does_not_change_the_image(oracle, cfg):
+    """Random scene under the three structures a host may hand over — the SAH tree the hosts build for large
+    scenes, the reference's median split (bvh_node.rs:31-82) and no tree at all (the linear list,
+    shared_scene.rs:37-53): the closest hit of every ray, hence every primary id and every pixel, is the same."""
+    sah = harness.prepare_job("random", cfg, 53, 31, seed=0)
+    saved = harness.SAH_MIN_OBJECTS
+    try:
+        harness.SAH_MIN_OBJECTS = 1 << 30
+        median = harness.prepare_job("random", cfg, 53, 31, seed=0)
+    finally:
+        harness.SAH_MIN_OBJECTS = saved
+    linear = harness.prepare_job("random", cfg, 53, 31, seed=0, use_bvh=False)
+    assert [n.left for n in sah.scene.nodes] != [n.left for n in median.scene.nodes] and linear.scene.c.n_nodes == 0
+    p = harness.make_params(53, 31, 2, 20, seed=8)
+    ids = oracle.primary_aov(sah, p)[0]
+    img = oracle.render(sah, p)
+    for other in (median, linear):
+        assert np.array_equal(oracle.primary_aov(other, p)[0], ids)
+        assert np.array_equal(oracle.render(other, p), img)
