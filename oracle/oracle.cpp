@@ -1,7 +1,9 @@
 // oracle.cpp — CPU parity oracle: an f64 restatement of racer-tracer's render
 // hot path.  TEST INFRASTRUCTURE ONLY (see oracle.h): never linked, loaded or
-// called by the product.  PARITY UNPINNED by the reference (it has no render
-// tests); pinned by tests/test_oracle_kat.py instead.
+// called by the product.  PARITY UNPINNED at the bit level by the reference (it
+// has no render tests and cannot be built here); pinned by hand-derived known
+// answers (tests/test_oracle_kat.py) and, statistically, by the reference's own
+// published renders (tests/test_reference_renders.py).
 //
 // Every function cites the reference lines it follows, relative to
 // /root/reference/racer-tracer/.  The code is a restatement over the flat

@@ -2,9 +2,11 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs import this module (see oracle/oracle.h).  The product
-package never does.  Parity is UNPINNED by the reference (no render tests
-exist there); tests/test_oracle_kat.py pins the oracle with hand-derived
-known-answer vectors instead.
+package never does.  Parity is UNPINNED at the bit level by the reference (no
+render tests exist there, and it cannot be built here); tests/test_oracle_kat.py
+pins the oracle with hand-derived known-answer vectors, and
+tests/test_reference_renders.py statistically with the reference's published
+renders.
 """
 from __future__ import annotations
 
