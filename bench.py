@@ -8,16 +8,22 @@ A "step" is one full render of the workload: every pixel x sample of
 cornell_box.yml at 1920x1080, 1024 spp, max_depth 20 (BASELINE configs[3], the
 configuration the metric is quoted on; it fits one GPU).  With N > 1 (one
 process per GPU under torchrun) the image is split into interleaved 16x8 tiles
-(tile k -> rank k mod N), every rank renders all samples of its tiles and rank
-0 receives the disjoint tiles with one NCCL reduce of the accumulation buffer
-(SUM over disjoint supports = gather); total work is fixed => "strong" scaling.
+(tile k -> rank k mod N); every rank renders all samples of its tiles and its
+render kernel STORES the finished pixels straight into rank 0's frame buffer
+over NVLink (a CUDA-IPC mapping): the gather happens inside the kernel, what is
+left of the exchange step is a per-rank "done" word rank 0's stream waits for.
+The sample-split workload (clown) sums partial buffers with an NCCL reduce
+instead.  Total work is fixed => "strong" scaling.
 
 `value` is timed with CUDA events on the launching stream with the scene and
 camera already resident on the device; `e2e` runs the same step through the
 public host call (scene + camera upload, render, download of the gamma'd f64
-image into host memory).  The roofline is the FP32 issue roofline of SURVEY
-§8(d): algorithmic flops per sample (cost table x oracle counters) x samples/s
-over the FFMA micro-benchmark measured in this run.
+image into host memory); `e2e_cancel` is the same call the way the reference's
+host makes it, with a cancel flag that is never raised (interactive.rs:236-251).
+The roofline is the FP32 issue roofline of SURVEY §8(d): algorithmic flops per
+sample (cost table x oracle counters) x samples/s over the FFMA micro-benchmark
+measured in this run; `roofline.ncu` carries the counters of the committed ncu
+capture of the same kernel and configuration (profiles/r02_ncu_bench_kernel.json).
 """
 from __future__ import annotations
 
@@ -47,9 +53,15 @@ WORKLOADS = {
 }
 
 
-# HBM traffic of the dominant kernel per launch, from the committed ncu capture (bytes); the megakernel reads the
-# accumulation buffer once and its stores stay in L2 until evicted, independent of spp
-NCU_DRAM_BYTES_PER_LAUNCH = {"cornell_box_1080p_1024spp": 24906496 + 768}
+def ncu_capture(workload):
+    """Counters of the committed `ncu --set full` capture of the dominant kernel at this workload
+    (profiles/r02_ncu_bench_kernel.json, written by tools/ncu_bench_json.py from the .ncu-rep): HBM bytes per
+    launch, issue-slot and pipe utilisation, active lanes.  None when no capture of that workload is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_bench_kernel.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(workload)
 
 
 def scene_file(scene):
@@ -236,35 +248,26 @@ def main():
 
     launches = [0]
 
-    # Tile split over several processes: rank 0 owns the frame buffer (two of them, alternating, so that a
-    # rank already tracing the next step never stores into the buffer rank 0 is still reading) and every rank
-    # maps it (CUDA IPC); the render kernel of every rank STORES its tiles into it over NVLink as they finish.
-    # The only exchange step left is a one-element all-reduce that orders rank 0's stream after the others.
-    shared = None
-    if world > 1 and split == capi.RC_SPLIT_TILES and variant == capi.RC_VARIANT_MEGAKERNEL and not os.environ.get("RC_BENCH_NCCL_GATHER"):
-        shared = []
-        for _ in range(2):
-            if rank == 0:
-                ptr, handle = r.shared_alloc(n * 4)
-                hbuf = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
-            else:
-                hbuf = torch.empty(64, dtype=torch.uint8, device="cuda")
+    # Tile split (every N, also 1): the whole exchange lives behind the ABI — rc_frame_create / rc_frame_open /
+    # rc_render_frame.  Rank 0 owns the frame (two images, alternating) and every rank maps it (CUDA IPC); the render
+    # kernel of every rank STORES sqrt(sum / spp) for its tiles into it over NVLink as they finish, then publishes a
+    # progress word that rank 0's stream waits for.  bench.py only carries the 64-byte handle to the other ranks.
+    frame = None
+    if split == capi.RC_SPLIT_TILES and variant == capi.RC_VARIANT_MEGAKERNEL and not os.environ.get("RC_BENCH_NCCL_GATHER"):
+        if rank == 0:
+            frame, handle = r.frame_create(w, h, world)
+            hbuf = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        else:
+            hbuf = torch.empty(64, dtype=torch.uint8, device="cuda")
+        if world > 1:
             dist.broadcast(hbuf, 0)
-            if rank != 0:
-                ptr = r.shared_open(bytes(hbuf.cpu().tolist()))
-            shared.append(ptr)
-    join = torch.zeros(1, dtype=torch.float32, device="cuda")
-    step_no = [0]
+        if rank != 0:
+            frame = r.frame_open(bytes(hbuf.cpu().tolist()), w, h, rank, world)
 
     def step(p=None):
         p = params if p is None else p
-        if shared is not None:
-            frame = shared[step_no[0] & 1]
-            step_no[0] += 1
-            r.render_tiles_into(p, frame)     # enqueues only: the library does not drain the stream
-            dist.all_reduce(join)             # stream-ordered join; the pixels already travelled inside the kernel
-            if rank == 0:
-                r.finalize(frame, w, h, spp, rgb.data_ptr())
+        if frame is not None:
+            r.render_frame(p, frame)          # enqueues only: kernels and stream-ordered waits, no host sync, no collective
             return
         accum.zero_()
         r.render_accumulate(p, accum.data_ptr())
@@ -277,7 +280,9 @@ def main():
     def launches_per_step():
         """Our kernels per step: the render call's own launches (read back after a step), + the zero-fill of the
         accumulation buffer when there is one, + finalize on rank 0."""
-        return int(r.stats().kernel_launches) + (0 if shared is not None else 1) + (1 if rank == 0 else 0)
+        if frame is not None:
+            return int(r.stats().kernel_launches)
+        return int(r.stats().kernel_launches) + 1 + (1 if rank == 0 else 0)
 
     def barrier():
         if world > 1:
@@ -330,26 +335,36 @@ def main():
     host32 = torch.empty(n, dtype=torch.float32, pin_memory=True)
     e2e_params = harness.make_params(w, h, spp, depth, seed=0, variant=variant, sampler=sampler, split=split,
                                      rank=rank, world=world, rng_rounds=args.rng_rounds, specialize=spec)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r.upload(job)                       # host -> device: scene tables + camera
-        if args.lbvh:
-            r.build_lbvh()
-        if world == 1:
-            out = r.render(e2e_params, out=host_out)   # render + device -> host of the gamma'd f64 image
-        else:
-            step(e2e_params)
-            if rank == 0:
-                host32.copy_(rgb, non_blocking=True)
-        torch.cuda.synchronize()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = total_samples / float(te.item())
-    d2h = n * (8 if world == 1 else 4)
+
+    def e2e_pass(cancel_flag=None):
+        """The step through the host-facing call, host buffers on both sides: scene tables + camera host -> device,
+        render, the gamma'd f64 image device -> host on rank 0.  Same call, unit and dtype at every N."""
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r.upload(job)                       # host -> device: scene tables + camera
+            if args.lbvh:
+                r.build_lbvh()
+            if frame is not None:
+                r.render_frame(e2e_params, frame, out=host_out if rank == 0 else None, cancel=cancel_flag)
+            elif world == 1:
+                r.render(e2e_params, out=host_out, cancel=cancel_flag)
+            else:
+                step(e2e_params)
+                if rank == 0:
+                    host32.copy_(rgb, non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return total_samples / float(te.item())
+
+    e2e_value = e2e_pass()
+    # the way the reference's host calls a full render: always with a cancel event (interactive.rs:236-251), here never raised
+    e2e_cancel_value = e2e_pass(C.c_int32(0)) if (frame is not None or world == 1) else None
+    d2h = n * (8 if (frame is not None or world == 1) else 4)
 
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
@@ -367,10 +382,14 @@ def main():
                        "tile_culling": "off" if os.environ.get("RC_NO_TILE_CULL") or job.camera.lens_radius != 0.0 else "on (bit-identical images)",
                        "l2": "256 MiB buffer written between timed iterations (flush)",
                        "parallelism": f"tiles{world}" if split_name == "tiles" else f"samples{world}",
-                       "exchange": ("none" if world == 1 else ("in-kernel peer stores into rank 0's frame buffer (CUDA IPC, NVLink) + 1-element all-reduce"
-                                                               if shared is not None else "NCCL reduce of the accumulation buffer to rank 0"))},
+                       "exchange": ("none" if world == 1 else ("in-kernel peer stores into rank 0's frame (CUDA IPC, NVLink) + per-rank progress words "
+                                                               "(rc_render_frame; no collective)"
+                                                               if frame is not None else "NCCL reduce of the accumulation buffer to rank 0"))},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(scene_bytes),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "call": "rc_render_frame" if frame is not None else ("rc_render" if world == 1 else "rc_render_accumulate + torch reduce")},
+            "e2e_cancel": {"value": e2e_cancel_value, "unit": "samples/s",
+                           "what": "the e2e call with a cancel flag that is never raised, as the reference's host always passes one"},
             "gpu_launches": launches[0],
             "clocks": sampler_thread.summary() if sampler_thread else None,
             "wall_s": wall,
@@ -395,15 +414,16 @@ def main():
                              "(f64, rejection samplers, sequential RNG, 10x10 tiles, all host threads)",
                    "segments_per_sample": cnt["segments"] / cnt["samples"],
                    "flops_per_sample_bvh": A, "flops_per_sample_linear": A_lin}
+        cap = ncu_capture(args.workload)
         if A is not None:
             # brute force (N_node = 0) when the scene has <= 8 primitives, else the
             # oracle's BVH counters
             A_used = A_lin if job.scene.c.n_prims <= 8 else A
             achieved = value / world * A_used / 1e12
             line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": fp32_tflops, "unit": "TFLOP/s",
-                                "frac": achieved / fp32_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
-                                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the megakernel launch, ncu --set full "
-                                                  "(profiles/r01_megakernel_v21_specialised_ncu.md): the accumulation buffer, once",
+                                "frac": achieved / fp32_tflops, "traffic": cap.get("dram_bytes_per_launch") if cap else None,
+                                "traffic_source": (cap.get("source") if cap else None),
+                                "ncu": cap,
                                 "peak_source": "FFMA micro-benchmark in this run (rc_fp32_peak), per GPU",
                                 "flops_per_sample": A_used, "lane_ginstr_per_s_peak": lane_ginstr,
                                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_kind,
@@ -411,9 +431,8 @@ def main():
         line["cpu_baseline"] = cpu
         print(json.dumps(line))
     barrier()
-    if shared is not None:
-        for ptr in shared:
-            r.shared_close(ptr)
+    if frame is not None:
+        r.frame_close(frame)
     r.close()
     if world > 1:
         dist.destroy_process_group()

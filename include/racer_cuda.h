@@ -337,6 +337,35 @@ int rc_shared_alloc(rc_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t handle[64
 int rc_shared_open(rc_ctx* ctx, const uint8_t handle[64], void** d_ptr);
 int rc_shared_close(rc_ctx* ctx, void* d_ptr);
 
+/* ---- the tile-split render of one box with one process per GPU, whole, behind the ABI ------------------------
+ * ("tile k -> GPU k mod N ... gather disjoint tiles to rank 0 ... direct remote stores into rank 0's
+ * buffer".  The reference is one process — CpuRenderer::render, src/renderer/cpu.rs:118-131, hands its tiles to a
+ * rayon pool and every tile is written into one ScreenBuffer (src/image_buffer.rs:147-170); this is that, with GPUs
+ * for pool threads and rank 0's frame for the ScreenBuffer.)
+ *
+ * rank 0 creates the frame: ONE allocation on its device 0 holding two width*height*3 float images (they
+ * alternate, so a rank already tracing the next frame never stores into the one being read) and a line of
+ * progress words per rank, and gets the 64-byte handle to pass to the other ranks (any byte channel); they map it
+ * with rc_frame_open (CUDA IPC: peer access over NVLink).  rc_frame_close unmaps / frees.
+ *
+ * rc_render_frame(params with rank / world, RC_SPLIT_TILES, megakernel), called by EVERY rank once per frame:
+ *   - waits on the device until rank 0 has released the image this frame goes into,
+ *   - traces this rank's tiles and stores sqrt(sum / samples) — Vec3::scale_sqrt (src/vec3.rs:119-125) folded into
+ *     the store — straight into rank 0's image as each tile finishes: the gather happens inside the render kernel,
+ *   - publishes "frame f done" in its progress word; rank 0's stream then waits for every rank's word.
+ * Nothing but kernels and stream-ordered waits is enqueued: no collective library, no host synchronisation.
+ * On rank 0, *d_rgb (if not NULL) receives the device pointer of the finished float image (stream-ordered: valid for
+ * work enqueued on the context's stream, until the next-but-one rc_render_frame); if out_rgb is not NULL the image is
+ * widened to f64, copied into it (width*height*3 doubles, like rc_render) and the call returns when it is there.
+ * On other ranks both must be NULL.  cancel: as for rc_render (every rank must pass a flag or none). */
+typedef struct rc_frame rc_frame;
+int rc_frame_create(rc_ctx* ctx, int32_t width, int32_t height, int32_t world, rc_frame** out, uint8_t handle[64]);
+int rc_frame_open(rc_ctx* ctx, const uint8_t handle[64], int32_t width, int32_t height, int32_t rank, int32_t world,
+                  rc_frame** out);
+int rc_frame_close(rc_ctx* ctx, rc_frame* frame);
+int rc_render_frame(rc_ctx* ctx, const rc_params* params, rc_frame* frame, const float** d_rgb, double* out_rgb,
+                    const volatile int32_t* cancel);
+
 /* scale_sqrt on a device accumulation buffer: d_rgb[i] = sqrt(d_accum[i] /
  * samples) (src/vec3.rs:119-125).  d_rgb may alias d_accum. */
 int rc_finalize(rc_ctx* ctx, const float* d_accum, int32_t width, int32_t height,

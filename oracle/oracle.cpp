@@ -131,8 +131,9 @@ struct Xoshiro {
 //   key = seed_lo ^ seed_hi
 // One PATH block per path segment e (0 = primary ray): the upper 24 bits of each word feed the
 // scattering event at the end of that segment (hit number b = e + 1); the low byte of each word
-// is spare, and in block 0 the two spare bytes are the sample's 16-bit v jitter.
-const uint32_t TAG_PATH = 0u;    // segment e: scatter bits of hit e + 1; e = 0 also: low bytes -> v jitter
+// is spare, and in block 0 the two spare bytes are the NEXT sample's 16-bit v jitter (sample s reads
+// them from block 0 of sample (s - 1) mod 2^24), so that no sample needs its own block before its first hit.
+const uint32_t TAG_PATH = 0u;    // segment e: scatter bits of hit e + 1; e = 0 also: low bytes -> v jitter of the next sample
 const uint32_t TAG_PIXEL = 1u;   // x -> per-pixel u jitter
 const uint32_t TAG_LENS = 2u;    // j = 0: direct lens sample, low bytes -> ray time; j >= 1: rejection iteration j
 const uint32_t TAG_REJECT = 3u;  // (hit number b, iteration j): three 21-bit uniforms
@@ -170,7 +171,7 @@ struct Draws {
     double v_jitter() const {  // cpu.rs:39-40
         if (backend != ORACLE_RNG_PHILOX) return seq->uniform();
         uint32_t w[2];
-        words(0u, sample, 0u, TAG_PATH, w);
+        words(0u, (sample - 1u) & 0xFFFFFFu, 0u, TAG_PATH, w);   // the spare bytes of the PREVIOUS sample's block 0
         return u16_low_bytes(w);
     }
     // j = 0: the direct lens sample (u1, u2); j >= 1: the j-th iteration of random_in_unit_disk
@@ -798,6 +799,11 @@ int oracle_render(const rc_scene* scene, const rc_camera* camera, const rc_param
                     V3 color = v3(0, 0, 0);
                     for (int s = s_begin; s < s_begin + s_count; ++s) {
                         dr.sample = (uint32_t)s;
+                        // COUNTERFACTUAL (not the reference): a fresh u jitter for every sample, i.e. what
+                        // cpu.rs:35-36 would be if it stood inside the sample loop.  Only the Q1 signature test
+                        // uses it, to show that the statistic it checks can tell the two apart.
+                        if ((opt.counterfactual & ORACLE_CF_PER_SAMPLE_U) && !params->fixed_jitter)
+                            u = ((double)x + seq.uniform()) / (double)(params->width - 1);
                         color = color + trace_sample(*scene, *camera, *params, dr, u, x, y, cnt).rgb;
                     }
                     double* o = out_rgb + 3 * ((size_t)y * params->width + x);
@@ -882,22 +888,37 @@ int oracle_primary_aov(const rc_scene* scene, const rc_camera* camera, const rc_
     rc_params p = *params;
     p.fixed_jitter = 1;
     p.max_depth = 1;  // one scene.hit; the scattered ray returns at depth 0
-    Counters cnt;
-    for (int y = 0; y < p.height; ++y)
-        for (int x = 0; x < p.width; ++x) {
-            Draws dr;
-            std::memset(&dr, 0, sizeof(dr));
-            dr.backend = ORACLE_RNG_PHILOX;
-            dr.rounds = 10;
-            dr.pixel = (uint32_t)(y * p.width + x);
-            double u = pixel_u(p, dr, x);
-            RayImageData d = trace_sample(*scene, *camera, p, dr, u, x, y, cnt);
-            size_t i = (size_t)y * p.width + x;
-            if (id) id[i] = d.obj_id;
-            if (t) t[i] = d.t;
-            if (normal) { normal[3 * i] = d.normal.x; normal[3 * i + 1] = d.normal.y; normal[3 * i + 2] = d.normal.z; }
-            if (point) { point[3 * i] = d.pos.x; point[3 * i + 1] = d.pos.y; point[3 * i + 2] = d.pos.z; }
+    // rows are independent (fixed jitter: no random stream is consumed): spread them over the host threads
+    std::atomic<int> next_row(0);
+    auto worker = [&]() {
+        Counters cnt;
+        for (;;) {
+            const int y = next_row.fetch_add(1);
+            if (y >= p.height) break;
+            for (int x = 0; x < p.width; ++x) {
+                Draws dr;
+                std::memset(&dr, 0, sizeof(dr));
+                dr.backend = ORACLE_RNG_PHILOX;
+                dr.rounds = 10;
+                dr.pixel = (uint32_t)(y * p.width + x);
+                double u = pixel_u(p, dr, x);
+                RayImageData d = trace_sample(*scene, *camera, p, dr, u, x, y, cnt);
+                size_t i = (size_t)y * p.width + x;
+                if (id) id[i] = d.obj_id;
+                if (t) t[i] = d.t;
+                if (normal) { normal[3 * i] = d.normal.x; normal[3 * i + 1] = d.normal.y; normal[3 * i + 2] = d.normal.z; }
+                if (point) { point[3 * i] = d.pos.x; point[3 * i + 1] = d.pos.y; point[3 * i + 2] = d.pos.z; }
+            }
         }
+    };
+    int n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1 || (long long)p.width * p.height < 65536) n_threads = 1;
+    if (n_threads == 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (int k = 0; k < n_threads; ++k) pool.emplace_back(worker);
+        for (auto& th : pool) th.join();
+    }
     return RC_OK;
 }
 

@@ -59,8 +59,13 @@ typedef struct oracle_options {
     int32_t sample_begin;   /* trace samples [sample_begin, +sample_count)   */
     int32_t sample_count;   /* 0 = params.samples                            */
     int32_t linear_sum;     /* 1: out_rgb = raw radiance sums (no scale_sqrt)*/
-    int32_t reserved;
+    int32_t counterfactual; /* ORACLE_CF_* bits; 0 = the reference's behaviour   */
 } oracle_options;
+
+/* Deliberate departures from the reference, for tests that must show a check can FAIL.
+ * ORACLE_CF_PER_SAMPLE_U: the horizontal jitter is drawn per sample instead of once per pixel
+ * (the opposite of quirk Q1, src/renderer/cpu.rs:35-36); sequential RNG only. */
+enum { ORACLE_CF_PER_SAMPLE_U = 1 };
 
 /* CpuRenderer::render for one image (src/renderer/cpu.rs:26-131).
  * out_rgb: width*height*3 doubles, row 0 = top.  counters may be NULL. */

@@ -22,6 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 
 RNG_PHILOX, RNG_SEQUENTIAL = 0, 1
+CF_PER_SAMPLE_U = 1   # oracle.h ORACLE_CF_PER_SAMPLE_U: NOT the reference (Q1 counterfactual)
 
 
 class oracle_counters(C.Structure):
@@ -42,7 +43,7 @@ class oracle_counters(C.Structure):
 class oracle_options(C.Structure):
     _fields_ = [("rng", C.c_int32), ("threads", C.c_int32), ("tiles_w", C.c_int32),
                 ("tiles_h", C.c_int32), ("sample_begin", C.c_int32), ("sample_count", C.c_int32),
-                ("linear_sum", C.c_int32), ("reserved", C.c_int32)]
+                ("linear_sum", C.c_int32), ("counterfactual", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -116,9 +117,10 @@ def d3(v):
 
 
 def render(job, params: rc_params, rng=RNG_PHILOX, threads=0, tiles=(10, 10), sample_begin=0,
-           sample_count=0, linear_sum=False, want_counters=False):
-    """oracle_render over a harness.Job; returns (H,W,3) float64 [and counters]."""
-    opt = oracle_options(rng, threads, tiles[0], tiles[1], sample_begin, sample_count, int(linear_sum), 0)
+           sample_count=0, linear_sum=False, want_counters=False, counterfactual=0):
+    """oracle_render over a harness.Job; returns (H,W,3) float64 [and counters].
+    counterfactual: CF_* bits, deliberate departures from the reference (tests that must be able to fail)."""
+    opt = oracle_options(rng, threads, tiles[0], tiles[1], sample_begin, sample_count, int(linear_sum), int(counterfactual))
     out = np.empty((params.height, params.width, 3), dtype=np.float64)
     cnt = oracle_counters()
     st = lib().oracle_render(job.scene.ptr, C.byref(job.camera), C.byref(params), C.byref(opt),

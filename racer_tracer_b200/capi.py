@@ -108,7 +108,7 @@ class rc_stats(C.Structure):
 ABI_SYMBOLS = [
     "rc_create", "rc_destroy", "rc_set_stream", "rc_upload_scene", "rc_set_camera", "rc_render",
     "rc_render_preview", "rc_build_lbvh", "rc_get_bvh", "rc_render_tiles_into", "rc_shared_alloc", "rc_shared_open",
-    "rc_shared_close",
+    "rc_shared_close", "rc_frame_create", "rc_frame_open", "rc_frame_close", "rc_render_frame",
     "rc_render_accumulate", "rc_finalize", "rc_postprocess", "rc_primary_aov", "rc_get_stats",
     "rc_last_error", "rc_abi_version", "rc_fp32_peak", "rc_partition", "rc_spec_source",
 ]
@@ -145,6 +145,10 @@ def load(path: str | None = None) -> C.CDLL:
     lib.rc_shared_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp), C.POINTER(C.c_uint8)]
     lib.rc_shared_open.argtypes = [vp, C.POINTER(C.c_uint8), C.POINTER(vp)]
     lib.rc_shared_close.argtypes = [vp, vp]
+    lib.rc_frame_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_uint8)]
+    lib.rc_frame_open.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.rc_frame_close.argtypes = [vp, vp]
+    lib.rc_render_frame.argtypes = [vp, C.POINTER(rc_params), vp, C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.rc_build_lbvh.argtypes = [vp]
     lib.rc_get_bvh.argtypes = [vp, C.POINTER(rc_bvh_node), C.c_int32, C.POINTER(C.c_int32), C.c_int32]
     lib.rc_render_preview.argtypes = [vp, C.POINTER(rc_params), C.c_int32, C.c_int32, C.POINTER(C.c_double),

@@ -7,8 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rt_kernels.cuh"
@@ -54,6 +56,8 @@ struct DevBuf {
         if (n == 0) return cudaSuccess;
         return cudaMalloc(&p, n * sizeof(T));
     }
+    // scratch buffers that are reused call after call: grow, never shrink
+    cudaError_t reserve(size_t count) { return (p && n >= count) ? cudaSuccess : resize(count); }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -66,6 +70,7 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_traced = nullptr;   // this device's share of the current render has been traced (cancel relay, fork)
     DevBuf<DevPrim> prims;
     DevBuf<DevPrim> prims_lin;
     DevBuf<DevNode> nodes;
@@ -84,6 +89,8 @@ struct DeviceState {
     DevBuf<float> accum;
     DevBuf<float> slice_buf;
     DevBuf<double> out64;
+    DevBuf<double> pp_in, pp_mapped;   // rc_postprocess scratch (kept between calls)
+    DevBuf<uint8_t> pp_rgba;
     DevBuf<unsigned long long> counter;
     WavefrontState wf;
     std::map<std::string, SpecKernel> spec_cache;   // scene-specialised kernels loaded on this device
@@ -91,6 +98,20 @@ struct DeviceState {
 };
 
 }  // namespace
+
+// One image shared by the ranks of a box (rc_frame_create / rc_frame_open): [image 0][image 1][progress words],
+// all in one allocation on rank 0's device.  Word 32 * r: the last frame rank r has stored completely (r >= 1);
+// word 0: the last frame whose image rank 0 has released for writing.
+struct rc_frame {
+    float* base = nullptr;
+    size_t image_floats = 0;
+    int* words = nullptr;
+    int width = 0, height = 0, rank = 0, world = 1;
+    int frame_no = 0;                  // frames rendered through this handle so far
+    bool owner = false;
+    int* timed_out = nullptr;          // mapped host word raised by a wait that gave up
+    DevBuf<double> out64;
+};
 
 struct rc_ctx {
     std::vector<DeviceState> devs;
@@ -108,6 +129,8 @@ struct rc_ctx {
     std::vector<int> prim_order;       // device primitive i = uploaded primitive prim_order[i] (empty: identity)
     bool lbvh = false;
     bool overwrite = false;            // set for the duration of rc_render_tiles_into
+    float final_scale = 0.0f;          // set for the duration of rc_render_frame (KParams::final_scale)
+    std::vector<rc_frame*> frames;     // rc_frame_create / rc_frame_open
     bool stats_pending = false;        // the last render's time / counters have not been read back yet
     std::vector<void*> shared_owned, shared_opened;   // rc_shared_alloc / rc_shared_open
     int n_prims = 0, n_perlin = 0;
@@ -115,6 +138,8 @@ struct rc_ctx {
     rc_camera camera;
     rc_stats stats;
     MultiState multi;
+    int* cancel_relay = nullptr;       // one word of mapped, portable host memory: the flag the kernels read (KParams::cancel_flag)
+    uint64_t spec_clock = 0;           // use counter of the scene-specialised kernel caches (LRU)
 };
 
 namespace {
@@ -137,6 +162,11 @@ int validate_scene(const rc_scene* s) {
     if (s->n_prims > 0 && (!s->prim_type || !s->prim_data || !s->prim_material || !s->prim_id))
         return fail(RC_ERR_INVALID, "primitive arrays missing");
     if (s->n_images > RT_MAX_IMAGES) return fail(RC_ERR_INVALID, "more than 8 image textures");
+    if ((s->n_materials > 0 && !s->materials) || (s->n_textures > 0 && !s->textures) || (s->n_nodes > 0 && !s->nodes) ||
+        (s->n_images > 0 && !s->images) || (s->n_perlin > 0 && !s->perlin))
+        return fail(RC_ERR_INVALID, "a table with a non-zero count is NULL");
+    for (int i = 0; i < s->n_images; ++i)
+        if (s->images[i].width <= 0 || s->images[i].height <= 0 || !s->images[i].rgba) return fail(RC_ERR_INVALID, "empty image texture");
     if (s->n_prims >= (1 << 24)) return fail(RC_ERR_INVALID, "too many primitives");
     for (int i = 0; i < s->n_prims; ++i) {
         if (s->prim_type[i] < 0 || s->prim_type[i] > RC_PRIM_MOVING_SPHERE) return fail(RC_ERR_INVALID, "unknown primitive type");
@@ -148,7 +178,7 @@ int validate_scene(const rc_scene* s) {
         int m = s->prim_material[i];
         if (m < 0 || m >= s->n_materials) return fail(RC_ERR_INVALID, "primitive material index out of range");
         if (s->prim_id[i] == 0) return fail(RC_ERR_INVALID, "object id 0 is reserved for a miss");
-        if (s->prim_instance && s->n_instances > 0 && s->prim_instance[i] >= s->n_instances)
+        if (s->prim_instance && s->n_instances > 0 && (s->prim_instance[i] >= s->n_instances || s->prim_instance[i] < -1))
             return fail(RC_ERR_INVALID, "primitive instance index out of range");
     }
     for (int i = 0; i < s->n_materials; ++i) {
@@ -296,6 +326,7 @@ void partition(KParams& kp, const rc_params* p, int part, int parts) {
     kp.tile_w = RT_TILE_W; kp.tile_h = RT_TILE_H;
     kp.slices = 1; kp.slice_buf = nullptr;
     kp.overwrite = 0;
+    kp.final_scale = 0.0f;
     kp.tiles_x = (p->width + RT_TILE_W - 1) / RT_TILE_W;
     int tiles_y = (p->height + RT_TILE_H - 1) / RT_TILE_H;
     int total = kp.tiles_x * tiles_y;
@@ -332,12 +363,21 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
     for (int k = 0; k < n_dev; ++k) {
         DeviceState& d = ctx->devs[k];
         CUDA_TRY(cudaSetDevice(d.device));
-        if (k == 0) CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
+        if (k == 0) {
+            CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
+            // fork: whatever device 0's stream holds so far — the zero-fill of the buffer the other devices are about
+            // to store into, the previous frame's finalize that still reads it — happens before any of them starts
+            if (n_dev > 1) CUDA_TRY(cudaEventRecord(d.ev_traced, d.stream));
+        } else {
+            CUDA_TRY(cudaStreamWaitEvent(d.stream, ctx->devs[0].ev_traced, 0));
+        }
         CUDA_TRY(cudaMemsetAsync(d.counter.p, 0, sizeof(unsigned long long), d.stream));
     }
-    // passes: one launch per device when no cancel flag is given, otherwise
-    // slices of the sample range with a poll in between (do_cancel per row,
-    // src/renderer/cpu.rs:55-62)
+    // A cancel flag does not change how the frame is launched (one launch per device, sliced if need be): the
+    // kernels watch a word of mapped host memory, and this call relays the caller's flag to it while it waits
+    // (do_cancel per row, src/renderer/cpu.rs:55-62).  The wavefront variant is not interruptible.
+    const bool relay = cancel != nullptr && p->variant == RC_VARIANT_MEGAKERNEL;
+    if (relay) *ctx->cancel_relay = 0;
     for (int k = 0; k < n_dev; ++k) {
         DeviceState& d = ctx->devs[k];
         CUDA_TRY(cudaSetDevice(d.device));
@@ -347,6 +387,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         kp.perlin = d.perlin.p; kp.perlin_perm = d.perm.p;
         for (size_t i = 0; i < d.tex.size(); ++i) kp.images[i] = d.tex[i];
         kp.segment_counter = d.counter.p;
+        kp.cancel_flag = relay ? ctx->cancel_relay : nullptr;
         partition(kp, p, p->rank * n_dev + k, parts);
         // tile culling needs one ray origin per tile (no lens), primitives that stay where they are, and a linear mode
         kp.tile_cull = (!kp.lens_enabled && !kp.has_motion && !p->fixed_jitter && std::getenv("RC_NO_TILE_CULL") == nullptr) ? 1 : 0;
@@ -359,7 +400,8 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         const bool direct = n_dev > 1 && p->split == RC_SPLIT_TILES && ctx->multi.peer_write_ok && p->variant == RC_VARIANT_MEGAKERNEL;
         float* accum = (k == 0 || direct) ? accum0 : d.accum.p;
         kp.overwrite = ctx->overwrite ? 1 : 0;
-        if (kp.n_tiles == 0 || kp.s_end <= kp.s_begin) continue;
+        kp.final_scale = ctx->final_scale;
+        if (kp.n_tiles == 0 || kp.s_end <= kp.s_begin) { if (relay) CUDA_TRY(cudaEventRecord(d.ev_traced, d.stream)); continue; }
         if (p->variant == RC_VARIANT_WAVEFRONT) {
             if (kp.has_motion && rounds != 10) return fail(RC_ERR_INVALID, "the wavefront variant traces moving spheres with 10 Philox rounds only");
             int rc = wavefront_render(d.wf, ctx->mode, kp, accum, p->sampler, rounds, ctx->smem_bytes, d.stream, d.sm_count, launches);
@@ -370,28 +412,27 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         SpecKernel* spec = nullptr;
         // (the constant-table path gets its primitives as immediates; the BVH paths get the scene's kinds of
         // primitive, material and wrapper compiled in or out — 48 KB of dynamic shared memory without opt-in)
-        const bool spec_mode_ok = ctx->mode == RT_MODE_CONST_LINEAR ||
-                                  ((ctx->mode == RT_MODE_SMEM_BVH || ctx->mode == RT_MODE_GLOBAL_BVH) && ctx->smem_bytes <= 48 * 1024 &&
-                                   std::getenv("RC_NO_BVH_SPEC") == nullptr);
+        const bool spec_mode_ok = ctx->smem_bytes <= 48 * 1024 &&
+                                  (ctx->mode == RT_MODE_CONST_LINEAR ||
+                                   ((ctx->mode == RT_MODE_SMEM_BVH || ctx->mode == RT_MODE_GLOBAL_BVH) && std::getenv("RC_NO_BVH_SPEC") == nullptr));
         if (p->specialize && spec_mode_ok && p->sampler == RC_SAMPLER_DIRECT && rounds == 10 && !p->fixed_jitter) {
             std::string err;
             if (!spec_load_api((const void*)&rc_abi_version)) err = spec_api().err;
             else {
                 if (ctx->spec_source.empty())
                     ctx->spec_source = spec_generate(ctx->kp, ctx->has_textures, ctx->mats_mask, ctx->mode, ctx->prims_mask, ctx->instanced);
-                spec = spec_build(d.spec_cache, ctx->spec_source, err);
+                spec = spec_build(d.spec_cache, ctx->spec_source, err, ++ctx->spec_clock);
             }
             if (!spec && p->specialize == 1) return fail(RC_ERR_STATE, "scene specialisation failed: " + err);
         } else if (p->specialize == 1) {
             return fail(RC_ERR_INVALID, "specialize = 1 needs the megakernel, the direct sampler, 10 Philox rounds and no fixed jitter");
         }
         const int s0 = kp.s_begin, s1 = kp.s_end;
-        const int step = cancel ? 32 : (s1 - s0);
         // few tiles on this device (its share of a multi-GPU render): cut every tile's sample range
         // into slices so that the grid is still >= 8 full machine loads of CTAs
         kp.slices = 1;
         kp.slice_buf = nullptr;
-        if (!cancel) {
+        {
             const long long want = 8LL * d.sm_count * 10;
             long long sl = (want + kp.n_tiles - 1) / kp.n_tiles;
             if (sl > (s1 - s0) / 16) sl = (s1 - s0) / 16;
@@ -402,16 +443,15 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
                 kp.slice_buf = d.slice_buf.p;
             }
         }
-        for (int s = s0; s < s1; s += step) {
-            kp.s_begin = s; kp.s_end = s + step < s1 ? s + step : s1;
-            int rc;
+        {
+            int rc = RC_ERR_CUDA;
             if (spec) {
-                used_spec = true;
                 rc = spec_launch(spec, kp, accum, kp.n_tiles * kp.slices, ctx->smem_bytes, d.stream) == 0 ? RC_OK : RC_ERR_CUDA;
-                if (rc != RC_OK) return fail(rc, "launch of the scene-specialised kernel failed");
-            } else {
-                rc = launch_mega(ctx->mode, ctx->has_textures, kp, accum, p->sampler, rounds, kp.n_tiles * kp.slices, ctx->smem_bytes, d.stream);
+                if (rc == RC_OK) used_spec = true;
+                else if (p->specialize == 1) return fail(rc, "launch of the scene-specialised kernel failed");
             }
+            if (rc != RC_OK)   // no specialised kernel, or (specialize == 2) it could not be launched: the precompiled one
+                rc = launch_mega(ctx->mode, ctx->has_textures, kp, accum, p->sampler, rounds, kp.n_tiles * kp.slices, ctx->smem_bytes, d.stream);
             if (rc != RC_OK) return rc;
             ++launches;
             if (kp.slices > 1) {
@@ -419,26 +459,50 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
                 CUDA_TRY(cudaGetLastError());
                 ++launches;
             }
-            if (cancel && n_dev == 1) {
-                CUDA_TRY(cudaStreamSynchronize(d.stream));
-                if (cancelled(cancel)) { was_cancelled = true; return RC_OK; }
-            }
         }
+        if (relay) CUDA_TRY(cudaEventRecord(d.ev_traced, d.stream));
     }
     ctx->stats.kernel_launches = launches;
     ctx->stats.specialized = used_spec ? 1 : 0;
+    if (relay) {
+        // wait for the frame while relaying the caller's flag; a raised flag empties the rest of the grid at once
+        for (;;) {
+            bool done = true;
+            for (int k = 0; k < n_dev && done; ++k) {
+                const cudaError_t e = cudaEventQuery(ctx->devs[k].ev_traced);
+                if (e == cudaErrorNotReady) done = false;
+                else if (e != cudaSuccess) return fail(RC_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+            }
+            if (!was_cancelled && cancelled(cancel)) {
+                was_cancelled = true;
+                *reinterpret_cast<volatile int*>(ctx->cancel_relay) = 1;
+            }
+            if (done) break;
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        CUDA_TRY(cudaSetDevice(ctx->devs[0].device));
+    }
     return RC_OK;
 }
 
-int ensure_accum(rc_ctx* ctx, const rc_params* p, bool device0_too) {
+int ensure_accum(rc_ctx* ctx, const rc_params* p, bool device0_too, bool zero = true) {
     size_t n = (size_t)p->width * p->height * 3;
     for (size_t k = device0_too ? 0 : 1; k < ctx->devs.size(); ++k) {
         DeviceState& d = ctx->devs[k];
         CUDA_TRY(cudaSetDevice(d.device));
         CUDA_TRY(d.accum.resize(n));
-        CUDA_TRY(cudaMemsetAsync(d.accum.p, 0, n * sizeof(float), d.stream));
+        if (zero) CUDA_TRY(cudaMemsetAsync(d.accum.p, 0, n * sizeof(float), d.stream));
     }
     return RC_OK;
+}
+
+// rc_render / rc_render_preview own their accumulation buffers and trace every pixel's samples in ONE launch, so the
+// megakernel can STORE the sums instead of adding them to a zero-filled buffer (no memset, no read of the frame):
+// always with one device; with several when every pixel of a buffer is written by exactly one kernel — peer stores
+// into device 0's buffer, or a sample split (every device writes all pixels of its own buffer, ncclReduce adds them).
+bool can_store(const rc_ctx* ctx, const rc_params* p) {
+    if (p->variant != RC_VARIANT_MEGAKERNEL) return false;
+    return ctx->devs.size() == 1 || direct_tiles(ctx, p) || p->split == RC_SPLIT_SAMPLES;
 }
 
 // End of a render call: the stop event is recorded, nothing is waited for.  Time and segment counters are
@@ -701,6 +765,8 @@ static void build_tables(const rc_scene* s, HostTables& t) {
 extern "C" {
 
 const char* rc_last_error(void) { return g_last_error.c_str(); }
+int rc_destroy(rc_ctx* ctx);
+int rc_frame_close(rc_ctx* ctx, rc_frame* frame);
 int rc_abi_version(void) { return RC_ABI_VERSION; }
 
 int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
@@ -728,6 +794,7 @@ int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
         if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
         if (err == cudaSuccess) err = cudaEventCreate(&d.ev0);
         if (err == cudaSuccess) err = cudaEventCreate(&d.ev1);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&d.ev_traced, cudaEventDisableTiming);
         if (err == cudaSuccess) err = d.counter.resize(1);
         cudaDeviceProp prop;
         if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, d.device);
@@ -747,6 +814,13 @@ int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
         return fail(rc, "peer access setup failed");
     }
     cudaSetDevice(ctx->devs[0].device);
+    // the word the kernels of a cancellable render watch: mapped host memory, visible to every device (UVA)
+    if (cudaHostAlloc((void**)&ctx->cancel_relay, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        rc_destroy(ctx);
+        return fail(RC_ERR_CUDA, "cudaHostAlloc of the cancel relay failed");
+    }
+    *ctx->cancel_relay = 0;
     *out = ctx;
     return RC_OK;
 }
@@ -754,14 +828,18 @@ int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
 int rc_destroy(rc_ctx* ctx) {
     if (!ctx) return RC_OK;
     cudaSetDevice(ctx->devs.empty() ? 0 : ctx->devs[0].device);
+    while (!ctx->frames.empty()) rc_frame_close(ctx, ctx->frames.back());
     for (void* q : ctx->shared_opened) cudaIpcCloseMemHandle(q);
     for (void* q : ctx->shared_owned) cudaFree(q);
+    if (ctx->cancel_relay) cudaFreeHost(ctx->cancel_relay);
     multi_destroy(ctx->multi);
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.device);
         cudaDeviceSynchronize();
         free_scene(d);
         d.accum.release(); d.slice_buf.release(); d.out64.release(); d.counter.release();
+        d.pp_in.release(); d.pp_mapped.release(); d.pp_rgba.release();
+        if (d.ev_traced) cudaEventDestroy(d.ev_traced);
         wavefront_release(d.wf);
         spec_release(d.spec_cache);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -790,6 +868,9 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     build_tables(s, t);
     if (!t.instances.empty() && t.kp.n_cobj == 0 && s->n_nodes == 0)
         return fail(RC_ERR_INVALID, "a scene with more than 8 instanced objects (or without prim_aabb) needs BVH nodes");
+    // everything above is validation on host memory; from here on the context changes.  It holds no scene until
+    // every device has all of its tables: a failed upload leaves has_scene == false, never a half-uploaded scene.
+    ctx->has_scene = false;
     {   // keep the camera / launch fields already stored in ctx->kp
         DevCamera<float> cam = ctx->kp.cam;
         int lens = ctx->kp.lens_enabled;
@@ -848,7 +929,6 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
             // image textures as CUDA texture objects: point filter, clamp, u8 -> float/255
             // (src/texture/image.rs:28-51, Q21)
             const rc_image& im = s->images[i];
-            if (im.width <= 0 || im.height <= 0 || !im.rgba) return fail(RC_ERR_INVALID, "empty image texture");
             cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
             cudaArray_t arr;
             CUDA_TRY(cudaMallocArray(&arr, &desc, im.width, im.height));
@@ -988,6 +1068,119 @@ int rc_shared_close(rc_ctx* ctx, void* d_ptr) {
     return fail(RC_ERR_INVALID, "pointer was not returned by rc_shared_alloc / rc_shared_open on this context");
 }
 
+// ---- the one-process-per-GPU tile split, whole (header: rc_render_frame) ----
+static size_t frame_bytes(int width, int height, int world, size_t* image_floats) {
+    size_t n = (size_t)width * height * 3;
+    n = (n + 63) & ~(size_t)63;                       // images start on 256-byte boundaries
+    *image_floats = n;
+    return 2 * n * sizeof(float) + (size_t)(world + 1) * 32 * sizeof(int);
+}
+
+static int frame_init(rc_ctx* ctx, rc_frame* f, void* base, int width, int height, int rank, int world, bool owner) {
+    size_t nf = 0;
+    frame_bytes(width, height, world, &nf);
+    f->base = (float*)base; f->image_floats = nf; f->words = (int*)(f->base + 2 * nf);
+    f->width = width; f->height = height; f->rank = rank; f->world = world; f->owner = owner;
+    if (cudaHostAlloc((void**)&f->timed_out, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return fail(RC_ERR_CUDA, "cudaHostAlloc failed");
+    *f->timed_out = 0;
+    ctx->frames.push_back(f);
+    return RC_OK;
+}
+
+int rc_frame_create(rc_ctx* ctx, int32_t width, int32_t height, int32_t world, rc_frame** out, uint8_t handle[64]) {
+    if (!ctx || !out || !handle || width < 2 || height < 2 || world < 1 || world > 30) return fail(RC_ERR_INVALID, "bad rc_frame_create arguments");
+    size_t nf = 0;
+    void* base = nullptr;
+    int rc = rc_shared_alloc(ctx, frame_bytes(width, height, world, &nf), &base, handle);   // zero-filled: frame 0 is "done" everywhere
+    if (rc != RC_OK) return rc;
+    rc_frame* f = new rc_frame();
+    rc = frame_init(ctx, f, base, width, height, 0, world, true);
+    if (rc != RC_OK) { delete f; return rc; }
+    *out = f;
+    return RC_OK;
+}
+
+int rc_frame_open(rc_ctx* ctx, const uint8_t handle[64], int32_t width, int32_t height, int32_t rank, int32_t world, rc_frame** out) {
+    if (!ctx || !out || !handle || width < 2 || height < 2 || world < 2 || rank < 1 || rank >= world) return fail(RC_ERR_INVALID, "bad rc_frame_open arguments");
+    void* base = nullptr;
+    int rc = rc_shared_open(ctx, handle, &base);
+    if (rc != RC_OK) return rc;
+    rc_frame* f = new rc_frame();
+    rc = frame_init(ctx, f, base, width, height, rank, world, false);
+    if (rc != RC_OK) { delete f; return rc; }
+    *out = f;
+    return RC_OK;
+}
+
+int rc_frame_close(rc_ctx* ctx, rc_frame* f) {
+    if (!ctx || !f) return fail(RC_ERR_INVALID, "bad rc_frame_close arguments");
+    auto it = std::find(ctx->frames.begin(), ctx->frames.end(), f);
+    if (it == ctx->frames.end()) return fail(RC_ERR_INVALID, "frame does not belong to this context");
+    ctx->frames.erase(it);
+    cudaSetDevice(ctx->devs[0].device);
+    cudaStreamSynchronize(ctx->devs[0].stream);
+    int rc = rc_shared_close(ctx, f->base);
+    if (f->timed_out) cudaFreeHost(f->timed_out);
+    f->out64.release();
+    delete f;
+    return rc;
+}
+
+int rc_render_frame(rc_ctx* ctx, const rc_params* p, rc_frame* f, const float** d_rgb, double* out_rgb, const volatile int32_t* cancel) {
+    if (!ctx || !f) return fail(RC_ERR_INVALID, "ctx or frame is NULL");
+    int rc = check_params(p);
+    if (rc != RC_OK) return rc;
+    if (std::find(ctx->frames.begin(), ctx->frames.end(), f) == ctx->frames.end()) return fail(RC_ERR_INVALID, "frame does not belong to this context");
+    if (p->split != RC_SPLIT_TILES || p->variant != RC_VARIANT_MEGAKERNEL) return fail(RC_ERR_INVALID, "rc_render_frame needs the tile split and the megakernel");
+    if (p->width != f->width || p->height != f->height) return fail(RC_ERR_INVALID, "params and frame sizes differ");
+    const int world = p->world > 0 ? p->world : 1;
+    if (world != f->world || p->rank != f->rank) return fail(RC_ERR_INVALID, "params and frame rank / world differ");
+    if (f->rank != 0 && (d_rgb || out_rgb)) return fail(RC_ERR_INVALID, "only rank 0 receives the image");
+    if (ctx->devs.size() != 1) return fail(RC_ERR_INVALID, "rc_render_frame is the one-process-per-GPU form: the context must hold one device");
+    if (!ctx->has_scene || !ctx->has_camera) return fail(RC_ERR_STATE, "upload a scene and set a camera first");
+    if (cancelled(cancel)) return fail(RC_ERR_CANCELLED, "cancel flag set before the render started");
+    if (*f->timed_out) return fail(RC_ERR_STATE, "an earlier frame never completed (a rank stopped publishing progress)");
+    DeviceState& d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    const int frame_no = ++f->frame_no;
+    float* image = f->base + (size_t)(frame_no & 1) * f->image_floats;
+    // the image of frame n was last used by frame n - 2: rank 0 releases it when it gets here (whatever read it was
+    // enqueued on this stream before), the others wait for that release
+    if (world > 1) {
+        if (f->rank == 0) frame_publish_kernel<<<1, 1, 0, d.stream>>>(f->words, frame_no);
+        else frame_wait_kernel<<<1, 32, 0, d.stream>>>(f->words, 0, 1, frame_no, f->timed_out);
+        CUDA_TRY(cudaGetLastError());
+    }
+    bool was_cancelled = false;
+    ctx->overwrite = true;
+    ctx->final_scale = 1.0f / (float)p->samples;
+    rc = trace_share(ctx, p, image, cancel, was_cancelled);
+    ctx->overwrite = false;
+    ctx->final_scale = 0.0f;
+    if (rc != RC_OK) return rc;
+    uint64_t extra = 0;
+    if (world > 1) {
+        if (f->rank != 0) { frame_publish_kernel<<<1, 1, 0, d.stream>>>(f->words + 32 * f->rank, frame_no); extra = 2; }
+        else { frame_wait_kernel<<<1, 32, 0, d.stream>>>(f->words, 1, world - 1, frame_no, f->timed_out); extra = 2; }
+        CUDA_TRY(cudaGetLastError());
+    }
+    rc = finish_stats(ctx, p);
+    if (rc != RC_OK) return rc;
+    ctx->stats.kernel_launches += extra;
+    if (d_rgb) *d_rgb = image;
+    if (out_rgb && !was_cancelled) {
+        const size_t n = (size_t)p->width * p->height * 3;
+        CUDA_TRY(f->out64.reserve(n));
+        widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(image, f->out64.p, n);
+        CUDA_TRY(cudaGetLastError());
+        ctx->stats.kernel_launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(out_rgb, f->out64.p, n * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        if (*f->timed_out) return fail(RC_ERR_STATE, "the frame never completed (a rank stopped publishing progress)");
+    }
+    return RC_OK;
+}
+
 int rc_finalize(rc_ctx* ctx, const float* d_accum, int32_t width, int32_t height, int32_t samples, float* d_rgb) {
     if (!ctx || !d_accum || !d_rgb || samples < 1) return fail(RC_ERR_INVALID, "bad finalize arguments");
     DeviceState& d = ctx->devs[0];
@@ -1006,10 +1199,13 @@ int rc_render(rc_ctx* ctx, const rc_params* p, double* out_rgb, const volatile i
     if (cancelled(cancel)) return fail(RC_ERR_CANCELLED, "cancel flag set before the render started");
     DeviceState& d0 = ctx->devs[0];
     size_t n = (size_t)p->width * p->height * 3;
-    rc = ensure_accum(ctx, p, true);
+    const bool store = can_store(ctx, p);
+    rc = ensure_accum(ctx, p, true, !store);
     if (rc != RC_OK) return rc;
     bool was_cancelled = false;
+    ctx->overwrite = store;
     rc = trace_share(ctx, p, d0.accum.p, cancel, was_cancelled);
+    ctx->overwrite = false;
     if (rc != RC_OK) return rc;
     if (was_cancelled) return RC_OK;  // a cancelled render writes nothing, cpu.rs:55-62
     if (ctx->devs.size() > 1 && direct_tiles(ctx, p)) {
@@ -1054,11 +1250,14 @@ int rc_render_preview(rc_ctx* ctx, const rc_params* p, int32_t scale_w, int32_t 
         return RC_OK;
     }
     // single traced row/column: check_params wants >= 2 only because u divides by W-1, which is the screen's here
-    rc = ensure_accum(ctx, &q, true);
+    const bool store = can_store(ctx, &q);
+    rc = ensure_accum(ctx, &q, true, !store);
     if (rc != RC_OK) return rc;
     ctx->preview_sw = scale_w; ctx->preview_sh = scale_h; ctx->preview_w = p->width; ctx->preview_h = p->height;
     bool was_cancelled = false;
+    ctx->overwrite = store;
     rc = trace_share(ctx, &q, d0.accum.p, cancel, was_cancelled);
+    ctx->overwrite = false;
     ctx->preview_sw = ctx->preview_sh = ctx->preview_w = ctx->preview_h = 0;
     if (rc != RC_OK) return rc;
     if (was_cancelled) return RC_OK;
@@ -1209,11 +1408,12 @@ int rc_postprocess(rc_ctx* ctx, const rc_tone_map* tm, const double* rgb, int32_
     DeviceState& d = ctx->devs[0];
     CUDA_TRY(cudaSetDevice(d.device));
     size_t np = (size_t)width * height;
-    DevBuf<double> in, mapped;
-    DevBuf<uint8_t> q;
-    CUDA_TRY(in.resize(np * 3));
-    CUDA_TRY(mapped.resize(np * 3));
-    CUDA_TRY(q.resize(np * 4));
+    DevBuf<double>& in = d.pp_in;          // scratch kept between calls (one tone-mapped frame per render)
+    DevBuf<double>& mapped = d.pp_mapped;
+    DevBuf<uint8_t>& q = d.pp_rgba;
+    CUDA_TRY(in.reserve(np * 3));
+    CUDA_TRY(mapped.reserve(np * 3));
+    CUDA_TRY(q.reserve(np * 4));
     ToneParams tp;
     std::memset(&tp, 0, sizeof(tp));
     tp.type = tm->type;
@@ -1234,7 +1434,6 @@ int rc_postprocess(rc_ctx* ctx, const rc_tone_map* tm, const double* rgb, int32_
     if (e == cudaSuccess && rgba) e = cudaMemcpyAsync(rgba, q.p, np * 4, cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess && rgb_out) e = cudaMemcpyAsync(rgb_out, mapped.p, np * 3 * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
-    in.release(); mapped.release(); q.release();
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, std::string("postprocess: ") + cudaGetErrorString(e));
     return RC_OK;
 }

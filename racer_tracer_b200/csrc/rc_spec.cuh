@@ -32,7 +32,12 @@ struct SpecKernel {
     void* function = nullptr;   // CUfunction
     std::string source;
     std::string error;          // non-empty: this source failed to compile / load (remembered, not retried per render)
+    uint64_t last_use = 0;      // LRU stamp
 };
+
+// A scene edit or a camera move into / out of a wall pair's slab is a new source text, hence a new module: the cache
+// keeps the most recently used few and unloads the rest (an interactive host re-uploads on every edit).
+#define RC_SPEC_CACHE_MAX 8
 
 struct SpecApi {
     bool tried = false, ok = false;
@@ -141,7 +146,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     o << "#define RT_SPEC_BG_BLACK " << (black ? 1 : 0) << "\n";
     o << "#define RT_HAS_INSTANCES " << (kp.n_cobj > 0 ? 1 : 0) << "\n";
     o << "#define RT_HAS_LENS " << (kp.lens_enabled ? 1 : 0) << "\n";   // part of the source, hence of the cache key
-    if (const char* e = std::getenv("RC_REGEN_MIN")) o << "#define RT_REGEN_MIN " << std::atoi(e) << "\n";
+    if (const char* e = std::getenv("RC_STEAL")) o << "#define RT_STEAL " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
     o << "#include \"rt_scene.cuh\"\n";
     // rectangle-only scenes keep the index of the best hit as a FLOAT, so that both conditional moves of the
@@ -400,15 +405,24 @@ inline bool spec_read(const std::string& path, std::string& out) {
 }
 
 // Compile + load; returns nullptr and sets err on failure.
-inline SpecKernel* spec_build(std::map<std::string, SpecKernel>& cache, const std::string& source, std::string& err) {
+inline SpecKernel* spec_build(std::map<std::string, SpecKernel>& cache, const std::string& source, std::string& err, uint64_t now = 0) {
     auto it = cache.find(source);
     if (it != cache.end()) {
+        it->second.last_use = now;
         if (!it->second.error.empty()) { err = it->second.error; return nullptr; }
         return &it->second;
+    }
+    while (cache.size() >= RC_SPEC_CACHE_MAX) {   // evict the least recently used entry
+        auto victim = cache.begin();
+        for (auto j = cache.begin(); j != cache.end(); ++j)
+            if (j->second.last_use < victim->second.last_use) victim = j;
+        if (victim->second.module && spec_api().cuModuleUnload) spec_api().cuModuleUnload(victim->second.module);
+        cache.erase(victim);
     }
     auto remember_failure = [&]() {
         SpecKernel bad;
         bad.error = err;
+        bad.last_use = now;
         cache.emplace(source, bad);
         return (SpecKernel*)nullptr;
     };
@@ -441,6 +455,7 @@ inline SpecKernel* spec_build(std::map<std::string, SpecKernel>& cache, const st
     a.DestroyProgram(&prog);
     SpecKernel k;
     k.source = source;
+    k.last_use = now;
     if (a.cuModuleLoadData(&k.module, cubin.data()) != 0) { err = "cuModuleLoadData failed"; return remember_failure(); }
     if (a.cuModuleGetFunction(&k.function, k.module, "spec_megakernel") != 0) { err = "spec_megakernel not found in module"; return remember_failure(); }
     auto res = cache.emplace(source, k);

@@ -100,12 +100,14 @@ struct PixelCtx {
     vec3f dir0;        // upper_left_corner + u*horizontal - origin, fixed per pixel (Q1)
     uint32_t pixel;
     int px, py;
+    float rowf;        // (float)(py * px_scale_y): the row term of v (cpu.rs:39-40)
 };
 
 template <int ROUNDS>
 RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
     PixelCtx c;
     c.px = px; c.py = py;
+    c.rowf = (float)(py * P.px_scale_y);
     c.pixel = (uint32_t)(py * P.width + px);
     float ujit = 0.5f;
     if (!RT_FIXED_JITTER(P)) ujit = u24(philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.ks).x);
@@ -119,7 +121,7 @@ RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
 template <int SAMPLER, int ROUNDS>
 RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit16, vec3f& o, vec3f& d, float& time) {
     // vjit16 = the v jitter times 65536 (an integer: the scaling is exact, so the fused form rounds like add(py, jitter))
-    float v = fmaf(vjit16, 1.0f / 65536.0f, (float)(c.py * P.px_scale_y)) * P.inv_hm1;  // cpu.rs:39-40 (cpu_scaled.rs:59-60)
+    float v = fmaf(vjit16, 1.0f / 65536.0f, c.rowf) * P.inv_hm1;  // cpu.rs:39-40 (cpu_scaled.rs:59-60)
     d = c.dir0 - v * P.cam.vertical;
     o = P.cam.origin;
     time = P.cam.time_a;
@@ -307,19 +309,34 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
 #ifndef RT_MIN_BLOCKS_GLOBAL_BVH
 #define RT_MIN_BLOCKS_GLOBAL_BVH 9
 #endif
-// Lanes whose path ended wait until at least this many lanes of the warp want a new sample
-// (or nobody is alive): regeneration is the one part of the loop that runs at low lane
-// occupancy, so it is batched.  1 = regenerate immediately.
-#ifndef RT_REGEN_MIN
-#define RT_REGEN_MIN 1
-#endif
 // Background known at compile time (scene-specialised kernels): 0 unknown, 1 solid black
 #ifndef RT_SPEC_BG_BLACK
 #define RT_SPEC_BG_BLACK 0
 #endif
 
+// Sample stealing inside a warp (RT_STEAL).  A lane owns a pixel and its samples; paths differ in length, and
+// pixels differ systematically (a pixel that looks at the light or past the geometry ends its paths after one
+// segment), so the lanes of a warp run out of samples at different times — at the BENCH configuration 1.7 of
+// 32 lanes idled on average (profiles/r02_megakernel_v22_1024spp_ncu.md).  A lane with nothing left takes the
+// upper half of the unstarted samples of the lane that has most.  Streams are counter-based (pixel, sample,
+// segment), so the samples traced are exactly the same ones; what changes is which lane adds them up: the thief
+// parks what it had summed for its previous pixel in shared memory (one lane at a time, in a fixed order), and
+// every pixel's total is its owner's own sum plus what was parked for it.  No pixel without a steal changes by
+// a bit; the schedule is a function of the inputs only, so renders stay reproducible.
+#ifndef RT_STEAL
+#define RT_STEAL 1
+#endif
+#ifndef RT_STEAL_MIN
+#define RT_STEAL_MIN 4      // a victim keeps at least half of >= 4 unstarted samples; below that the tail is left alone
+#endif
+
 template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
 RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned char* smem) {
+    __shared__ float steal_parked[RT_STEAL ? 3 * RT_BLOCK : 1];   // per lane of the CTA: sums other lanes traced for its pixel
+    // A render the host may cancel (interactive.rs:236-251 always passes a cancel event): CTAs that have not started
+    // when the flag is raised do nothing, so a cancelled frame drains in the time of the CTAs already running.
+    if (P.cancel_flag != nullptr &&
+        __syncthreads_or(threadIdx.x == 0 && *reinterpret_cast<const volatile int*>(P.cancel_flag) != 0)) return;
     SmemLayout L = stage_scene<MODE>(P, smem);
     TexCtx X; X.perlin = L.perlin; X.perm = L.perm;
 
@@ -347,6 +364,17 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
 
     PixelCtx pc = pixel_setup<ROUNDS>(P, valid ? px : 0, valid ? py : 0);
     RngCtx R; R.ks = P.ks; R.pixel = pc.pixel; R.sample = 0;
+    const uint32_t own_pixel = pc.pixel;
+    PhiloxPre ppre = philox2x32_pre(pc.pixel, P.ks);   // round 0 of every PATH block of this pixel, but for the xor with c1
+    // 16-bit v jitter of the next sample this lane starts: the spare bytes of the previous sample's block 0
+    uint32_t vj_bits = __byte_perm(0u, 0u, 0);
+    {
+        const uint2 w = philox2x32_from<ROUNDS>(ppre, rt_ctr1(rt_vjit_sample((uint32_t)s_first), 0u, RT_TAG_PATH), P.ks);
+        vj_bits = __byte_perm(w.y, w.x, 0x0040);
+    }
+    int owner = lane;          // the lane of this warp whose pixel `sum` is being traced for
+    float* const parked = steal_parked + 96 * warp;
+    if (RT_STEAL) { parked[lane] = 0.0f; parked[lane + 32] = 0.0f; parked[lane + 64] = 0.0f; __syncwarp(); }
 
     // Path state.  Radiance is only ever picked up where a path ENDS (escape, light, depth
     // exhaustion): lights do not scatter and nothing else emits (src/material/*.rs), so
@@ -382,7 +410,7 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                     if (RT_SPEC_BG_BLACK) { s = s_last; break; }
                     vec3f bg;
                     if (__float_as_int(P.bg_a.w) == 0) {   // Sky: depends on the sample's direction
-                        const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1((uint32_t)s, 0u, RT_TAG_PATH), P.ks);
+                        const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(rt_vjit_sample((uint32_t)s), 0u, RT_TAG_PATH), P.ks);
                         const float vjit = RT_FIXED_JITTER(P) ? 32768.0f : u16lo_int(rnd);
                         camera_ray<SAMPLER, ROUNDS>(P, pc, (uint32_t)s, vjit, o, d, time);
                         bg = background_color(P, d);
@@ -394,17 +422,10 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         }
     }
 
-#pragma unroll 1
-    while (true) {
-        // ---- lanes whose path ended take the next sample of their pixel (bookkeeping only) ----
-        bool fresh = depth_left == 0.0f && s < s_last;
-        if (RT_REGEN_MIN > 1) {
-            const unsigned want = __ballot_sync(0xffffffffu, fresh), live = __ballot_sync(0xffffffffu, depth_left != 0.0f);
-            if ((want | live) == 0u) break;
-            if (live != 0u && __popc(want) < RT_REGEN_MIN) fresh = false;
-        } else {
-            if (!__any_sync(0xffffffffu, (depth_left != 0.0f) | (s < s_last))) break;
-        }
+    // One iteration of the path loop: lanes whose path ended take the next sample of their pixel (bookkeeping
+    // only), every lane with a path draws its segment's block and traces one segment.
+    auto iteration = [&]() {
+        const bool fresh = depth_left == 0.0f && s < s_last;
         if (fresh) {
             R.sample = (uint32_t)s;
             ctr1 = R.sample;
@@ -414,12 +435,15 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         }
         s += fresh ? 1 : 0;
         if (depth_left != 0.0f) {
-            // ---- the segment's random block: drawn here, by all lanes together ----
-            const uint2 rnd = philox2x32_ks<ROUNDS>(pc.pixel, ctr1, P.ks);   // == rt_ctr1(R.sample, seg, RT_TAG_PATH)
-            if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337
-                const float vjit = RT_FIXED_JITTER(P) ? 32768.0f : u16lo_int(rnd);
+            if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337; its v jitter came with the PREVIOUS sample's block 0
+                const float vjit = RT_FIXED_JITTER(P) ? 32768.0f : (float)(unsigned short)vj_bits;
                 camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d, time);
             }
+            // ---- the segment's random block: drawn here, by all lanes together.  Nothing before the hit record needs
+            // it (the spare bytes of a sample's block 0 are the NEXT sample's v jitter), so its ten dependent
+            // multiply-xor rounds are scheduled between the instructions of the closest hit instead of in front of them.
+            const uint2 rnd = philox2x32_from<ROUNDS>(ppre, ctr1, P.ks);   // == philox2x32_ks(pc.pixel, rt_ctr1(R.sample, seg, RT_TAG_PATH))
+            if (fresh) vj_bits = __byte_perm(rnd.y, rnd.x, 0x0040);
             RayT<float> r = make_ray(o, d, time);
             float t;
             int prim;
@@ -452,6 +476,73 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
                 }
             }
         }
+        };
+#define RT_LANE_BUSY ((depth_left != 0.0f) | (s < s_last))
+    if (!RT_STEAL) {
+#pragma unroll 1
+        while (__any_sync(0xffffffffu, RT_LANE_BUSY)) iteration();
+    } else {
+        const bool warp_has_pixels = __any_sync(0xffffffffu, valid);   // (a warp entirely outside the image has nothing to wait for)
+        for (;;) {
+            // the hot loop: every lane of the warp (that has a pixel at all) has a path or a sample to start
+            if (warp_has_pixels && __all_sync(0xffffffffu, RT_LANE_BUSY | !valid)) {
+#pragma unroll 1
+                do iteration(); while (__all_sync(0xffffffffu, RT_LANE_BUSY | !valid));
+            }
+            if (!__any_sync(0xffffffffu, RT_LANE_BUSY)) break;
+            // some lane has neither (the warp's tail): let it take samples over
+            bool stolen = false;
+            for (;;) {
+                const int rem = s_last - s;
+                const unsigned idle = __ballot_sync(0xffffffffu, valid && !(RT_LANE_BUSY));   // (lanes outside the image never take part)
+                if (idle == 0u) break;
+                const int most = __reduce_max_sync(0xffffffffu, rem);
+                if (most < RT_STEAL_MIN) break;      // unstarted samples only ever shrink: nothing worth taking, now or later
+                const int victim = __ffs(__ballot_sync(0xffffffffu, rem == most)) - 1, thief = __ffs(idle) - 1;
+                const int take = most >> 1;
+                const int v_last = __shfl_sync(0xffffffffu, s_last, victim), v_owner = __shfl_sync(0xffffffffu, owner, victim);
+                const uint32_t v_pixel = __shfl_sync(0xffffffffu, pc.pixel, victim);
+                const float v_row = __shfl_sync(0xffffffffu, pc.rowf, victim);
+                const float vx = __shfl_sync(0xffffffffu, pc.dir0.x, victim), vy = __shfl_sync(0xffffffffu, pc.dir0.y, victim),
+                            vz = __shfl_sync(0xffffffffu, pc.dir0.z, victim);
+                if (lane == victim) s_last -= take;
+                if (lane == thief) {
+                    // what this lane has summed belongs to `owner`'s pixel: park it (only this lane is active here)
+                    parked[owner] += sum.x; parked[owner + 32] += sum.y; parked[owner + 64] += sum.z;
+                    sum = mk3(0.0f, 0.0f, 0.0f);
+                    owner = v_owner;
+                    pc.pixel = v_pixel; pc.rowf = v_row; pc.dir0 = mk3(vx, vy, vz);
+                    R.pixel = v_pixel;
+                    ppre = philox2x32_pre(v_pixel, P.ks);
+                    s = v_last - take; s_last = v_last;
+                    const uint2 w = philox2x32_from<ROUNDS>(ppre, rt_ctr1(rt_vjit_sample((uint32_t)s), 0u, RT_TAG_PATH), P.ks);
+                    vj_bits = __byte_perm(w.y, w.x, 0x0040);
+                }
+                __syncwarp();
+                stolen = true;
+            }
+            if (!stolen) {
+                // nothing worth taking is left: the rest of the warp's tail runs as it is
+#pragma unroll 1
+                while (__any_sync(0xffffffffu, RT_LANE_BUSY)) iteration();
+                break;
+            }
+        }
+    }
+#undef RT_LANE_BUSY
+    if (RT_STEAL) {
+        // sums still held for another lane's pixel are parked one lane at a time, in lane order; then every pixel's
+        // total = what its owner summed itself (if it still owns it) + what was parked.  x + 0 = x: nothing changes
+        // for a pixel nobody helped with.
+        unsigned pending = __ballot_sync(0xffffffffu, owner != lane);
+        while (pending) {
+            const int l = __ffs(pending) - 1;
+            pending &= pending - 1;
+            if (lane == l) { parked[owner] += sum.x; parked[owner + 32] += sum.y; parked[owner + 64] += sum.z; }
+            __syncwarp();
+        }
+        if (owner != lane) sum = mk3(0.0f, 0.0f, 0.0f);
+        sum = mk3(sum.x + parked[lane], sum.y + parked[lane + 32], sum.z + parked[lane + 64]);
     }
     if (P.slices > 1) {
         // partial sum of this slice; reduce_slices_kernel adds the slices in order (deterministic)
@@ -459,7 +550,8 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         a[0] = sum.x; a[1] = sum.y; a[2] = sum.z;
     } else if (valid) {
         // (possibly a peer GPU's memory: the gather of a multi-GPU tile split happens here, over NVLink)
-        float* a = accum + 3 * (size_t)pc.pixel;
+        float* a = accum + 3 * (size_t)own_pixel;
+        if (P.final_scale != 0.0f) sum = mk3(sqrtf(P.final_scale * sum.x), sqrtf(P.final_scale * sum.y), sqrtf(P.final_scale * sum.z));
         if (P.overwrite) { a[0] = sum.x; a[1] = sum.y; a[2] = sum.z; }
         else { a[0] += sum.x; a[1] += sum.y; a[2] += sum.z; }
     }
@@ -486,6 +578,7 @@ __global__ void reduce_slices_kernel(const __grid_constant__ KParams P, float* _
         sx += a[0]; sy += a[1]; sz += a[2];
     }
     float* dst = accum + 3 * ((size_t)py * P.width + px);
+    if (P.final_scale != 0.0f) { sx = sqrtf(P.final_scale * sx); sy = sqrtf(P.final_scale * sy); sz = sqrtf(P.final_scale * sz); }
     if (P.overwrite) { dst[0] = sx; dst[1] = sy; dst[2] = sz; }
     else { dst[0] += sx; dst[1] += sy; dst[2] += sz; }
 }
@@ -735,6 +828,31 @@ __global__ void preview_expand_kernel(const float* __restrict__ accum, double* _
         r = sqrt(scale * (double)a[0]); g = sqrt(scale * (double)a[1]); b = sqrt(scale * (double)a[2]);
     }
     rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
+}
+
+// ---- progress words of a frame shared by several processes (rc_render_frame) ----
+// publish: everything this stream did before (the render kernel's stores into the peer's image) is visible
+// system-wide before the word changes
+__global__ void frame_publish_kernel(int* word, int value) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(word) = value;
+    __threadfence_system();
+}
+// wait until words[32 * i] >= target for i in [first, first + n); gives up after ~4 s of GPU time (a rank died:
+// the frame would never complete) and raises *timed_out instead of hanging the device
+__global__ void frame_wait_kernel(const int* words, int first, int n, int target, int* timed_out) {
+    if ((int)threadIdx.x >= n) return;
+    const volatile int* w = reinterpret_cast<const volatile int*>(words + 32 * (first + (int)threadIdx.x));
+    const long long t0 = clock64();
+    while (*w < target) {
+        __nanosleep(200);
+        if (clock64() - t0 > 8000000000LL) { *timed_out = 1; break; }
+    }
+    __threadfence_system();
+}
+__global__ void widen_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
 }
 
 __global__ void finalize_to_f64_kernel(const float* __restrict__ accum, double* __restrict__ rgb, size_t n, double scale) {

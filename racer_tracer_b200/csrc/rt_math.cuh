@@ -112,6 +112,29 @@ RT_D uint2 philox2x32_ks(uint32_t c0, uint32_t c1, const uint32_t* ks) {
     return make_uint2(c0, c1);
 }
 
+// The same block with round 0's multiplication hoisted: c0 is the pixel index, constant over all the blocks a
+// lane draws for one pixel.  philox2x32_from(philox2x32_pre(c0, ks), c1, ks) == philox2x32_ks(c0, c1, ks).
+struct PhiloxPre { uint32_t hi_k0, lo; };
+RT_D PhiloxPre philox2x32_pre(uint32_t c0, const uint32_t* ks) {
+    const uint64_t p = (uint64_t)PHILOX2_M * c0;
+    PhiloxPre q;
+    q.hi_k0 = (uint32_t)(p >> 32) ^ ks[0];
+    q.lo = (uint32_t)p;
+    return q;
+}
+template <int ROUNDS>
+RT_D uint2 philox2x32_from(PhiloxPre q, uint32_t c1, const uint32_t* ks) {
+    uint32_t c0 = q.hi_k0 ^ c1;
+    c1 = q.lo;
+#pragma unroll
+    for (int r = 1; r < ROUNDS; ++r) {
+        const uint64_t p = (uint64_t)PHILOX2_M * c0;
+        c0 = (uint32_t)(p >> 32) ^ ks[r] ^ c1;
+        c1 = (uint32_t)p;
+    }
+    return make_uint2(c0, c1);
+}
+
 // Counter layout (DESIGN.md "RNG streams"):
 //   c0 = pixel index (24 bits) | iteration j of a rejection loop << 24
 //   c1 = sample index (24 bits) | segment or bounce (6 bits) << 24 | stream tag << 30
@@ -119,13 +142,17 @@ RT_D uint2 philox2x32_ks(uint32_t c0, uint32_t c1, const uint32_t* ks) {
 // ONE PATH block per path segment: block e of a sample belongs to segment e (e = 0 is the primary
 // ray) and is drawn before the segment is intersected, by every lane of the warp together.  Its
 // upper 24 bits per word feed the scattering event at the END of that segment (hit number e + 1);
-// the low byte of each word is spare, and in block 0 the two spare bytes are the sample's v jitter.
-#define RT_TAG_PATH   0u   // segment e: scatter bits of hit e + 1; e = 0 also: low bytes -> 16-bit v jitter (cpu.rs:39-40)
+// the low byte of each word is spare, and in block 0 the two spare bytes are the NEXT sample's v jitter
+// (rt_vjit_sample).
+#define RT_TAG_PATH   0u   // segment e: scatter bits of hit e + 1; e = 0 also: low bytes -> 16-bit v jitter of the next sample (cpu.rs:39-40)
 #define RT_TAG_PIXEL  1u   // sample = segment = 0: x -> per-pixel u jitter (cpu.rs:35-36)
 #define RT_TAG_LENS   2u   // j = 0: (x, y) -> direct lens sample, low bytes -> 16-bit ray time; j >= 1: rejection iteration j
 #define RT_TAG_REJECT 3u   // (hit number b, iteration j): three 21-bit uniforms of a rejection iteration
 
 RT_HD uint32_t rt_ctr1(uint32_t sample, uint32_t bounce, uint32_t tag) { return sample | (bounce << 24) | (tag << 30); }
+// The sample whose PATH block 0 carries, in its two spare bytes, the v jitter of sample `s`: the one before it
+// (24-bit wrap for s = 0).  A sample's own block is therefore not needed before its first hit is shaded.
+RT_HD uint32_t rt_vjit_sample(uint32_t s) { return (s - 1u) & 0xFFFFFFu; }
 
 // 24-bit and 21-bit uniforms in [0,1): exactly representable in fp32 and f64
 RT_HD float u24(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }

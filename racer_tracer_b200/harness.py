@@ -880,6 +880,17 @@ def prepare_job(scene_path: str, config: Config | None = None, width=None, heigh
 # ---------------------------------------------------------------------------
 # The renderer handle: a thin, loud wrapper over the C ABI
 # ---------------------------------------------------------------------------
+class _DevicePointer:
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def device_view(ptr: int, n: int):
+    """A torch view (no copy) of n floats of device memory the library owns, e.g. rc_render_frame's image."""
+    import torch
+    return torch.as_tensor(_DevicePointer(ptr, n), device="cuda")
+
+
 class CudaRenderer:
     """Plays `impl Renderer for CudaRenderer` of the Rust shim:
     render(job, params) returns what CpuRenderer sends in BufferUpdate messages."""
@@ -966,6 +977,35 @@ class CudaRenderer:
 
     def shared_close(self, ptr: int):
         capi.check(self.lib, self.lib.rc_shared_close(self.ctx, C.c_void_p(ptr)))
+
+    # ---- the one-process-per-GPU tile split (rc_frame_* / rc_render_frame) ----
+    def frame_create(self, width: int, height: int, world: int):
+        """rank 0: -> (frame handle, 64-byte IPC handle for the other ranks)."""
+        f, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        capi.check(self.lib, self.lib.rc_frame_create(self.ctx, width, height, world, C.byref(f), handle))
+        return f.value, bytes(handle)
+
+    def frame_open(self, handle: bytes, width: int, height: int, rank: int, world: int) -> int:
+        f = C.c_void_p()
+        capi.check(self.lib, self.lib.rc_frame_open(self.ctx, (C.c_uint8 * 64).from_buffer_copy(handle), width, height,
+                                                    rank, world, C.byref(f)))
+        return f.value
+
+    def frame_close(self, frame: int):
+        capi.check(self.lib, self.lib.rc_frame_close(self.ctx, C.c_void_p(frame)))
+
+    def render_frame(self, params: rc_params, frame: int, want_device_ptr=False, out: np.ndarray | None = None, cancel=None):
+        """rc_render_frame.  Rank 0: returns the device pointer of the finished float image (want_device_ptr) and / or
+        fills `out` ((H, W, 3) float64, e.g. pinned); other ranks pass neither."""
+        dptr = C.c_void_p()
+        optr = None
+        if out is not None:
+            assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == params.height * params.width * 3
+            optr = out.ctypes.data_as(C.POINTER(C.c_double))
+        cptr = C.cast(C.pointer(cancel), C.POINTER(C.c_int32)) if cancel is not None else None
+        capi.check(self.lib, self.lib.rc_render_frame(self.ctx, C.byref(params), C.c_void_p(frame),
+                                                      C.byref(dptr) if want_device_ptr else None, optr, cptr))
+        return dptr.value if want_device_ptr else None
 
     def finalize(self, d_accum_ptr: int, width: int, height: int, samples: int, d_rgb_ptr: int):
         capi.check(self.lib, self.lib.rc_finalize(self.ctx, C.c_void_p(d_accum_ptr), width, height,

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Two (or more) processes, one GPU each, one frame: every rank stores its tiles into rank 0's frame buffer
-(rc_shared_alloc / rc_shared_open / rc_render_tiles_into) and rank 0 compares the frame with its own
-single-GPU render of the whole image.  Run under torchrun; prints IPC_TILES_OK on success.
+(rc_shared_alloc / rc_shared_open / rc_render_tiles_into, then the whole exchange behind the ABI:
+rc_frame_create / rc_frame_open / rc_render_frame) and rank 0 compares the frames with its own single-GPU renders.  Run under torchrun; prints IPC_TILES_OK on success.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/ipc_tiles_check.py
 """
+import ctypes as C
 import os
 import sys
 
@@ -48,6 +49,45 @@ for spec in (0, 2):
         assert np.array_equal(got, want), f"specialize={spec}: {np.abs(got - want).max()}"
     dist.barrier()
 r.shared_close(ptr)
+
+# ---- the same split behind the ABI: rc_frame_* + rc_render_frame.  Several frames are enqueued back to back with
+# no host synchronisation in between (the two images of the frame alternate; the progress words order the ranks),
+# each with another seed; rank 0 keeps a device copy of every finished image and checks them all at the end.
+if rank == 0:
+    frame, handle = r.frame_create(w, h, world)
+    hbuf = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+else:
+    hbuf = torch.empty(64, dtype=torch.uint8, device="cuda")
+dist.broadcast(hbuf, 0)
+if rank != 0:
+    frame = r.frame_open(bytes(hbuf.cpu().tolist()), w, h, rank, world)
+seeds = [3, 4, 5, 6, 7]
+kept = []
+for seed in seeds:
+    p = harness.make_params(w, h, spp, 20, seed=seed, rank=rank, world=world, specialize=2)
+    dptr = r.render_frame(p, frame, want_device_ptr=(rank == 0))
+    if rank == 0:   # a stream-ordered copy of the finished image (the frame's own image is reused two frames later)
+        keep = torch.empty(n, dtype=torch.float32, device="cuda")
+        keep.copy_(harness.device_view(dptr, n), non_blocking=True)
+        kept.append(keep)
+torch.cuda.synchronize()
+dist.barrier()
+if rank == 0:
+    for seed, keep in zip(seeds, kept):
+        got = keep.cpu().numpy().reshape(h, w, 3)
+        want = r.render(harness.make_params(w, h, spp, 20, seed=seed, specialize=2))
+        # sqrtf(sum / n) in the kernel's store vs sqrt in f64 of the same float sum: two roundings apart at most
+        assert np.allclose(got, want, rtol=3e-7, atol=1e-7), f"frame seed {seed}: {np.abs(got - want).max()}"
+    # the host-buffer form (what `e2e` times): f64 out, synchronous on rank 0
+out = np.empty((h, w, 3), dtype=np.float64) if rank == 0 else None
+p = harness.make_params(w, h, spp, 20, seed=11, rank=rank, world=world, specialize=2)
+r.render_frame(p, frame, out=out)
+torch.cuda.synchronize()
+dist.barrier()
+if rank == 0:
+    want = r.render(harness.make_params(w, h, spp, 20, seed=11, specialize=2))
+    assert np.allclose(out, want, rtol=3e-7, atol=1e-7), np.abs(out - want).max()
+r.frame_close(frame)
 r.close()
 if rank == 0:
     print("IPC_TILES_OK")

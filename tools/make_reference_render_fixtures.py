@@ -7,6 +7,9 @@ They are the only outputs of the reference that exist (SURVEY §4 "de-facto gold
 Block means remove most of their sampling noise, which makes them usable as a statistical pin for the oracle and
 the CUDA path: tests/test_reference_renders.py.  Runs only where /root/reference exists.
 
+For the two scenes with sharp silhouettes (clown, three_balls) the full-resolution image is kept as well, as the
+per-pixel sum R + G + B (uint16, <scene>_rgbsum.npz): the Q1 signature test needs single pixels, not block means.
+
     python tools/make_reference_render_fixtures.py
 """
 import os
@@ -34,3 +37,6 @@ if __name__ == "__main__":
         rgb = np.asarray(im.convert("RGB"), dtype=np.float64) / 255.0
         np.save(os.path.join(OUT, name + ".npy"), block_means(rgb).astype(np.float32))
         print("wrote", name, block_means(rgb).mean(axis=(0, 1)).round(4))
+        if name in ("clown", "three_balls"):
+            rgb8 = np.asarray(im.convert("RGB"), dtype=np.uint16)
+            np.savez_compressed(os.path.join(OUT, name + "_rgbsum.npz"), rgbsum=rgb8.sum(axis=2).astype(np.uint16))

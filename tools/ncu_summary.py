@@ -37,8 +37,8 @@ for k, vals in enumerate(rows[2:]):
         ("dram__bytes_read.sum", "HBM read"),
         ("dram__bytes_write.sum", "HBM written"),
         ("dram__bytes.sum.per_second", "HBM bandwidth"),
-        ("lts__t_bytes.sum", "L2 bytes"),
-        ("lts__t_bytes.sum.per_second", "L2 bandwidth"),
+        ("lts__t_sectors.sum", "L2 sectors (32 B each)"),
+        ("lts__t_sectors.sum.per_second", "L2 sector rate"),
         ("lts__t_sector_hit_rate.pct", "L2 hit rate"),
         ("l1tex__t_bytes.sum", "L1 bytes"),
         ("idc__request_cycles_active.avg.pct_of_peak_sustained_elapsed", "indexed-constant cache busy"),
