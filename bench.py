@@ -424,6 +424,13 @@ def main():
                                 "frac": achieved / fp32_tflops, "traffic": cap.get("dram_bytes_per_launch") if cap else None,
                                 "traffic_source": (cap.get("source") if cap else None),
                                 "ncu": cap,
+                                # what was actually ISSUED (ncu, same kernel and configuration) next to what is credited
+                                "frac_executed": (cap["fp32_tflops_executed"] / fp32_tflops) if cap and cap.get("fp32_tflops_executed") else None,
+                                "note": ("achieved = ALGORITHMIC flops (SURVEY §8(d): the reference algorithm's work per sample, oracle counters "
+                                         "x cost table) / time.  This path does not execute all of them: tiles whose frustum contains no "
+                                         "primitive trace nothing, opposite walls share one test, and BVH scenes walk a SAH tree instead of the "
+                                         "reference's median-split tree whose node tests the oracle counts — so the fraction can exceed what the "
+                                         "FP32 pipes issued (frac_executed) and, for scenes that are mostly culled, even 1."),
                                 "peak_source": "FFMA micro-benchmark in this run (rc_fp32_peak), per GPU",
                                 "flops_per_sample": A_used, "lane_ginstr_per_s_peak": lane_ginstr,
                                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_kind,

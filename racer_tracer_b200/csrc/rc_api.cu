@@ -41,20 +41,30 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    cudaError_t assign(const std::vector<T>& h) {
-        release();
+    size_t cap = 0;   // elements allocated (>= n): a re-upload of a scene of the same or a smaller size allocates nothing
+    // host -> device on `st` (asynchronous with respect to the host only for pinned memory; the caller synchronises
+    // the stream before `h` goes away)
+    cudaError_t assign(const std::vector<T>& h, cudaStream_t st = nullptr) {
+        if (h.size() > cap || !p) {
+            release();
+            if (h.empty()) return cudaSuccess;
+            cudaError_t e = cudaMalloc(&p, h.size() * sizeof(T));
+            if (e != cudaSuccess) return e;
+            cap = h.size();
+        }
         n = h.size();
         if (n == 0) return cudaSuccess;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-        if (e != cudaSuccess) return e;
-        return cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+        return cudaMemcpyAsync(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, st);
     }
     cudaError_t resize(size_t count) {
         if (count == n && p) return cudaSuccess;
+        if (count <= cap && p && count > 0) { n = count; return cudaSuccess; }
         release();
         n = count;
         if (n == 0) return cudaSuccess;
-        return cudaMalloc(&p, n * sizeof(T));
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
     }
     // scratch buffers that are reused call after call: grow, never shrink
     cudaError_t reserve(size_t count) { return (p && n >= count) ? cudaSuccess : resize(count); }
@@ -62,6 +72,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
+        cap = 0;
     }
 };
 
@@ -150,6 +161,9 @@ void free_scene(DeviceState& d) {
     for (auto a : d.arrays) cudaFreeArray(a);
     d.tex.clear();
     d.arrays.clear();
+}
+
+void free_tables(DeviceState& d) {
     d.prims.release(); d.prims_lin.release(); d.nodes.release(); d.textures.release(); d.instances.release();
     d.perlin.release(); d.perm.release(); d.prims_d.release(); d.prim_kind.release();
     d.prim_id.release(); d.nodes_d.release(); d.prim_inst.release(); d.instances_d.release();
@@ -542,6 +556,152 @@ int resolve_stats(rc_ctx* ctx) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// Tree quality.  A host hands over the tree it has; the reference's is a median split along a RANDOM axis
+// (src/bvh_node.rs:31-82), and one huge object — the Random scene's radius-1000 ground sphere — then inflates every
+// ancestor box.  The closest hit does not depend on the tree (exact ties aside, Q13), the number of boxes a ray
+// visits does: for instance-free scenes of RC_SAH_MIN_LEAVES leaves and more the library re-splits THE SAME LEAVES by
+// the surface-area heuristic (full sweep over three axes per node; same algorithm as harness._build_bvh_sah and
+// racer_host.cpp::build_bvh_sah) and keeps the result when its expected number of box tests per ray is at least
+// 10 % below the given tree's — so a tree that is already SAH-quality is walked exactly as passed.
+// Scenes with instances keep their tree: there the stored boxes decide visibility (Q14).  RC_KEEP_TREE=1: never.
+// ---------------------------------------------------------------------------
+#define RC_SAH_MIN_LEAVES 65
+struct ResplitScene {   // a re-ordered copy of the primitive arrays + the new nodes; `scene` points into it
+    rc_scene scene;
+    std::vector<int32_t> type, material, instance, order;
+    std::vector<double> data, aabb, motion;
+    std::vector<uint32_t> id;
+    std::vector<rc_bvh_node> nodes;
+};
+
+namespace {
+struct SahLeaf { double lo[3], hi[3]; int first, count; };
+
+double sah_area(const double* lo, const double* hi) {
+    const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return 2.0 * (dx * dy + dy * dz + dz * dx);
+}
+
+// expected box tests per ray ~ sum over nodes of area(node) / area(root)
+double sah_tree_cost(const rc_bvh_node* nodes, int n) {
+    const double root = sah_area(nodes[0].bmin, nodes[0].bmax);
+    double c = 0.0;
+    for (int i = 0; i < n; ++i) c += sah_area(nodes[i].bmin, nodes[i].bmax);
+    return root > 0.0 ? c / root : (double)n;
+}
+
+int sah_build(const std::vector<SahLeaf>& leaves, std::vector<int>& idx, int begin, int end, std::vector<rc_bvh_node>& nodes, std::vector<int>& leaf_order) {
+    const int me = (int)nodes.size();
+    nodes.push_back(rc_bvh_node());
+    const int m = end - begin;
+    if (m == 1) {
+        const SahLeaf& l = leaves[idx[begin]];
+        for (int a = 0; a < 3; ++a) { nodes[me].bmin[a] = l.lo[a]; nodes[me].bmax[a] = l.hi[a]; }
+        nodes[me].left = ~(int)leaf_order.size();   // patched to the primitive range afterwards
+        nodes[me].right = 1;
+        leaf_order.push_back(idx[begin]);
+        return me;
+    }
+    int best_axis = 0, best_k = 1;
+    double best_cost = 0.0;
+    bool have = false;
+    std::vector<int> srt(idx.begin() + begin, idx.begin() + end);
+    std::vector<double> rarea((size_t)m);
+    for (int axis = 0; axis < 3; ++axis) {
+        std::sort(srt.begin(), srt.end(), [&](int x, int y) {
+            const double kx = leaves[x].lo[axis] + leaves[x].hi[axis], ky = leaves[y].lo[axis] + leaves[y].hi[axis];
+            return kx < ky || (kx == ky && x < y);
+        });
+        double lo[3], hi[3];
+        for (int i = m - 1; i >= 1; --i) {      // area of the box of srt[i..m)
+            const SahLeaf& l = leaves[srt[i]];
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = i == m - 1 ? l.lo[a] : std::min(lo[a], l.lo[a]);
+                hi[a] = i == m - 1 ? l.hi[a] : std::max(hi[a], l.hi[a]);
+            }
+            rarea[i] = sah_area(lo, hi);
+        }
+        for (int k = 1; k < m; ++k) {           // left = srt[0..k)
+            const SahLeaf& l = leaves[srt[k - 1]];
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = k == 1 ? l.lo[a] : std::min(lo[a], l.lo[a]);
+                hi[a] = k == 1 ? l.hi[a] : std::max(hi[a], l.hi[a]);
+            }
+            const double cost = sah_area(lo, hi) * (double)k + rarea[k] * (double)(m - k);
+            if (!have || cost < best_cost) { have = true; best_cost = cost; best_axis = axis; best_k = k; }
+        }
+    }
+    std::sort(idx.begin() + begin, idx.begin() + end, [&](int x, int y) {
+        const double kx = leaves[x].lo[best_axis] + leaves[x].hi[best_axis], ky = leaves[y].lo[best_axis] + leaves[y].hi[best_axis];
+        return kx < ky || (kx == ky && x < y);
+    });
+    const int l = sah_build(leaves, idx, begin, begin + best_k, nodes, leaf_order);
+    const int r = sah_build(leaves, idx, begin + best_k, end, nodes, leaf_order);
+    nodes[me].left = l; nodes[me].right = r;
+    for (int a = 0; a < 3; ++a) {
+        nodes[me].bmin[a] = std::min(nodes[l].bmin[a], nodes[r].bmin[a]);
+        nodes[me].bmax[a] = std::max(nodes[l].bmax[a], nodes[r].bmax[a]);
+    }
+    return me;
+}
+}  // namespace
+
+// Returns true and fills `out` (out.scene = the scene to upload instead of *s) when the tree was replaced.
+static bool resplit_sah(const rc_scene* s, ResplitScene& out) {
+    if (s->n_nodes < 2 * RC_SAH_MIN_LEAVES - 1 || std::getenv("RC_KEEP_TREE") != nullptr) return false;
+    if (s->prim_instance && s->n_instances > 0)
+        for (int i = 0; i < s->n_prims; ++i) if (s->prim_instance[i] >= 0) return false;
+    std::vector<SahLeaf> leaves;
+    for (int i = 0; i < s->n_nodes; ++i) {
+        const rc_bvh_node& n = s->nodes[i];
+        if (n.left >= 0) continue;
+        SahLeaf l;
+        for (int a = 0; a < 3; ++a) { l.lo[a] = n.bmin[a]; l.hi[a] = n.bmax[a]; }
+        l.first = ~n.left; l.count = n.right;
+        leaves.push_back(l);
+    }
+    if ((int)leaves.size() < RC_SAH_MIN_LEAVES || leaves.size() > 200000) return false;
+    std::vector<int> idx(leaves.size()), leaf_order;
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+    out.nodes.clear();
+    out.nodes.reserve((size_t)s->n_nodes);
+    sah_build(leaves, idx, 0, (int)leaves.size(), out.nodes, leaf_order);
+    if (sah_tree_cost(out.nodes.data(), (int)out.nodes.size()) > 0.9 * sah_tree_cost(s->nodes, s->n_nodes)) return false;
+    // primitives into the new tree's depth-first leaf order
+    std::vector<int> first_new(leaf_order.size());
+    out.order.clear();
+    for (size_t k = 0; k < leaf_order.size(); ++k) {
+        const SahLeaf& l = leaves[leaf_order[k]];
+        first_new[k] = (int)out.order.size();
+        for (int j = 0; j < l.count; ++j) out.order.push_back(l.first + j);
+    }
+    if ((int)out.order.size() != s->n_prims) return false;   // a primitive outside every leaf: leave the scene alone
+    for (rc_bvh_node& n : out.nodes)
+        if (n.left < 0) { const int k = ~n.left; n.left = ~first_new[k]; n.right = leaves[leaf_order[k]].count; }
+    const int np = s->n_prims;
+    out.type.resize(np); out.material.resize(np); out.id.resize(np); out.data.resize(5 * (size_t)np);
+    out.instance.assign(np, -1);
+    if (s->prim_aabb) out.aabb.resize(6 * (size_t)np);
+    if (s->prim_motion) out.motion.resize(5 * (size_t)np);
+    for (int i = 0; i < np; ++i) {
+        const int src = out.order[i];
+        out.type[i] = s->prim_type[src]; out.material[i] = s->prim_material[src]; out.id[i] = s->prim_id[src];
+        std::memcpy(&out.data[5 * (size_t)i], s->prim_data + 5 * (size_t)src, 5 * sizeof(double));
+        if (s->prim_aabb) std::memcpy(&out.aabb[6 * (size_t)i], s->prim_aabb + 6 * (size_t)src, 6 * sizeof(double));
+        if (s->prim_motion) std::memcpy(&out.motion[5 * (size_t)i], s->prim_motion + 5 * (size_t)src, 5 * sizeof(double));
+    }
+    out.scene = *s;
+    out.scene.prim_type = out.type.data(); out.scene.prim_material = out.material.data(); out.scene.prim_id = out.id.data();
+    out.scene.prim_data = out.data.data();
+    out.scene.prim_instance = s->prim_instance ? out.instance.data() : nullptr;
+    out.scene.prim_aabb = s->prim_aabb ? out.aabb.data() : nullptr;
+    out.scene.prim_motion = s->prim_motion ? out.motion.data() : nullptr;
+    out.scene.nodes = out.nodes.data();
+    out.scene.n_nodes = (int32_t)out.nodes.size();
+    return true;
+}
+
 struct HostTables {   // everything rc_upload_scene derives from an rc_scene, before any device call
     std::vector<DevPrim> prims, prims_lin;
     std::vector<DevPrimD> prims_d;
@@ -837,6 +997,7 @@ int rc_destroy(rc_ctx* ctx) {
         cudaSetDevice(d.device);
         cudaDeviceSynchronize();
         free_scene(d);
+        free_tables(d);
         d.accum.release(); d.slice_buf.release(); d.out64.release(); d.counter.release();
         d.pp_in.release(); d.pp_mapped.release(); d.pp_rgba.release();
         if (d.ev_traced) cudaEventDestroy(d.ev_traced);
@@ -864,6 +1025,9 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     if (!ctx) return fail(RC_ERR_INVALID, "ctx is NULL");
     int rc = validate_scene(s);
     if (rc != RC_OK) return rc;
+    ResplitScene resplit;
+    const bool resplit_done = resplit_sah(s, resplit);
+    if (resplit_done) s = &resplit.scene;   // same leaves, better tree; rc_get_bvh reports it and the permutation
     HostTables t;
     build_tables(s, t);
     if (!t.instances.empty() && t.kp.n_cobj == 0 && s->n_nodes == 0)
@@ -888,6 +1052,7 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     // top-level objects = runs of primitives that share an object id (id >> 3; a Box's six sides) and a stored Aabb
     ctx->objects.clear();
     ctx->prim_order.clear();
+    if (resplit_done) ctx->prim_order = resplit.order;
     ctx->lbvh = false;
     ctx->n_prims = s->n_prims; ctx->n_perlin = s->n_perlin;
     ctx->instanced = !t.instances.empty();
@@ -910,21 +1075,25 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
     std::vector<DevTexture>& textures = t.textures; std::vector<float4>& perlin = t.perlin; std::vector<uint8_t>& perm = t.perm;
 
     for (auto& d : ctx->devs) {
-        free_scene(d);
+        // An interactive host re-uploads after every scene edit (main.rs:178-183): the table allocations are kept
+        // and refilled with stream-ordered copies — the stream also orders them after any render still reading the
+        // old tables — and the stream is drained once at the end instead of once per table.
         CUDA_TRY(cudaSetDevice(d.device));
-        CUDA_TRY(d.prims.assign(prims));
-        CUDA_TRY(d.prims_lin.assign(prims_lin));
-        CUDA_TRY(d.nodes.assign(nodes));
-        CUDA_TRY(d.textures.assign(textures));
-        CUDA_TRY(d.perlin.assign(perlin));
-        CUDA_TRY(d.perm.assign(perm));
-        CUDA_TRY(d.prims_d.assign(prims_d));
-        CUDA_TRY(d.prim_kind.assign(kinds));
-        CUDA_TRY(d.prim_id.assign(ids));
-        CUDA_TRY(d.nodes_d.assign(nodes_d));
-        CUDA_TRY(d.instances.assign(t.instances));
-        CUDA_TRY(d.instances_d.assign(t.instances_d));
-        CUDA_TRY(d.prim_inst.assign(t.prim_inst));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        free_scene(d);
+        CUDA_TRY(d.prims.assign(prims, d.stream));
+        CUDA_TRY(d.prims_lin.assign(prims_lin, d.stream));
+        CUDA_TRY(d.nodes.assign(nodes, d.stream));
+        CUDA_TRY(d.textures.assign(textures, d.stream));
+        CUDA_TRY(d.perlin.assign(perlin, d.stream));
+        CUDA_TRY(d.perm.assign(perm, d.stream));
+        CUDA_TRY(d.prims_d.assign(prims_d, d.stream));
+        CUDA_TRY(d.prim_kind.assign(kinds, d.stream));
+        CUDA_TRY(d.prim_id.assign(ids, d.stream));
+        CUDA_TRY(d.nodes_d.assign(nodes_d, d.stream));
+        CUDA_TRY(d.instances.assign(t.instances, d.stream));
+        CUDA_TRY(d.instances_d.assign(t.instances_d, d.stream));
+        CUDA_TRY(d.prim_inst.assign(t.prim_inst, d.stream));
         for (int i = 0; i < s->n_images; ++i) {
             // image textures as CUDA texture objects: point filter, clamp, u8 -> float/255
             // (src/texture/image.rs:28-51, Q21)
@@ -948,6 +1117,7 @@ int rc_upload_scene(rc_ctx* ctx, const rc_scene* s) {
             CUDA_TRY(cudaCreateTextureObject(&tex, &res, &td, nullptr));
             d.tex.push_back(tex);
         }
+        CUDA_TRY(cudaStreamSynchronize(d.stream));   // the host tables above go out of scope with this call
     }
     CUDA_TRY(cudaSetDevice(ctx->devs[0].device));
     ctx->has_scene = true;

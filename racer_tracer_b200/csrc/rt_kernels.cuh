@@ -838,15 +838,16 @@ __global__ void frame_publish_kernel(int* word, int value) {
     *reinterpret_cast<volatile int*>(word) = value;
     __threadfence_system();
 }
-// wait until words[32 * i] >= target for i in [first, first + n); gives up after ~4 s of GPU time (a rank died:
-// the frame would never complete) and raises *timed_out instead of hanging the device
+// wait until words[32 * i] >= target for i in [first, first + n); gives up after ~30 s of GPU time (a rank died:
+// the frame would never complete — ranks that are merely late, e.g. still compiling their kernel, are waited
+// for) and raises *timed_out instead of hanging the device
 __global__ void frame_wait_kernel(const int* words, int first, int n, int target, int* timed_out) {
     if ((int)threadIdx.x >= n) return;
     const volatile int* w = reinterpret_cast<const volatile int*>(words + 32 * (first + (int)threadIdx.x));
     const long long t0 = clock64();
     while (*w < target) {
         __nanosleep(200);
-        if (clock64() - t0 > 8000000000LL) { *timed_out = 1; break; }
+        if (clock64() - t0 > 60000000000LL) { *timed_out = 1; break; }
     }
     __threadfence_system();
 }

@@ -59,14 +59,18 @@ struct Reader {
     Reader(const uint8_t* d, size_t len) : p(d), n(len) {}
     int byte() { if (i >= n) throw Error("unexpected end of JPEG data"); return p[i++]; }
     int word() { int a = byte(); return (a << 8) | byte(); }
+    int starved = 0;                  // bytes of padding fed because the entropy data ran into a marker or the end
     int bit() {
         if (cnt == 0) {
-            int b = i < n ? p[i++] : 0;
+            bool real = i < n;
+            int b = real ? p[i++] : 0;
             if (b == 0xFF) {
                 int b2 = i < n ? p[i] : 0;
                 if (b2 == 0) ++i;                 // stuffed zero
-                else { --i; b = 0; }              // a marker: feed zeros, leave it for the caller
+                else { --i; b = 0; real = false; }   // a marker: feed zeros, leave it for the caller
             }
+            // a decoder may look a few bits past the last code; a scan that keeps reading there is truncated
+            if (!real && ++starved > 8) throw Error("premature end of JPEG entropy data");
             acc = (uint32_t)b; cnt = 8;
         }
         --cnt;
@@ -154,6 +158,7 @@ inline Image decode(const uint8_t* data, size_t len) {
         } else if (m == 0xC0 || m == 0xC1) {
             if (r.byte() != 8) throw Error("only 8-bit JPEG is supported");
             height = r.word(); width = r.word();
+            if (width <= 0 || height <= 0 || (long long)width * height > (1LL << 28)) throw Error("bad image size");
             int nc = r.byte();
             if (nc != 1 && nc != 3) throw Error("only 1- or 3-component JPEG is supported");
             comps.resize(nc);
@@ -161,7 +166,7 @@ inline Image decode(const uint8_t* data, size_t len) {
                 c.id = r.byte();
                 int hv = r.byte();
                 c.h = hv >> 4; c.v = hv & 15; c.tq = r.byte();
-                if (c.h < 1 || c.v < 1 || c.tq > 3) throw Error("bad frame component");
+                if (c.h < 1 || c.v < 1 || c.h > 4 || c.v > 4 || c.tq > 3) throw Error("bad frame component");
                 hmax = c.h > hmax ? c.h : hmax; vmax = c.v > vmax ? c.v : vmax;
             }
         } else if (m == 0xC2 || (m >= 0xC5 && m <= 0xCF && m != 0xC8)) {
@@ -174,7 +179,10 @@ inline Image decode(const uint8_t* data, size_t len) {
             if (ns != (int)comps.size()) throw Error("non-interleaved scans are not supported");
             for (int k = 0; k < ns; ++k) {
                 int id = r.byte(), t = r.byte();
-                for (auto& c : comps) if (c.id == id) { c.td = t >> 4; c.ta = t & 15; }
+                if ((t >> 4) > 3 || (t & 15) > 3) throw Error("bad entropy table selector in the scan header");   // dc[] / ac[] hold 4 tables
+                bool found = false;
+                for (auto& c : comps) if (c.id == id) { c.td = t >> 4; c.ta = t & 15; found = true; }
+                if (!found) throw Error("scan component is not in the frame");
             }
             r.i = end;
             break;
@@ -193,6 +201,7 @@ inline Image decode(const uint8_t* data, size_t len) {
         for (int mx = 0; mx < mcus_x; ++mx) {
             if (restart && to_restart == 0) {
                 r.reset_bits();
+                r.starved = 0;
                 // skip to the RSTn marker
                 while (r.i + 1 < r.n && !(r.p[r.i] == 0xFF && r.p[r.i + 1] >= 0xD0 && r.p[r.i + 1] <= 0xD7)) ++r.i;
                 r.i += 2;
@@ -204,6 +213,7 @@ inline Image decode(const uint8_t* data, size_t len) {
                     for (int bx = 0; bx < c.h; ++bx) {
                         double coef[64] = {0};
                         int t = decode_symbol(r, dc[c.td]);
+                        if (t < 0 || t > 11) throw Error("bad DC coefficient size");   // baseline: at most 11 bits (extend() shifts by it)
                         int diff = t ? extend(r.bitsn(t), t) : 0;
                         c.pred += diff;
                         coef[0] = (double)c.pred * qt[c.tq][0];

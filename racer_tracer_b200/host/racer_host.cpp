@@ -9,6 +9,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <sstream>
 
 #include "jpeg_baseline.hpp"
@@ -902,14 +903,29 @@ size_t get_highest_divdable(size_t value, size_t div) {   // cpu_scaled.rs:17-23
 }
 }  // namespace
 
-CudaRenderer::CudaRenderer(const RenderConfig& config, const GpuConfig& gpu) : config_(config), gpu_(gpu) {
+namespace {
+// ONE rc_ctx per process and device list, shared by the full and the preview renderer (both are made by
+// make_renderer, main.rs:127-129, and never render at the same time): the scene is uploaded once, whichever of the
+// two renders first after a change.  Destroyed with its last renderer.
+std::shared_ptr<rc_ctx> acquire_context(const GpuConfig& gpu) {
+    static std::mutex mutex;
+    static std::map<std::vector<int32_t>, std::weak_ptr<rc_ctx>> live;
+    std::lock_guard<std::mutex> lock(mutex);
+    std::weak_ptr<rc_ctx>& slot = live[gpu.devices];
+    if (std::shared_ptr<rc_ctx> alive = slot.lock()) return alive;
+    rc_ctx* raw = nullptr;
     const int32_t* devs = gpu.devices.empty() ? nullptr : gpu.devices.data();
-    check(rc_create(devs, gpu.devices.empty() ? 1 : (int32_t)gpu.devices.size(), &ctx_), "rc_create");
+    check(rc_create(devs, gpu.devices.empty() ? 1 : (int32_t)gpu.devices.size(), &raw), "rc_create");
+    std::shared_ptr<rc_ctx> fresh(raw, [](rc_ctx* c) { rc_destroy(c); });
+    slot = fresh;
+    return fresh;
 }
+}  // namespace
 
-CudaRenderer::~CudaRenderer() {
-    if (ctx_) rc_destroy(ctx_);
-}
+CudaRenderer::CudaRenderer(const RenderConfig& config, const GpuConfig& gpu)
+    : config_(config), gpu_(gpu), shared_(acquire_context(gpu)), ctx_(shared_.get()) {}
+
+CudaRenderer::~CudaRenderer() {}
 
 rc_stats CudaRenderer::stats() const {
     rc_stats s;

@@ -212,6 +212,7 @@ protected:
     rc_params params(const RenderData& rd) const;
     RenderConfig config_;
     GpuConfig gpu_;
+    std::shared_ptr<rc_ctx> shared_;   // one context per process and device list, shared with the other renderer
     rc_ctx* ctx_ = nullptr;
 };
 

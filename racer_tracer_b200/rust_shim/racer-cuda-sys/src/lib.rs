@@ -93,7 +93,18 @@ pub struct rc_stats {
     pub n_devices: i32, pub sm_count: i32, pub sm_clock_khz: i32, pub specialized: i32,
 }
 
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct rc_tone_map {
+    pub type_: i32, pub reserved: i32, pub max_white: f64, pub hable: [f64; 6], pub exposure_bias: f64,
+    pub linear_white_point: f64, pub aces_in: [f64; 9], pub aces_out: [f64; 9],
+}
+pub const RC_TONE_NONE: i32 = 0;
+pub const RC_TONE_REINHARD: i32 = 1;
+pub const RC_TONE_HABLE: i32 = 2;
+pub const RC_TONE_ACES: i32 = 3;
+
 #[repr(C)] pub struct rc_ctx { _private: [u8; 0] }
+#[repr(C)] pub struct rc_frame { _private: [u8; 0] }
 
 extern "C" {
     pub fn rc_create(devices: *const i32, n: i32, out: *mut *mut rc_ctx) -> c_int;
@@ -112,6 +123,14 @@ extern "C" {
     pub fn rc_shared_close(ctx: *mut rc_ctx, d_ptr: *mut c_void) -> c_int;
     pub fn rc_render_accumulate(ctx: *mut rc_ctx, params: *const rc_params, d_accum: *mut f32, cancel: *const i32) -> c_int;
     pub fn rc_finalize(ctx: *mut rc_ctx, d_accum: *const f32, width: i32, height: i32, samples: i32, d_rgb: *mut f32) -> c_int;
+    pub fn rc_postprocess(ctx: *mut rc_ctx, tone_map: *const rc_tone_map, rgb: *const f64, width: i32, height: i32,
+                          rgba: *mut u8, rgb_out: *mut f64) -> c_int;
+    pub fn rc_frame_create(ctx: *mut rc_ctx, width: i32, height: i32, world: i32, out: *mut *mut rc_frame, handle: *mut u8) -> c_int;
+    pub fn rc_frame_open(ctx: *mut rc_ctx, handle: *const u8, width: i32, height: i32, rank: i32, world: i32,
+                         out: *mut *mut rc_frame) -> c_int;
+    pub fn rc_frame_close(ctx: *mut rc_ctx, frame: *mut rc_frame) -> c_int;
+    pub fn rc_render_frame(ctx: *mut rc_ctx, params: *const rc_params, frame: *mut rc_frame, d_rgb: *mut *const f32,
+                           out_rgb: *mut f64, cancel: *const i32) -> c_int;
     pub fn rc_primary_aov(ctx: *mut rc_ctx, params: *const rc_params, precision: i32, id: *mut u32, t: *mut f64,
                           normal: *mut f64, point: *mut f64) -> c_int;
     pub fn rc_partition(params: *const rc_params, part: i32, parts: i32, out: *mut i32) -> c_int;

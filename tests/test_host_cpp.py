@@ -89,6 +89,28 @@ def test_baseline_jpeg_decoder_against_pillow(racer_render, tmp_path):
     assert abs(meta["byte_sum"] - int(im.sum())) / im.size < 0.5
 
 
+def test_malformed_jpeg_is_an_error_not_a_crash(racer_render, tmp_path):
+    """The reference decodes through the memory-safe `image` crate; the host's own decoder must reject what it
+    cannot index: entropy-table selectors above 3 in the scan header, a scan component that is not in the frame, a
+    truncated file.  Exit code 21 = TracerError::FailedToOpenImage (src/error.rs:71-97), never a signal."""
+    good = open(os.path.join(IMAGES, "earthmap.jpg"), "rb").read()
+    sos = good.index(b"\xff\xda")
+    ns = good[sos + 4]
+    assert ns == 3
+    bad_selector = bytearray(good); bad_selector[sos + 6] = 0x4F            # component 1: td = 4, ta = 15
+    bad_component = bytearray(good); bad_component[sos + 5] = 0x77          # an id the frame header does not list
+    cases = {"selector.jpg": bytes(bad_selector), "component.jpg": bytes(bad_component), "truncated.jpg": good[:sos + 40]}
+    scene = open(scene_path("noise_and_textures")).read()
+    for name, data in cases.items():
+        d = tmp_path / name.split(".")[0]
+        (d / "scenes").mkdir(parents=True)
+        (d / "resources" / "images").mkdir(parents=True)
+        (d / "resources" / "images" / "earthmap.jpg").write_bytes(data)
+        (d / "scenes" / "scene.yml").write_text(scene)
+        r = run(racer_render, "--config", CONFIG, "--scene", str(d / "scenes" / "scene.yml"), "--dump-flat", str(d / "flat.json"), check=False)
+        assert r.returncode == 21, (name, r.returncode, r.stderr[-300:])
+
+
 def test_reference_style_yaml_and_errors(racer_render, tmp_path):
     """The reference's own files use `---`, values on the next line and spaced flow lists
     (resources/scenes/*.yml, config.yml:28-29); errors map to the reference's TracerError ordinals

@@ -15,8 +15,10 @@ already fail it (its floor sits at 60 dB).  Measured with the oracle (DESIGN §6
 three_balls renders give 59.97 .. 60.73 dB, four renders against the published image 59.74 .. 60.02 dB — the
 published image is one more draw from the same distribution to within the spread of the floor estimate itself
 (+-0.5 dB), which is where TOL_DB = 1.5 comes from.  The same holds per pixel: the FULL-RESOLUTION PSNR against
-the published image equals the one between two of our renders to 0.1 dB (40.34 vs 40.34 dB, three_balls), which
-pins the per-pixel variance, i.e. the sample count and the jitter model.
+the published image equals the one between two of our renders (three_balls 40.34 vs 40.34 dB; clown: six pairs of
+ours 37.1 .. 37.6 dB, four of ours against the published image 37.3 .. 37.5 dB — the estimate is dominated by the
+jagged silhouette pixels of quirk Q1 and scatters by +-0.25 dB, hence the 0.6 dB bound), which pins the per-pixel
+variance, i.e. the sample count and the jitter model.
 
 Perlin gradient tables are drawn from an unseeded RNG in the reference (texture/noise.rs:44-55), so for
 `emissive` and `noise_and_textures` the two renders of ours also use different tables: the floor then contains the
@@ -79,7 +81,7 @@ def check_equivalence(name, imgs8):
         pub = published_pixels(name)
         la, lb = (i.mean(axis=2) for i in imgs8)
         f_full, g_full = psnr(la, lb), psnr_of_mean_mse([(la, pub), (lb, pub)])
-        assert abs(g_full - f_full) < 0.3, (name, "full-resolution PSNR vs published", g_full, "between our renders", f_full)
+        assert abs(g_full - f_full) < 0.6, (name, "full-resolution PSNR vs published", g_full, "between our renders", f_full)
         out.update(floor_full=f_full, got_full=g_full)
     return out
 
