@@ -195,6 +195,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         return name;
     };
     // slab pairs (below) need every ray origin inside the slab: rectangles only, nothing instanced, a pinhole
+    bool nothing_yet = n_sph == 0;   // no test emitted so far: best_t / bestf still hold their start values
     const bool slab_scene_ok = kp.n_cobj == 0 && !kp.lens_enabled && std::getenv("RC_SPEC_NO_SLAB") == nullptr;
     for (int g = 0; g < 3; ++g) {
         const int begin = kp.lin_end[g], end = kp.lin_end[g + 1];
@@ -245,8 +246,6 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
             o << "        pair_t(" << spec_float(p.b.x) << ", " << spec_float(q.b.x) << ", " << on[g] << ", " << in[g] << ", t" << s0 << ", t" << s1 << ");\n";
             o << "        const float ts" << s0 << " = fmaxf(t" << s0 << ", t" << s1 << ");   // slab pair " << s0 << " / " << s1 << "\n";
             o << "        fma2_bcast(ts" << s0 << ", " << da[g] << ", " << db[g] << ", " << va[s0 - begin] << ", " << vb[s0 - begin] << ", xa" << s0 << ", xb" << s0 << ");\n";
-            o << "        const float fi" << s0 << " = fmaf(t" << s1 << " > t" << s0 << " ? 1.0f : 0.0f, " << spec_float((float)(s1 - s0)) << ", "
-              << spec_float((float)s0) << ");\n";
         }
         for (size_t u = 0; u < rest.size(); ++u) {
             const int i = rest[u];
@@ -288,11 +287,19 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         }
         if (s0 >= 0) {
             const float4 c = kp.crect_bounds[g][s0 - begin];
-            o << "        rect_closest_fma(ts" << s0 << ", xa" << s0 << ", xb" << s0 << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", fi" << s0
-              << ", best_t, bestf);\n";
+            o << "        rect_closest_fma_pair(ts" << s0 << ", xa" << s0 << ", xb" << s0 << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", t" << s0
+              << ", t" << s1 << ", " << spec_float((float)s0) << ", " << spec_float((float)(s1 - s0)) << ", best_t, bestf);\n";
         }
+        if (s0 >= 0) nothing_yet = false;
         for (int i : rest) {
             const float4 c = kp.crect_bounds[g][i - begin];
+            if (chain && fidx && nothing_yet) {   // the first test of the function: selects between literals
+                o << "        rect_closest_first(t" << i << ", xa" << i << ", xb" << i << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", "
+                  << spec_float((float)i) << ", best_t, bestf);\n";
+                nothing_yet = false;
+                continue;
+            }
+            nothing_yet = false;
             if (chain && fidx)
                 o << "        rect_closest_fma(t" << i << ", xa" << i << ", xb" << i << ", " << spec_float(c.y) << ", " << spec_float(c.w) << ", "
                   << spec_float((float)i) << ", best_t, bestf);\n";

@@ -229,7 +229,11 @@ template <int SAMPLER, int ROUNDS, bool TEX, class Scene>
 RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const RngCtx& R, int prim,
                     const RayT<float>& r, float t, uint32_t bounce, uint2 rnd, vec3f& o, vec3f& d,
                     vec3f& T, vec3f& emit) {
-    Hit h = make_hit(S, prim, r, t);
+    Hit h = make_hit(S, prim, r, t, X.k_two);
+    // The next segment starts at the hit point.  Assigned here, unconditionally: a path that ends below never reads
+    // its origin again, and this way the point is formed in the origin's registers instead of being copied into them
+    // by the surviving lanes (`r` holds its own copy of the old origin).
+    o = h.p;
     float4 pb = S.pb(prim), pc = S.pc(prim);
     // the material kind as a float (n.w of the table): one float compare instead of mask + integer compare
     const float mat = S.pn(prim).w;
@@ -246,7 +250,7 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
     if (RT_HAS_MAT(RT_MAT_LAMBERTIAN) && (mat == (float)RT_MAT_LAMBERTIAN || !(RT_HAS_MAT(RT_MAT_METAL) || RT_HAS_MAT(RT_MAT_DIELECTRIC)))) {  // lambertian.rs:25-39
         vec3f rv;
         if (SAMPLER == 1) rv = unit_vector(reject_in_unit_sphere<ROUNDS>(R, bounce));
-        else rv = sphere_direct_w(rnd.x, rnd.y);
+        else rv = sphere_direct_w(rnd.x, rnd.y, X.k_phi);
         nd = h.n + rv;
         // near_zero, vec3.rs:127-130: all three components below 1e-8 (rv = -n; one draw in 2^24) -> the normal.
         // As arithmetic (nd + k n, k = 1 in that case: what is left of nd vanishes against the unit normal)
@@ -288,7 +292,6 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
     }
     mul2(T.x, T.y, col.x, col.y, T.x, T.y);
     T.z = T.z * col.z;
-    o = h.p;
     d = nd;
     return true;
 }
@@ -337,8 +340,14 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     // when the flag is raised do nothing, so a cancelled frame drains in the time of the CTAs already running.
     if (P.cancel_flag != nullptr &&
         __syncthreads_or(threadIdx.x == 0 && *reinterpret_cast<const volatile int*>(P.cancel_flag) != 0)) return;
-    SmemLayout L = stage_scene<MODE>(P, smem);
+    __shared__ float reg_consts[2];
+    if (threadIdx.x == 0) { reg_consts[0] = 2.0f; reg_consts[1] = 6.283185307179586f / 16777216.0f; }
+    SmemLayout L = stage_scene<MODE>(P, smem);    // (ends with the barrier that publishes reg_consts)
     TexCtx X; X.perlin = L.perlin; X.perm = L.perm;
+    {   // volatile: a plain load would be folded back into the literal (the only value ever stored there)
+        const volatile float* rc = reg_consts;
+        X.k_two = rc[0]; X.k_phi = rc[1];   // held in registers across the path loop, see TexCtx
+    }
 
     // CTA -> (tile, slice of the sample range).  With one GPU there are thousands of tiles and
     // slices == 1; when the tiles are shared out over several GPUs each tile's samples are cut
@@ -433,7 +442,8 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
             T = mk3(1.0f, 1.0f, 1.0f);
             depth_left = (float)P.max_depth;
         }
-        s += fresh ? 1 : 0;
+        // (a predicated add: `s += fresh ? 1 : 0` compiled to a zeroed register, a predicated move and an add)
+        asm("{\n\t.reg .pred pf;\n\tsetp.ne.s32 pf, %1, 0;\n\t@pf add.s32 %0, %0, 1;\n\t}" : "+r"(s) : "r"((int)fresh));
         if (depth_left != 0.0f) {
             if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337; its v jitter came with the PREVIOUS sample's block 0
                 const float vjit = RT_FIXED_JITTER(P) ? 32768.0f : (float)(unsigned short)vj_bits;

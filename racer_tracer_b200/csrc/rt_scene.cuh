@@ -415,6 +415,49 @@ RT_D void rect_closest_fma(float t, float xa, float xb, float ha, float hb, floa
         : "+f"(best_t), "+f"(best_index) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "f"(index));
 }
 
+// The FIRST test of a generated closest hit: nothing has been hit yet (best_t = RT_NO_HIT, index -1), so the two
+// results are selects between literals instead of updates of running values — two instructions fewer than the
+// general form, whose multiply-adds with the known start values ptxas does not fold.  `t <= RT_NO_HIT` stays: a
+// ray parallel to the plane has t = +-inf or NaN.
+RT_D void rect_closest_first(float t, float xa, float xb, float ha, float hb, float index, float& best_t, float& best_index) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.f32 p, %2, %4;\n\t"
+        "setp.le.and.f32 p, %3, %5, p;\n\t"
+        "setp.ge.and.f32 p, %6, 0f3A83126F, p;\n\t"   /* t >= 0.001f */
+        "setp.le.and.f32 p, %6, 0f7F61B1E6, p;\n\t"   /* t <= RT_NO_HIT (3e38f) */
+        "selp.f32 %0, %6, 0f7F61B1E6, p;\n\t"
+        "selp.f32 %1, %7, 0fBF800000, p;\n\t}"
+        : "=f"(best_t), "=f"(best_index) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "f"(index));
+}
+
+// The update for a SLAB PAIR (rc_spec.cuh): `t` = max(t_lo, t_hi) is the distance of whichever of the two parallel
+// walls lies in front of the ray, and the index that goes with it is `base` (wall lo) or `base + step` (wall hi,
+// when t_hi > t_lo).  The choice is one FSET (1.0 / 0.0) and the predicated move an FADD / FFMA with an immediate,
+// instead of compare + select between two literals (one of which costs a register move per iteration) + move.
+RT_D void rect_closest_fma_pair(float t, float xa, float xb, float ha, float hb, float t_lo, float t_hi, float base, float step,
+                                float& best_t, float& best_index) {
+    if (step == 1.0f)   // (a literal in generated code: neighbouring table entries, the usual case — an add needs no second literal)
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 w;\n\t"
+        "setp.le.f32 p, %2, %4;\n\t"
+        "setp.le.and.f32 p, %3, %5, p;\n\t"
+        "setp.ge.and.f32 p, %6, 0f3A83126F, p;\n\t"   /* t >= 0.001f */
+        "setp.le.and.f32 p, %6, %0, p;\n\t"
+        "set.gt.f32.f32 w, %8, %7;\n\t"
+        "@p fma.rn.f32 %0, %6, 0f3F800000, 0f00000000;\n\t"
+        "@p add.f32 %1, w, %9;\n\t}"
+        : "+f"(best_t), "+f"(best_index) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "f"(t_lo), "f"(t_hi), "f"(base));
+    else
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 w;\n\t"
+        "setp.le.f32 p, %2, %4;\n\t"
+        "setp.le.and.f32 p, %3, %5, p;\n\t"
+        "setp.ge.and.f32 p, %6, 0f3A83126F, p;\n\t"   /* t >= 0.001f */
+        "setp.le.and.f32 p, %6, %0, p;\n\t"
+        "set.gt.f32.f32 w, %8, %7;\n\t"
+        "@p fma.rn.f32 %0, %6, 0f3F800000, 0f00000000;\n\t"
+        "@p fma.rn.f32 %1, w, %10, %9;\n\t}"
+        : "+f"(best_t), "+f"(best_index) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "f"(t_lo), "f"(t_hi), "f"(base), "f"(step));
+}
+
 // Packed FP32 (sm_100a FFMA2 / FADD2 / FMUL2: two fp32 lanes per instruction, one issue slot, scalar operands
 // broadcast).  The pipe spends two cycles on them, so the FP32 peak is unchanged (tools/micro/ffma2_bench.cu:
 // 71 vs 73 TFLOP/s) — but this kernel is bound by ISSUE slots, not by the FMA pipe (34 % busy), and two
@@ -805,7 +848,7 @@ struct Hit {
 };
 
 template <class Scene>
-RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT<float>& r, float t) {
+RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT<float>& r, float t, float k_two = 2.0f) {
     Hit h;
     fma2_bcast(t, r.d.x, r.d.y, r.o.x, r.o.y, h.p.x, h.p.y);   // Ray::at
     h.p.z = fmaf(t, r.d.z, r.o.z);
@@ -830,7 +873,7 @@ RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT
         h.front_face = dn < 0.0f;   // dot(d, axis) < 0, geometry.rs:49-56
         // +1 if dn < 0 else -1, on the FMA pipe: sat(-dn * 3e38) is 1 or 0 (|dn| below 3e-39 — an fp32 subnormal —
         // would give a fraction; a ray that parallel to the plane has no hit to shade)
-        const float sgn = fmaf(2.0f, __saturatef(dn * -3.0e38f), -1.0f);
+        const float sgn = fmaf(k_two, __saturatef(dn * -3.0e38f), -1.0f);
         h.outward = N;
         mul2_bcast(sgn, N.x, N.y, h.n.x, h.n.y);
         h.n.z = sgn * N.z;
@@ -844,13 +887,13 @@ RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT
 // WORLD normal (rotate_y.rs:51-63, Q15); Translate adds the offset and runs set_face_normal
 // again on the already-flipped normal (translate.rs:34-37, Q15).
 template <class Scene>
-RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t) {
+RT_D Hit make_hit(const Scene& S, int prim, const RayT<float>& r, float t, float k_two = 2.0f) {
     float4 a = S.pa(prim), b = S.pb(prim);
     const int inst = kinds_inst(b.z);
-    if (!RT_HAS_INSTANCES || inst < 0) return make_hit_local(S, prim, a, b, r, t);
+    if (!RT_HAS_INSTANCES || inst < 0) return make_hit_local(S, prim, a, b, r, t, k_two);
     const DevInstance in = S.instances()[inst];
     const RayT<float> lr = to_local(in, r);
-    Hit h = make_hit_local(S, prim, a, b, lr, t);
+    Hit h = make_hit_local(S, prim, a, b, lr, t, k_two);
     if (in.flags & 1) {
         const float s = in.sin_theta, c = in.cos_theta;
         h.p = mk3(c * h.p.x + s * h.p.z, h.p.y, -s * h.p.x + c * h.p.z);
@@ -928,6 +971,12 @@ RT_D float perlin_turbulence(const float4* grad, const uint8_t* perm, vec3f p, i
 struct TexCtx {            // where the Perlin tables live for this kernel
     const float4* perlin;  // n_perlin x 256
     const uint8_t* perm;   // n_perlin x 768
+    // Two literals of the shading code that share an instruction with another literal (FFMA takes one immediate), so
+    // one of the two has to sit in a register.  Left to itself ptxas re-creates that register in every iteration of
+    // the path loop (a MOV / HFMA2 per use); the megakernel loads them once, from shared memory, which ptxas cannot
+    // fold back into an immediate.  Same values either way.
+    float k_two = 2.0f;                                   // make_hit_local: face sign
+    float k_phi = 6.283185307179586f / 16777216.0f;       // sphere_direct_w: 24-bit integer -> angle
 };
 
 // Texture::value for a non-solid texture index (solid colours are folded into
@@ -1000,14 +1049,14 @@ RT_D vec3f sphere_direct(float u1, float u2) {
 
 // sphere_direct(u24(wx), u24(wy)) with the integer -> uniform scalings folded into the
 // multiply-adds (same values: u24 is exact in fp32 and the scale factors are powers of two)
-RT_D vec3f sphere_direct_w(uint32_t wx, uint32_t wy) {
+RT_D vec3f sphere_direct_w(uint32_t wx, uint32_t wy, float k_phi = 6.283185307179586f / 16777216.0f) {
     // (w >> 8 as the high word of w * 2^24: an IMAD.HI on the FMA pipe instead of a shift on the ALU pipe)
     wx = __umulhi(wx, 1u << 24); wy = __umulhi(wy, 1u << 24);
     // 1 - 2 u1, in [-1 + 2^-23, 1]; as multiply (exact: a power of two) + add with immediates, so that no constant
     // has to be put into a register with a MOV on the ALU pipe
     const float z = __fadd_rn(1.0f, __fmul_rn((float)wx, -1.0f / 8388608.0f));
     const float r = fast_sqrt(fmaf(-z, z, 1.0f));                                       // |z| <= 1 exactly: never negative
-    const float phi = fmaf((float)wy, 6.283185307179586f / 16777216.0f, -3.14159265358979323846f);
+    const float phi = fmaf((float)wy, k_phi, -3.14159265358979323846f);
     return mk3(-r * __cosf(phi), -r * __sinf(phi), z);
 }
 

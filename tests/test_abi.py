@@ -185,16 +185,19 @@ def test_opposite_walls_become_one_test_only_when_every_ray_starts_between_them(
     only floor / ceiling; with a lens, or in a scene with spheres or instanced boxes, none."""
     from conftest import scene_path
     job = harness.prepare_job(scene_path("cornell_box"), cfg, 64, 64)
+    def n_tests(src):   # rectangle tests of the closest hit, whichever form of the update each one uses
+        return src.count("rect_closest_fma(") + src.count("rect_closest_fma_pair(") + src.count("rect_closest_first(")
     inside = _spec_source(cuda_lib, job, camera=job.camera.origin)
-    assert inside.count("// slab pair") == 2 and inside.count("rect_closest_fma(") == 4
+    assert inside.count("// slab pair") == 2 and n_tests(inside) == 4 and inside.count("rect_closest_fma_pair(") == 2
+    assert inside.count("rect_closest_first(") == 1    # the first test selects between literals
     _compile_like_the_library(inside, tmp_path)
     left_of_the_box = _spec_source(cuda_lib, job, camera=(-100.0, 278.0, -800.0))
-    assert left_of_the_box.count("// slab pair") == 1 and left_of_the_box.count("rect_closest_fma(") == 5
+    assert left_of_the_box.count("// slab pair") == 1 and n_tests(left_of_the_box) == 5
     assert "pair_t(0.0f, 555.0f, r.o.y" in left_of_the_box and "fmaxf(t1, t2)" in left_of_the_box
     above = _spec_source(cuda_lib, job, camera=(278.0, 900.0, 278.0))
     assert above.count("// slab pair") == 1 and "pair_t(0.0f, 555.0f, r.o.x" in above
     no_camera = _spec_source(cuda_lib, job)            # origin (0, 0, 0): on the walls, not between them
-    assert no_camera.count("// slab pair") == 0 and no_camera.count("rect_closest_fma(") == 6
+    assert no_camera.count("// slab pair") == 0 and n_tests(no_camera) == 6
     for other in ("sandbox_boxes", "emissive"):
         j = harness.prepare_job(scene_path(other), cfg, 64, 64)
         assert "// slab pair" not in _spec_source(cuda_lib, j, camera=j.camera.origin)
