@@ -327,6 +327,12 @@ int check_params(const rc_params* p) {
     return RC_OK;
 }
 
+// KParams::vstep from the camera and the (screen) height behind inv_hm1: vertical / ((H - 1) * 65536), in f64
+void set_vstep(KParams& kp, int screen_height) {
+    const double s = 1.0 / ((double)(screen_height - 1) * 65536.0);
+    kp.vstep = make_float4((float)(kp.cam.vertical.x * s), (float)(kp.cam.vertical.y * s), (float)(kp.cam.vertical.z * s), 0.0f);
+}
+
 // Fill the per-launch part of KParams for participant `part` of `parts`.
 void partition(KParams& kp, const rc_params* p, int part, int parts) {
     kp.width = p->width; kp.height = p->height;
@@ -336,6 +342,7 @@ void partition(KParams& kp, const rc_params* p, int part, int parts) {
     for (int r = 0; r < 10; ++r) kp.ks[r] = kp.key + (uint32_t)r * PHILOX2_W;
     kp.inv_wm1 = 1.0f / (float)(p->width - 1); kp.inv_hm1 = 1.0f / (float)(p->height - 1);
     kp.wm1 = (float)(p->width - 1);
+    set_vstep(kp, p->height);
     kp.px_scale_x = kp.px_scale_y = 1;
     kp.tile_w = RT_TILE_W; kp.tile_h = RT_TILE_H;
     kp.slices = 1; kp.slice_buf = nullptr;
@@ -409,6 +416,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
             kp.px_scale_x = ctx->preview_sw; kp.px_scale_y = ctx->preview_sh;
             kp.wm1 = (float)(ctx->preview_w - 1);
             kp.inv_wm1 = 1.0f / (float)(ctx->preview_w - 1); kp.inv_hm1 = 1.0f / (float)(ctx->preview_h - 1);
+            set_vstep(kp, ctx->preview_h);
         }
         // direct tile split: every device stores its pixels into device 0's buffer (peer memory) itself
         const bool direct = n_dev > 1 && p->split == RC_SPLIT_TILES && ctx->multi.peer_write_ok && p->variant == RC_VARIANT_MEGAKERNEL;

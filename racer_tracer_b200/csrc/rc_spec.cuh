@@ -123,7 +123,8 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
         else if (mode == RT_MODE_GLOBAL_BVH) o << "#define RT_MIN_BLOCKS RT_MIN_BLOCKS_GLOBAL_BVH\n";   // see rt_kernels.cuh
         o << "#include \"rt_scene.cuh\"\n";
-        o << "RT_D int spec_closest_hit(const RayT<float>&, int, float&) { return -1; }   // constant-table scenes only\n";
+        o << "RT_D int spec_closest_hit(const RayT<float>&, int, float&, const TexCtx&) { return -1; }   // constant-table scenes only\n";
+        o << "#define RT_SPEC_REG_CONSTS 0\nRT_D void spec_reg_consts(float*) {}\n";
         o << "#define RT_SPECIALIZED 1\n";
         o << "#define RT_SPEC_MATS " << mats_mask << "\n";
         o << "#define RT_FIXED_JITTER(P) 0\n";
@@ -146,6 +147,36 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     o << "#define RT_SPEC_BG_BLACK " << (black ? 1 : 0) << "\n";
     o << "#define RT_HAS_INSTANCES " << (kp.n_cobj > 0 ? 1 : 0) << "\n";
     o << "#define RT_HAS_LENS " << (kp.lens_enabled ? 1 : 0) << "\n";   // part of the source, hence of the cache key
+    // Scene origin of the kernel.  In a rectangle-only scene without textures nothing but the closest hit and the
+    // hit record ever looks at a POSITION, and both only at differences to rectangle centres and planes.  The kernel
+    // therefore traces in coordinates relative to the most common rectangle centre of each axis (Cornell: the centre
+    // of the box): for every rectangle centred there `origin - centre` is the origin itself — one FADD less per axis
+    // and ray.  Camera origin, plane constants (tests and the staged table's, from the same literal) and centres are
+    // shifted; directions, distances and colours are what they were up to fp32 rounding.
+    double shift[3] = {0.0, 0.0, 0.0};
+    const bool shift_ok = (prims_mask & 1) == 0 && kp.n_cobj == 0 && !tex && std::getenv("RC_SPEC_NO_SHIFT") == nullptr &&
+                          std::getenv("RC_SPEC_SELECT") == nullptr && std::getenv("RC_SPEC_INT_INDEX") == nullptr;
+    if (shift_ok) o << "#define RT_SPEC_SNAP_TABLE 1\n";    // (see spec_snap_row below)
+    if (shift_ok) {
+        std::map<float, int> votes[3];
+        for (int g = 0; g < 3; ++g)
+            for (int i = kp.lin_end[g]; i < kp.lin_end[g + 1]; ++i) {
+                const float4 c = kp.crect_bounds[g][i - kp.lin_end[g]];
+                ++votes[g == 2 ? 1 : 0][c.x];    // in-plane axis a: x for the xy and xz groups, y for the yz group
+                ++votes[g == 0 ? 1 : 2][c.z];    // in-plane axis b: y for the xy group, z for the others
+            }
+        for (int ax = 0; ax < 3; ++ax) {
+            int best = 0;
+            for (auto& kv : votes[ax])
+                if (kv.second > best) { best = kv.second; shift[ax] = (double)kv.first; }
+        }
+        if (shift[0] != 0.0 || shift[1] != 0.0 || shift[2] != 0.0)
+            o << "#define RT_SPEC_SHIFT mk3(" << spec_float((float)shift[0]) << ", " << spec_float((float)shift[1]) << ", " << spec_float((float)shift[2]) << ")\n";
+    }
+    // plane constant / centre of a rectangle in the kernel's coordinates (same literal wherever it is used)
+    auto plane = [&](int i, int g) { return (float)((double)kp.cprims[i].b.x - shift[2 - g]); };
+    auto centre_a = [&](float c, int g) { return (float)((double)c - shift[g == 2 ? 1 : 0]); };
+    auto centre_b = [&](float c, int g) { return (float)((double)c - shift[g == 0 ? 1 : 2]); };
     if (const char* e = std::getenv("RC_STEAL")) o << "#define RT_STEAL " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
     o << "#include \"rt_scene.cuh\"\n";
@@ -153,7 +184,18 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     // closest-hit update are predicated FFMAs on the FMA pipe (rect_closest_fma); with spheres around, the
     // index stays an integer (rect_closest)
     const bool fidx = (prims_mask & 1) == 0 && std::getenv("RC_SPEC_SELECT") == nullptr && std::getenv("RC_SPEC_INT_INDEX") == nullptr;
-    o << "RT_D int spec_closest_hit(const RayT<float>& r, int last_prim, float& best_t) {\n";
+    o << "RT_D int spec_closest_hit(const RayT<float>& r, int last_prim, float& best_t, const TexCtx& X) {\n";
+    o << "    (void)X;\n";
+    // literals handed to the kernel as register constants (TexCtx::k_spec): the plane pairs of slab pairs
+    std::vector<float> reg_consts;
+    auto reg_pair = [&](float k1, float k2) {   // -> the two operand expressions
+        for (size_t j = 0; j + 1 < reg_consts.size(); j += 2)
+            if (reg_consts[j] == k1 && reg_consts[j + 1] == k2) return std::make_pair("X.k_spec[" + std::to_string(j) + "]", "X.k_spec[" + std::to_string(j + 1) + "]");
+        if (reg_consts.size() + 2 > 4 || std::getenv("RC_SPEC_NO_REG_CONSTS") != nullptr) return std::make_pair(spec_float(k1), spec_float(k2));
+        reg_consts.push_back(k1); reg_consts.push_back(k2);
+        const size_t j = reg_consts.size() - 2;
+        return std::make_pair("X.k_spec[" + std::to_string(j) + "]", "X.k_spec[" + std::to_string(j + 1) + "]");
+    };
     o << "    int best = -1;\n    best_t = RT_NO_HIT;\n    (void)last_prim;\n";
     if (fidx) o << "    float bestf = -1.0f;\n";
     const int n_sph = kp.lin_end[0];
@@ -186,6 +228,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     const char* db[3] = {"r.d.y", "r.d.z", "r.d.z"};
     std::map<std::string, std::string> rel;   // "r.o.x - 277.5f" -> variable name
     auto rel_origin = [&](const char* axis, float centre) {
+        if (centre == 0.0f) return std::string(axis);    // (the kernel's origin is this rectangle's centre on that axis)
         std::string key = std::string(axis) + " - " + spec_float(centre);
         auto it = rel.find(key);
         if (it != rel.end()) return it->second;
@@ -193,6 +236,17 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         o << "    const float " << name << " = " << key << ";\n";
         rel[key] = name;
         return name;
+    };
+    // The two in-plane coordinates of ONE rectangle, t * (d_a, d_b) + (oc_a, oc_b): one packed multiply-add when the
+    // operands already sit in register pairs — the ray direction is held as (x, y), z, so that is the xy group —
+    // and two scalar ones otherwise: building a pair costs a MOV per operand on the ALU pipe, which made the packed
+    // form of the xz / yz groups 2.5 - 3 instructions against 2 (RC_SPEC_PACK_ALL=1: packed everywhere, as before).
+    const bool pack_all = std::getenv("RC_SPEC_PACK_ALL") != nullptr;
+    auto coords = [&](const std::string& t, int g, const std::string& oca, const std::string& ocb, const std::string& xa, const std::string& xb) {
+        if (g == 0 || pack_all)
+            o << "        fma2_bcast(" << t << ", " << da[g] << ", " << db[g] << ", " << oca << ", " << ocb << ", " << xa << ", " << xb << ");\n";
+        else
+            o << "        " << xa << " = fmaf(" << t << ", " << da[g] << ", " << oca << "); " << xb << " = fmaf(" << t << ", " << db[g] << ", " << ocb << ");\n";
     };
     // slab pairs (below) need every ray origin inside the slab: rectangles only, nothing instanced, a pinhole
     bool nothing_yet = n_sph == 0;   // no test emitted so far: best_t / bestf still hold their start values
@@ -203,8 +257,8 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         std::vector<std::string> va(end - begin), vb(end - begin);
         for (int i = begin; i < end; ++i) {
             const float4 c = kp.crect_bounds[g][i - begin];
-            va[i - begin] = rel_origin(oa[g], c.x);
-            vb[i - begin] = rel_origin(ob[g], c.z);
+            va[i - begin] = rel_origin(oa[g], centre_a(c.x, g));
+            vb[i - begin] = rel_origin(ob[g], centre_b(c.z, g));
         }
         o << "    {\n";
         const bool chain = std::getenv("RC_SPEC_SELECT") == nullptr;   // predicate chain (default) or candidate + select reduction
@@ -243,9 +297,12 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
             const DevPrim& p = kp.cprims[s0];
             const DevPrim& q = kp.cprims[s1];
             o << "        float t" << s0 << ", t" << s1 << ", xa" << s0 << ", xb" << s0 << ";\n";
-            o << "        pair_t(" << spec_float(p.b.x) << ", " << spec_float(q.b.x) << ", " << on[g] << ", " << in[g] << ", t" << s0 << ", t" << s1 << ");\n";
+            (void)p; (void)q;
+            const auto kk = reg_pair(plane(s0, g), plane(s1, g));
+            o << "        pair_t(" << kk.first << ", " << kk.second << ", " << on[g] << ", " << in[g] << ", t" << s0 << ", t" << s1 << ");   // planes "
+              << spec_float(plane(s0, g)) << ", " << spec_float(plane(s1, g)) << "\n";
             o << "        const float ts" << s0 << " = fmaxf(t" << s0 << ", t" << s1 << ");   // slab pair " << s0 << " / " << s1 << "\n";
-            o << "        fma2_bcast(ts" << s0 << ", " << da[g] << ", " << db[g] << ", " << va[s0 - begin] << ", " << vb[s0 - begin] << ", xa" << s0 << ", xb" << s0 << ");\n";
+            coords("ts" + std::to_string(s0), g, va[s0 - begin], vb[s0 - begin], "xa" + std::to_string(s0), "xb" + std::to_string(s0));
         }
         for (size_t u = 0; u < rest.size(); ++u) {
             const int i = rest[u];
@@ -256,7 +313,8 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
                 const DevPrim& q = kp.cprims[j];
                 const float4 c2 = kp.crect_bounds[g][j - begin];
                 o << "        float t" << i << ", t" << j << ", xa" << i << ", xa" << j << ", xb" << i << ", xb" << j << ";\n";
-                o << "        pair_t(" << spec_float(p.b.x) << ", " << spec_float(q.b.x) << ", " << on[g] << ", " << in[g] << ", t" << i << ", t" << j << ");\n";
+                (void)q;
+                o << "        pair_t(" << spec_float(plane(i, g)) << ", " << spec_float(plane(j, g)) << ", " << on[g] << ", " << in[g] << ", t" << i << ", t" << j << ");\n";
                 auto centres = [&](const char* axis, float ca1, float ca2, const std::string& v1, const std::string& v2, const char* tag) {
                     if (ca1 == ca2) return std::make_pair(v1, v2);      // one shared scalar, broadcast
                     const std::string n1 = std::string(tag) + std::to_string(i), n2 = std::string(tag) + std::to_string(j);
@@ -264,17 +322,18 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
                     o << "        pair_oc(" << axis << ", " << spec_float(ca1) << ", " << spec_float(ca2) << ", " << n1 << ", " << n2 << ");\n";
                     return std::make_pair(n1, n2);
                 };
-                const auto pa = centres(oa[g], c.x, c2.x, va[i - begin], va[j - begin], "pa");
-                const auto pb = centres(ob[g], c.z, c2.z, vb[i - begin], vb[j - begin], "pb");
+                const auto pa = centres(oa[g], centre_a(c.x, g), centre_a(c2.x, g), va[i - begin], va[j - begin], "pa");
+                const auto pb = centres(ob[g], centre_b(c.z, g), centre_b(c2.z, g), vb[i - begin], vb[j - begin], "pb");
                 o << "        pair_x(t" << i << ", t" << j << ", " << da[g] << ", " << pa.first << ", " << pa.second << ", xa" << i << ", xa" << j << ");\n";
                 o << "        pair_x(t" << i << ", t" << j << ", " << db[g] << ", " << pb.first << ", " << pb.second << ", xb" << i << ", xb" << j << ");\n";
                 ++u;
                 continue;
             }
-            o << "        const float t" << i << " = (" << spec_float(p.b.x) << " - " << on[g] << ") * " << in[g] << ";\n";
+            (void)p;
+            o << "        const float t" << i << " = (" << spec_float(plane(i, g)) << " - " << on[g] << ") * " << in[g] << ";\n";
             if (packed) {   // one rectangle: its two in-plane coordinates are the two lanes
                 o << "        float xa" << i << ", xb" << i << ";\n";
-                o << "        fma2_bcast(t" << i << ", " << da[g] << ", " << db[g] << ", " << va[i - begin] << ", " << vb[i - begin] << ", xa" << i << ", xb" << i << ");\n";
+                coords("t" + std::to_string(i), g, va[i - begin], vb[i - begin], "xa" + std::to_string(i), "xb" + std::to_string(i));
                 continue;
             }
             if (chain) {
@@ -390,6 +449,28 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     }
     if (fidx) o << "    best = __float2int_rn(bestf);\n";
     o << "    return best;\n}\n";
+    o << "#define RT_SPEC_REG_CONSTS " << reg_consts.size() << "\n";
+    o << "RT_D void spec_reg_consts(float* out) {\n    (void)out;\n";
+    for (size_t j = 0; j < reg_consts.size(); ++j) o << "    out[" << j << "] = " << spec_float(reg_consts[j]) << ";\n";
+    o << "}\n";
+    if (shift_ok) {
+        // Rectangle-only scenes: the hit record puts the hit point back onto the plane the TEST used (rt_scene.cuh
+        // make_hit_local) as p * M + K with M = 1 - N (0 on the plane's axis, 1 on the others) and K = k N, k the
+        // plane constant in the kernel's coordinates from the same literal as the test's: a packed and a scalar
+        // multiply-add instead of a dot product, a subtraction and three multiply-adds, same bits (p_axis * 0 + k = k,
+        // p * 1 + 0 = p).  The CTA patches its staged table once: row a = (M.x, M.y, K.x, K.y), b.x = K.z, c.w = M.z
+        // (bounds, plane constant and object id, which a rectangle's hit record and shading do not read).
+        o << "RT_D void spec_snap_row(int i, float4& a, float& bx, float& cw) {\n    switch (i) {\n";
+        for (int g = 0; g < 3; ++g)
+            for (int i = kp.lin_end[g]; i < kp.lin_end[g + 1]; ++i) {
+                const int ax = 2 - g;   // plane axis
+                const std::string k = spec_float(plane(i, g));
+                o << "        case " << i << ": a = make_float4(" << (ax == 0 ? "0.0f" : "1.0f") << ", " << (ax == 1 ? "0.0f" : "1.0f") << ", "
+                  << (ax == 0 ? k : std::string("0.0f")) << ", " << (ax == 1 ? k : std::string("0.0f")) << "); bx = " << (ax == 2 ? k : std::string("0.0f"))
+                  << "; cw = " << (ax == 2 ? "0.0f" : "1.0f") << "; break;\n";
+            }
+        o << "    }\n}\n";
+    }
     o << "#define RT_SPECIALIZED 1\n";
     o << "#define RT_SPEC_MATS " << mats_mask << "\n";
     o << "#define RT_HAS_MOTION " << (any_motion ? 1 : 0) << "\n";

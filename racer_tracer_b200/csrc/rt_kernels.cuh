@@ -83,9 +83,9 @@ RT_D SmemLayout stage_scene(const KParams& P, unsigned char* smem) {
 #endif
 
 template <int MODE, class Scene>
-RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& t) {
+RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int last_prim, float& t, const TexCtx& X = TexCtx()) {
 #ifdef RT_SPECIALIZED
-    if constexpr (MODE == RT_MODE_CONST_LINEAR) return spec_closest_hit(r, last_prim, t);
+    if constexpr (MODE == RT_MODE_CONST_LINEAR) return spec_closest_hit(r, last_prim, t, X);
 #else
     if constexpr (MODE == RT_MODE_CONST_LINEAR) return closest_hit_linear<true>(P, S, r, last_prim, t);
 #endif
@@ -97,33 +97,37 @@ RT_D int closest_hit(const KParams& P, const Scene& S, const RayT<float>& r, int
 // Ray generation: src/renderer/cpu.rs:35-40 + Camera::get_ray (camera.rs:326-337)
 // ---------------------------------------------------------------------------
 struct PixelCtx {
-    vec3f dir0;        // upper_left_corner + u*horizontal - origin, fixed per pixel (Q1)
+    vec3f dir0;        // upper_left_corner + u*horizontal - origin (fixed per pixel, Q1) - (row / (H-1)) * vertical:
+                       // the direction of the pixel's ray with v jitter 0
     uint32_t pixel;
     int px, py;
-    float rowf;        // (float)(py * px_scale_y): the row term of v (cpu.rs:39-40)
 };
 
 template <int ROUNDS>
 RT_D PixelCtx pixel_setup(const KParams& P, int px, int py) {
     PixelCtx c;
     c.px = px; c.py = py;
-    c.rowf = (float)(py * P.px_scale_y);
     c.pixel = (uint32_t)(py * P.width + px);
     float ujit = 0.5f;
     if (!RT_FIXED_JITTER(P)) ujit = u24(philox2x32_ks<ROUNDS>(c.pixel, rt_ctr1(0u, 0u, RT_TAG_PIXEL), P.ks).x);
     float u = ((float)(px * P.px_scale_x) + ujit) / P.wm1;  // once per pixel, cpu.rs:35-36 (cpu_scaled.rs:55-56)
     // cam.upper_left_corner holds (upper_left_corner - origin), formed in f64 on the host
     c.dir0 = P.cam.upper_left_corner + u * P.cam.horizontal;
+    c.dir0 = c.dir0 - ((float)(py * P.px_scale_y) * P.inv_hm1) * P.cam.vertical;   // the row term of v (cpu.rs:39-40)
     return c;
 }
 
 // Primary ray of one sample.  `w` = the sample's start block (x -> v jitter).
 template <int SAMPLER, int ROUNDS>
 RT_D void camera_ray(const KParams& P, const PixelCtx& c, uint32_t sample, float vjit16, vec3f& o, vec3f& d, float& time) {
-    // vjit16 = the v jitter times 65536 (an integer: the scaling is exact, so the fused form rounds like add(py, jitter))
-    float v = fmaf(vjit16, 1.0f / 65536.0f, c.rowf) * P.inv_hm1;  // cpu.rs:39-40 (cpu_scaled.rs:59-60)
-    d = c.dir0 - v * P.cam.vertical;
+    // cpu.rs:39-40 (cpu_scaled.rs:59-60): v = (row + jitter) / (H - 1), direction = .. - v * vertical.  The row's share
+    // is in c.dir0 (once per pixel); the sample's share is vjit16 — the v jitter times 65536, an integer — times
+    // P.vstep = vertical / ((H - 1) * 65536), formed in f64 on the host: three multiply-adds per primary ray.
+    d = mk3(fmaf(-vjit16, P.vstep.x, c.dir0.x), fmaf(-vjit16, P.vstep.y, c.dir0.y), fmaf(-vjit16, P.vstep.z, c.dir0.z));
     o = P.cam.origin;
+#ifdef RT_SPEC_SHIFT
+    o = o - RT_SPEC_SHIFT;   // scene-specialised kernels may trace relative to another origin (rc_spec.cuh)
+#endif
     time = P.cam.time_a;
     if (RT_HAS_MOTION && P.has_motion && !RT_FIXED_JITTER(P)) {
         // camera.rs:335: random_double_range(time_a, time_b); the draw is the spare 16 bits of LENS block 0
@@ -250,7 +254,7 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
     if (RT_HAS_MAT(RT_MAT_LAMBERTIAN) && (mat == (float)RT_MAT_LAMBERTIAN || !(RT_HAS_MAT(RT_MAT_METAL) || RT_HAS_MAT(RT_MAT_DIELECTRIC)))) {  // lambertian.rs:25-39
         vec3f rv;
         if (SAMPLER == 1) rv = unit_vector(reject_in_unit_sphere<ROUNDS>(R, bounce));
-        else rv = sphere_direct_w(rnd.x, rnd.y, X.k_phi);
+        else rv = sphere_direct_w(rnd.x, rnd.y, X.k_phi, X.k_one);
         nd = h.n + rv;
         // near_zero, vec3.rs:127-130: all three components below 1e-8 (rv = -n; one draw in 2^24) -> the normal.
         // As arithmetic (nd + k n, k = 1 in that case: what is left of nd vanishes against the unit normal)
@@ -333,6 +337,7 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
 #define RT_STEAL_MIN 4      // a victim keeps at least half of >= 4 unstarted samples; below that the tail is left alone
 #endif
 
+
 template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
 RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned char* smem) {
     __shared__ float steal_parked[RT_STEAL ? 3 * RT_BLOCK : 1];   // per lane of the CTA: sums other lanes traced for its pixel
@@ -340,13 +345,22 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     // when the flag is raised do nothing, so a cancelled frame drains in the time of the CTAs already running.
     if (P.cancel_flag != nullptr &&
         __syncthreads_or(threadIdx.x == 0 && *reinterpret_cast<const volatile int*>(P.cancel_flag) != 0)) return;
-    __shared__ float reg_consts[2];
-    if (threadIdx.x == 0) { reg_consts[0] = 2.0f; reg_consts[1] = 6.283185307179586f / 16777216.0f; }
+    __shared__ float reg_consts[7];
+    if (threadIdx.x == 0) {
+        reg_consts[0] = 2.0f; reg_consts[1] = 6.283185307179586f / 16777216.0f; reg_consts[2] = 1.0f;
+#ifdef RT_SPECIALIZED
+        spec_reg_consts(reg_consts + 3);
+#endif
+    }
     SmemLayout L = stage_scene<MODE>(P, smem);    // (ends with the barrier that publishes reg_consts)
     TexCtx X; X.perlin = L.perlin; X.perm = L.perm;
     {   // volatile: a plain load would be folded back into the literal (the only value ever stored there)
         const volatile float* rc = reg_consts;
-        X.k_two = rc[0]; X.k_phi = rc[1];   // held in registers across the path loop, see TexCtx
+        X.k_two = rc[0]; X.k_phi = rc[1]; X.k_one = rc[2];   // held in registers across the path loop, see TexCtx
+#ifdef RT_SPECIALIZED
+#pragma unroll
+        for (int j = 0; j < RT_SPEC_REG_CONSTS; ++j) X.k_spec[j] = rc[3 + j];
+#endif
     }
 
     // CTA -> (tile, slice of the sample range).  With one GPU there are thousands of tiles and
@@ -431,10 +445,27 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         }
     }
 
-    // One iteration of the path loop: lanes whose path ended take the next sample of their pixel (bookkeeping
-    // only), every lane with a path draws its segment's block and traces one segment.
+#ifdef RT_SPEC_SNAP_TABLE
+    // The path loop of a rectangle-only scene reads the staged table's rows in another layout (and, with
+    // RT_SPEC_SHIFT, in the kernel's own coordinates): rc_spec.cuh, spec_snap_row.  The tile test above read the
+    // table as uploaded; every thread of the CTA passes both barriers.
+    __syncthreads();
+    if ((int)threadIdx.x < P.n_prims) {
+        float* row = const_cast<float*>(reinterpret_cast<const float*>(L.prims + threadIdx.x));
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        float bx = 0.f, cw = 0.f;
+        spec_snap_row((int)threadIdx.x, a, bx, cw);
+        row[0] = a.x; row[1] = a.y; row[2] = a.z; row[3] = a.w; row[4] = bx; row[11] = cw;
+    }
+    __syncthreads();
+#endif
+
+    // One iteration of the path loop, for a lane that has a path or a sample to start (RT_LANE_BUSY: every loop below
+    // only lets such lanes in): a lane whose path ended takes the next sample of its pixel (bookkeeping only), then
+    // every lane draws its segment's block and traces one segment.  ONE body for all loops: what a sample
+    // contributes must not depend on which loop traced it (ptxas contracts multiply-adds per code copy).
     auto iteration = [&]() {
-        const bool fresh = depth_left == 0.0f && s < s_last;
+        const bool fresh = depth_left == 0.0f;      // no path: then there is a sample (the lane is busy)
         if (fresh) {
             R.sample = (uint32_t)s;
             ctr1 = R.sample;
@@ -444,100 +475,105 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         }
         // (a predicated add: `s += fresh ? 1 : 0` compiled to a zeroed register, a predicated move and an add)
         asm("{\n\t.reg .pred pf;\n\tsetp.ne.s32 pf, %1, 0;\n\t@pf add.s32 %0, %0, 1;\n\t}" : "+r"(s) : "r"((int)fresh));
-        if (depth_left != 0.0f) {
-            if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337; its v jitter came with the PREVIOUS sample's block 0
-                const float vjit = RT_FIXED_JITTER(P) ? 32768.0f : (float)(unsigned short)vj_bits;
-                camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d, time);
+        if (fresh) {   // primary ray: cpu.rs:39-40, camera.rs:326-337; its v jitter came with the PREVIOUS sample's block 0
+            const float vjit = RT_FIXED_JITTER(P) ? 32768.0f : (float)(unsigned short)vj_bits;
+            camera_ray<SAMPLER, ROUNDS>(P, pc, R.sample, vjit, o, d, time);
+        }
+        // ---- the segment's random block: drawn here, by all lanes together.  Nothing before the hit record needs
+        // it (the spare bytes of a sample's block 0 are the NEXT sample's v jitter), so its ten dependent
+        // multiply-xor rounds are scheduled between the instructions of the closest hit instead of in front of them.
+        const uint2 rnd = philox2x32_from<ROUNDS>(ppre, ctr1, P.ks);   // == philox2x32_ks(pc.pixel, rt_ctr1(R.sample, seg, RT_TAG_PATH))
+        if (fresh) vj_bits = __byte_perm(rnd.y, rnd.x, 0x0040);
+        RayT<float> r = make_ray(o, d, time);
+        float t;
+        int prim;
+        if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, sh_prims); prim = closest_hit<MODE>(P, S, r, last_prim, t, X); }
+        else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t, X); }
+        ++nseg;
+        if (prim < 0) {  // renderer.rs:78-88
+            if (!RT_SPEC_BG_BLACK) {
+                const vec3f bg = background_color(P, d);
+                sum = mk3(fmaf(T.x, bg.x, sum.x), fmaf(T.y, bg.y, sum.y), fmaf(T.z, bg.z, sum.z));
             }
-            // ---- the segment's random block: drawn here, by all lanes together.  Nothing before the hit record needs
-            // it (the spare bytes of a sample's block 0 are the NEXT sample's v jitter), so its ten dependent
-            // multiply-xor rounds are scheduled between the instructions of the closest hit instead of in front of them.
-            const uint2 rnd = philox2x32_from<ROUNDS>(ppre, ctr1, P.ks);   // == philox2x32_ks(pc.pixel, rt_ctr1(R.sample, seg, RT_TAG_PATH))
-            if (fresh) vj_bits = __byte_perm(rnd.y, rnd.x, 0x0040);
-            RayT<float> r = make_ray(o, d, time);
-            float t;
-            int prim;
-            if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, sh_prims); prim = closest_hit<MODE>(P, S, r, last_prim, t); }
-            else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t); }
-            ++nseg;
-            if (prim < 0) {  // renderer.rs:78-88
-                if (!RT_SPEC_BG_BLACK) {
-                    const vec3f bg = background_color(P, d);
-                    sum = mk3(fmaf(T.x, bg.x, sum.x), fmaf(T.y, bg.y, sum.y), fmaf(T.z, bg.z, sum.z));
-                }
+            depth_left = 0.0f;
+        } else {
+            ++seg;   // hit number along the path (1 = primary hit)
+            ctr1 += 1u << 24;
+            vec3f X_end;   // radiance that ends the path
+            bool cont;
+            if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, sh_prims); cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
+            else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
+            if (!cont) {                 // absorbed (X_end = 0) or a light (X_end = emission)
+                sum = sum + T * X_end;
                 depth_left = 0.0f;
             } else {
-                ++seg;   // hit number along the path (1 = primary hit)
-                ctr1 += 1u << 24;
-                vec3f X_end;   // radiance that ends the path
-                bool cont;
-                if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, sh_prims); cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
-                else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; cont = shade_hit<SAMPLER, ROUNDS, TEX>(P, X, S, R, prim, r, t, seg, rnd, o, d, T, X_end); }
-                if (!cont) {                 // absorbed (X_end = 0) or a light (X_end = emission)
-                    sum = sum + T * X_end;
-                    depth_left = 0.0f;
-                } else {
-                    last_prim = prim;
-                    // white at depth 0 (renderer.rs:48-56): sum += w T with w = 1 when the budget is spent, as arithmetic
-                    depth_left -= 1.0f;
-                    const float w = __saturatef(1.0f - depth_left);   // 1 when the budget is spent (depth_left == 0), else 0
-                    fma2_bcast(w, T.x, T.y, sum.x, sum.y, sum.x, sum.y);
-                    sum.z = fmaf(w, T.z, sum.z);
-                }
+                last_prim = prim;
+                // white at depth 0 (renderer.rs:48-56): sum += w T with w = 1 when the budget is spent, as arithmetic
+                depth_left -= 1.0f;
+                const float w = __saturatef(1.0f - depth_left);   // 1 when the budget is spent (depth_left == 0), else 0
+                fma2_bcast(w, T.x, T.y, sum.x, sum.y, sum.x, sum.y);
+                sum.z = fmaf(w, T.z, sum.z);
             }
         }
         };
 #define RT_LANE_BUSY ((depth_left != 0.0f) | (s < s_last))
-    if (!RT_STEAL) {
-#pragma unroll 1
-        while (__any_sync(0xffffffffu, RT_LANE_BUSY)) iteration();
-    } else {
-        const bool warp_has_pixels = __any_sync(0xffffffffu, valid);   // (a warp entirely outside the image has nothing to wait for)
+    // The loops of one warp over the lanes in `m` (all of them converged here).  Hot loop: while EVERY lane is busy,
+    // one iteration each — no per-lane test inside.  When some lane has run out (the warp's tail) it takes over half
+    // of the unstarted samples of the lane that has most, and the hot loop resumes; when nothing is worth taking any
+    // more, each lane finishes what it has and leaves (a lane that is idle then stays idle).
+    auto warp_loops = [&](const unsigned m) {
         for (;;) {
-            // the hot loop: every lane of the warp (that has a pixel at all) has a path or a sample to start
-            if (warp_has_pixels && __all_sync(0xffffffffu, RT_LANE_BUSY | !valid)) {
+            if (__all_sync(m, RT_LANE_BUSY)) {
 #pragma unroll 1
-                do iteration(); while (__all_sync(0xffffffffu, RT_LANE_BUSY | !valid));
+                do iteration(); while (__all_sync(m, RT_LANE_BUSY));
             }
-            if (!__any_sync(0xffffffffu, RT_LANE_BUSY)) break;
-            // some lane has neither (the warp's tail): let it take samples over
             bool stolen = false;
-            for (;;) {
-                const int rem = s_last - s;
-                const unsigned idle = __ballot_sync(0xffffffffu, valid && !(RT_LANE_BUSY));   // (lanes outside the image never take part)
-                if (idle == 0u) break;
-                const int most = __reduce_max_sync(0xffffffffu, rem);
-                if (most < RT_STEAL_MIN) break;      // unstarted samples only ever shrink: nothing worth taking, now or later
-                const int victim = __ffs(__ballot_sync(0xffffffffu, rem == most)) - 1, thief = __ffs(idle) - 1;
-                const int take = most >> 1;
-                const int v_last = __shfl_sync(0xffffffffu, s_last, victim), v_owner = __shfl_sync(0xffffffffu, owner, victim);
-                const uint32_t v_pixel = __shfl_sync(0xffffffffu, pc.pixel, victim);
-                const float v_row = __shfl_sync(0xffffffffu, pc.rowf, victim);
-                const float vx = __shfl_sync(0xffffffffu, pc.dir0.x, victim), vy = __shfl_sync(0xffffffffu, pc.dir0.y, victim),
-                            vz = __shfl_sync(0xffffffffu, pc.dir0.z, victim);
-                if (lane == victim) s_last -= take;
-                if (lane == thief) {
-                    // what this lane has summed belongs to `owner`'s pixel: park it (only this lane is active here)
-                    parked[owner] += sum.x; parked[owner + 32] += sum.y; parked[owner + 64] += sum.z;
-                    sum = mk3(0.0f, 0.0f, 0.0f);
-                    owner = v_owner;
-                    pc.pixel = v_pixel; pc.rowf = v_row; pc.dir0 = mk3(vx, vy, vz);
-                    R.pixel = v_pixel;
-                    ppre = philox2x32_pre(v_pixel, P.ks);
-                    s = v_last - take; s_last = v_last;
-                    const uint2 w = philox2x32_from<ROUNDS>(ppre, rt_ctr1(rt_vjit_sample((uint32_t)s), 0u, RT_TAG_PATH), P.ks);
-                    vj_bits = __byte_perm(w.y, w.x, 0x0040);
+            if (RT_STEAL) {
+                if (!__any_sync(m, RT_LANE_BUSY)) break;
+                for (;;) {
+                    const int rem = s_last - s;
+                    const unsigned idle = __ballot_sync(m, !(RT_LANE_BUSY));
+                    if (idle == 0u) break;
+                    const int most = __reduce_max_sync(m, rem);
+                    if (most < RT_STEAL_MIN) break;      // unstarted samples only ever shrink: nothing worth taking, now or later
+                    const int victim = __ffs(__ballot_sync(m, rem == most)) - 1, thief = __ffs(idle) - 1;
+                    const int take = most >> 1;
+                    const int v_last = __shfl_sync(m, s_last, victim), v_owner = __shfl_sync(m, owner, victim);
+                    const uint32_t v_pixel = __shfl_sync(m, pc.pixel, victim);
+                    const float vx = __shfl_sync(m, pc.dir0.x, victim), vy = __shfl_sync(m, pc.dir0.y, victim),
+                                vz = __shfl_sync(m, pc.dir0.z, victim);
+                    if (lane == victim) s_last -= take;
+                    if (lane == thief) {
+                        // what this lane has summed belongs to `owner`'s pixel: park it (only this lane is active here)
+                        parked[owner] += sum.x; parked[owner + 32] += sum.y; parked[owner + 64] += sum.z;
+                        sum = mk3(0.0f, 0.0f, 0.0f);
+                        owner = v_owner;
+                        pc.pixel = v_pixel; pc.dir0 = mk3(vx, vy, vz);
+                        R.pixel = v_pixel;
+                        ppre = philox2x32_pre(v_pixel, P.ks);
+                        s = v_last - take; s_last = v_last;
+                        const uint2 w = philox2x32_from<ROUNDS>(ppre, rt_ctr1(rt_vjit_sample((uint32_t)s), 0u, RT_TAG_PATH), P.ks);
+                        vj_bits = __byte_perm(w.y, w.x, 0x0040);
+                    }
+                    __syncwarp(m);
+                    stolen = true;
                 }
-                __syncwarp();
-                stolen = true;
             }
             if (!stolen) {
-                // nothing worth taking is left: the rest of the warp's tail runs as it is
+                // nothing (more) to take over: every lane finishes what it has and leaves
 #pragma unroll 1
-                while (__any_sync(0xffffffffu, RT_LANE_BUSY)) iteration();
+                while (RT_LANE_BUSY) iteration();
                 break;
             }
         }
+    };
+    {
+        // lanes outside the image (right / bottom edge tiles of an image that is not a multiple of the tile) have no
+        // pixel and take no part; a full warp — the rule — votes with the constant mask
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (vmask == 0xffffffffu) warp_loops(0xffffffffu);
+        else if (valid) warp_loops(vmask);
+        __syncwarp();
     }
 #undef RT_LANE_BUSY
     if (RT_STEAL) {

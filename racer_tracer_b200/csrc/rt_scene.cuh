@@ -103,6 +103,7 @@ struct KParams {
     int width, height;          // the grid of traced pixels (preview: the grid of scaled blocks)
     float inv_wm1, inv_hm1;     // 1/(W-1), 1/(H-1) of the SCREEN (cpu.rs:35-40 divide by W-1 and H-1)
     float wm1;                  // (float)(screen width - 1)
+    float4 vstep;               // cam.vertical / ((H - 1) * 65536): what one unit of the 16-bit v jitter adds to a ray direction
     int px_scale_x, px_scale_y; // screen pixels per traced pixel: 1 for a full render; the preview renderer's
                                 // scale_width / scale_height (cpu_scaled.rs:31-34) otherwise
     int s_begin, s_end;         // sample range traced by this launch
@@ -866,9 +867,16 @@ RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT
         // of k) and so is the sum, so the next segment's re-test of this plane gives t = 0.
         const float4 n4 = S.pn(prim);
         const vec3f N = mk3(n4.x, n4.y, n4.z);
+#ifdef RT_SPEC_SNAP_TABLE
+        // the same, from the mask / offset form of the plane that the specialised kernel keeps in its staged table
+        // (rc_spec.cuh, spec_snap_row): p * M + K
+        fma2(h.p.x, h.p.y, a.x, a.y, a.z, a.w, h.p.x, h.p.y);
+        h.p.z = fmaf(h.p.z, S.pc(prim).w, b.x);
+#else
         const float e = b.x - dot(h.p, N);
         fma2_bcast(e, N.x, N.y, h.p.x, h.p.y, h.p.x, h.p.y);
         h.p.z = fmaf(e, N.z, h.p.z);
+#endif
         const float dn = dot(r.d, N);
         h.front_face = dn < 0.0f;   // dot(d, axis) < 0, geometry.rs:49-56
         // +1 if dn < 0 else -1, on the FMA pipe: sat(-dn * 3e38) is 1 or 0 (|dn| below 3e-39 — an fp32 subnormal —
@@ -977,6 +985,10 @@ struct TexCtx {            // where the Perlin tables live for this kernel
     // fold back into an immediate.  Same values either way.
     float k_two = 2.0f;                                   // make_hit_local: face sign
     float k_phi = 6.283185307179586f / 16777216.0f;       // sphere_direct_w: 24-bit integer -> angle
+    float k_one = 1.0f;                                   // sphere_direct_w: 1 - 2u as ONE multiply-add
+    // ... and literals of a GENERATED closest hit that would otherwise be re-created per iteration (the plane pair of
+    // a slab pair is a packed operand: two UMOVs); which ones, the generator decides (spec_reg_consts, rc_spec.cuh)
+    float k_spec[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 };
 
 // Texture::value for a non-solid texture index (solid colours are folded into
@@ -1049,12 +1061,12 @@ RT_D vec3f sphere_direct(float u1, float u2) {
 
 // sphere_direct(u24(wx), u24(wy)) with the integer -> uniform scalings folded into the
 // multiply-adds (same values: u24 is exact in fp32 and the scale factors are powers of two)
-RT_D vec3f sphere_direct_w(uint32_t wx, uint32_t wy, float k_phi = 6.283185307179586f / 16777216.0f) {
+RT_D vec3f sphere_direct_w(uint32_t wx, uint32_t wy, float k_phi = 6.283185307179586f / 16777216.0f, float k_one = 1.0f) {
     // (w >> 8 as the high word of w * 2^24: an IMAD.HI on the FMA pipe instead of a shift on the ALU pipe)
     wx = __umulhi(wx, 1u << 24); wy = __umulhi(wy, 1u << 24);
-    // 1 - 2 u1, in [-1 + 2^-23, 1]; as multiply (exact: a power of two) + add with immediates, so that no constant
-    // has to be put into a register with a MOV on the ALU pipe
-    const float z = __fadd_rn(1.0f, __fmul_rn((float)wx, -1.0f / 8388608.0f));
+    // 1 - 2 u1, in [-1 + 2^-23, 1]: one multiply-add whose second literal, 1, the caller holds in a register (TexCtx;
+    // the product is exact — a power of two — so it rounds like a multiply followed by an add)
+    const float z = fmaf((float)wx, -1.0f / 8388608.0f, k_one);
     const float r = fast_sqrt(fmaf(-z, z, 1.0f));                                       // |z| <= 1 exactly: never negative
     const float phi = fmaf((float)wy, k_phi, -3.14159265358979323846f);
     return mk3(-r * __cosf(phi), -r * __sinf(phi), z);

@@ -164,8 +164,8 @@ wf_generate(const __grid_constant__ KParams P, WfPool W, float* __restrict__ acc
         pc.pixel = info.x;
         pc.py = (int)(info.x / (uint32_t)P.width);
         pc.px = (int)(info.x - (uint32_t)pc.py * (uint32_t)P.width);
-        pc.rowf = (float)(pc.py * P.px_scale_y);
         pc.dir0 = P.cam.upper_left_corner + W.pixel_u[info.x] * P.cam.horizontal;
+        pc.dir0 = pc.dir0 - ((float)(pc.py * P.px_scale_y) * P.inv_hm1) * P.cam.vertical;   // as pixel_setup()
         const uint32_t sample = info.y;
         float vjit = 32768.0f;   // the v jitter times 65536 (camera_ray)
         if (!P.fixed_jitter) vjit = u16lo_int(philox2x32_ks<ROUNDS>(pc.pixel, rt_ctr1(rt_vjit_sample(sample), 0u, RT_TAG_PATH), P.ks));

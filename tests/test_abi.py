@@ -100,7 +100,17 @@ def test_specialised_source_compiles_for_sm_100a(cuda_lib, cfg, tmp_path):
     buf = C.create_string_buffer(n + 1)
     assert cuda_lib.rc_spec_source(job.scene.ptr, buf, n + 1) == n
     src = buf.value.decode()
-    assert "spec_closest_hit" in src and "554.0f" in src and "#define RT_SPEC_MATS 9" in src   # lambertian + light
+    assert "spec_closest_hit" in src and "#define RT_SPEC_MATS 9" in src   # lambertian + light
+    # ... relative to the kernel's own origin, the centre of the box: the light's plane y = 554 is 276.5 above it
+    assert "#define RT_SPEC_SHIFT mk3(277.5f, 277.5f, 277.5f)" in src and "276.5f" in src and "554.0f" not in src
+    os.environ["RC_SPEC_NO_SHIFT"] = "1"
+    try:
+        n0 = cuda_lib.rc_spec_source(job.scene.ptr, None, 0)
+        buf0 = C.create_string_buffer(n0 + 1)
+        cuda_lib.rc_spec_source(job.scene.ptr, buf0, n0 + 1)
+    finally:
+        os.environ.pop("RC_SPEC_NO_SHIFT")
+    assert "554.0f" in buf0.value.decode() and "RT_SPEC_SHIFT" not in buf0.value.decode()
     cu = tmp_path / "spec.cu"
     cu.write_text(src)
     subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I",
@@ -193,9 +203,11 @@ def test_opposite_walls_become_one_test_only_when_every_ray_starts_between_them(
     _compile_like_the_library(inside, tmp_path)
     left_of_the_box = _spec_source(cuda_lib, job, camera=(-100.0, 278.0, -800.0))
     assert left_of_the_box.count("// slab pair") == 1 and n_tests(left_of_the_box) == 5
-    assert "pair_t(0.0f, 555.0f, r.o.y" in left_of_the_box and "fmaxf(t1, t2)" in left_of_the_box
+    # (planes y = 0 / 555 relative to the kernel's origin, handed over as register constants)
+    assert "pair_t(X.k_spec[0], X.k_spec[1], r.o.y, r.inv_d.y, t1, t2);   // planes -277.5f, 277.5f" in left_of_the_box
+    assert "fmaxf(t1, t2)" in left_of_the_box
     above = _spec_source(cuda_lib, job, camera=(278.0, 900.0, 278.0))
-    assert above.count("// slab pair") == 1 and "pair_t(0.0f, 555.0f, r.o.x" in above
+    assert above.count("// slab pair") == 1 and "pair_t(X.k_spec[0], X.k_spec[1], r.o.x" in above
     no_camera = _spec_source(cuda_lib, job)            # origin (0, 0, 0): on the walls, not between them
     assert no_camera.count("// slab pair") == 0 and n_tests(no_camera) == 6
     for other in ("sandbox_boxes", "emissive"):

@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("scene")
 ap.add_argument("--dump")
 ap.add_argument("-D", action="append", default=[])
+ap.add_argument("--csrc", help="directory with the rt_*.cuh headers to compile against (default: the tree's csrc/)")
 args = ap.parse_args()
 
 lib = capi.load()
@@ -36,7 +37,7 @@ cu = os.path.join(tmp, "spec.cu")
 open(cu, "w").write(src)
 cubin = os.path.join(tmp, "spec.cubin")
 cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-lineinfo", "-Xptxas", "-v",
-       "-I", os.path.join(ROOT, "racer_tracer_b200", "csrc"), "-cubin", "-o", cubin, cu] + ["-D" + d for d in args.D]
+       "-I", args.csrc or os.path.join(ROOT, "racer_tracer_b200", "csrc"), "-cubin", "-o", cubin, cu] + ["-D" + d for d in args.D]
 r = subprocess.run(cmd, capture_output=True, text=True)
 if r.returncode:
     print(r.stderr)
