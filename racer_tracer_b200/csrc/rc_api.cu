@@ -82,6 +82,8 @@ struct DeviceState {
     bool own_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_traced = nullptr;   // this device's share of the current render has been traced (cancel relay, fork)
+    DevBuf<int> cancel_word;           // the word this device's kernels watch during a cancellable render (KParams::cancel_flag)
+    cudaStream_t cancel_stream = nullptr;   // carries the 4-byte copy that raises it while the render kernel runs
     DevBuf<DevPrim> prims;
     DevBuf<DevPrim> prims_lin;
     DevBuf<DevNode> nodes;
@@ -149,7 +151,7 @@ struct rc_ctx {
     rc_camera camera;
     rc_stats stats;
     MultiState multi;
-    int* cancel_relay = nullptr;       // one word of mapped, portable host memory: the flag the kernels read (KParams::cancel_flag)
+    int* cancel_relay = nullptr;       // one page-locked word holding 1: the source of the copy that raises a device's cancel word
     uint64_t spec_clock = 0;           // use counter of the scene-specialised kernel caches (LRU)
 };
 
@@ -394,11 +396,19 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         }
         CUDA_TRY(cudaMemsetAsync(d.counter.p, 0, sizeof(unsigned long long), d.stream));
     }
-    // A cancel flag does not change how the frame is launched (one launch per device, sliced if need be): the
-    // kernels watch a word of mapped host memory, and this call relays the caller's flag to it while it waits
-    // (do_cancel per row, src/renderer/cpu.rs:55-62).  The wavefront variant is not interruptible.
+    // A cancel flag does not change how the frame is launched (one launch per device, sliced if need be): every CTA
+    // reads a word in its device's memory before it starts, and this call relays the caller's flag to that word — a
+    // 4-byte copy on a second stream — while it waits (do_cancel per row, src/renderer/cpu.rs:55-62).  (The word used to
+    // be mapped HOST memory: ten thousand CTAs per GPU then each read it over PCIe, which cost 0.7 ms per frame on one
+    // GPU and 7 ms with eight processes on one host.)  The wavefront variant is not interruptible.
     const bool relay = cancel != nullptr && p->variant == RC_VARIANT_MEGAKERNEL;
-    if (relay) *ctx->cancel_relay = 0;
+    if (relay)
+        for (int k = 0; k < n_dev; ++k) {
+            DeviceState& d = ctx->devs[k];
+            CUDA_TRY(cudaSetDevice(d.device));
+            CUDA_TRY(d.cancel_word.resize(1));
+            CUDA_TRY(cudaMemsetAsync(d.cancel_word.p, 0, sizeof(int), d.stream));
+        }
     for (int k = 0; k < n_dev; ++k) {
         DeviceState& d = ctx->devs[k];
         CUDA_TRY(cudaSetDevice(d.device));
@@ -408,7 +418,7 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         kp.perlin = d.perlin.p; kp.perlin_perm = d.perm.p;
         for (size_t i = 0; i < d.tex.size(); ++i) kp.images[i] = d.tex[i];
         kp.segment_counter = d.counter.p;
-        kp.cancel_flag = relay ? ctx->cancel_relay : nullptr;
+        kp.cancel_flag = relay ? d.cancel_word.p : nullptr;
         partition(kp, p, p->rank * n_dev + k, parts);
         // tile culling needs one ray origin per tile (no lens), primitives that stay where they are, and a linear mode
         kp.tile_cull = (!kp.lens_enabled && !kp.has_motion && !p->fixed_jitter && std::getenv("RC_NO_TILE_CULL") == nullptr) ? 1 : 0;
@@ -454,11 +464,14 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         // into slices so that the grid is still >= 8 full machine loads of CTAs
         kp.slices = 1;
         kp.slice_buf = nullptr;
+        kp.slice_halving = 0;
+        if (const char* e = std::getenv("RC_SLICE_HALVING")) kp.slice_halving = std::atoi(e);
         {
             const long long want = 8LL * d.sm_count * 10;
             long long sl = (want + kp.n_tiles - 1) / kp.n_tiles;
             if (sl > (s1 - s0) / 16) sl = (s1 - s0) / 16;
             if (const char* e = std::getenv("RC_SLICES")) sl = std::atoll(e);
+            while (kp.slice_halving && sl > 1 && ((s1 - s0) >> (sl - 1)) < 8) --sl;   // the last two slices keep >= 8 samples
             if (sl > 1) {
                 CUDA_TRY(d.slice_buf.resize((size_t)sl * kp.n_tiles * RT_BLOCK * 3));
                 kp.slices = (int)sl;
@@ -497,7 +510,13 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
             }
             if (!was_cancelled && cancelled(cancel)) {
                 was_cancelled = true;
-                *reinterpret_cast<volatile int*>(ctx->cancel_relay) = 1;
+                for (int k = 0; k < n_dev; ++k) {
+                    DeviceState& d = ctx->devs[k];
+                    CUDA_TRY(cudaSetDevice(d.device));
+                    CUDA_TRY(cudaMemcpyAsync(d.cancel_word.p, ctx->cancel_relay, sizeof(int), cudaMemcpyHostToDevice, d.cancel_stream));
+                }
+                // (the copy has landed before this call returns, so it can never hit the word of a later frame)
+                for (int k = 0; k < n_dev; ++k) CUDA_TRY(cudaStreamSynchronize(ctx->devs[k].cancel_stream));
             }
             if (done) break;
             std::this_thread::sleep_for(std::chrono::microseconds(20));
@@ -982,13 +1001,22 @@ int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
         return fail(rc, "peer access setup failed");
     }
     cudaSetDevice(ctx->devs[0].device);
-    // the word the kernels of a cancellable render watch: mapped host memory, visible to every device (UVA)
-    if (cudaHostAlloc((void**)&ctx->cancel_relay, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    // the source of the copies that raise the devices' cancel words: one page-locked word holding 1
+    if (cudaHostAlloc((void**)&ctx->cancel_relay, sizeof(int), cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         rc_destroy(ctx);
         return fail(RC_ERR_CUDA, "cudaHostAlloc of the cancel relay failed");
     }
-    *ctx->cancel_relay = 0;
+    *ctx->cancel_relay = 1;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.device);
+        if (cudaStreamCreateWithFlags(&d.cancel_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            rc_destroy(ctx);
+            return fail(RC_ERR_CUDA, "cudaStreamCreate of the cancel stream failed");
+        }
+    }
+    cudaSetDevice(ctx->devs[0].device);
     *out = ctx;
     return RC_OK;
 }
@@ -1006,7 +1034,8 @@ int rc_destroy(rc_ctx* ctx) {
         cudaDeviceSynchronize();
         free_scene(d);
         free_tables(d);
-        d.accum.release(); d.slice_buf.release(); d.out64.release(); d.counter.release();
+        d.accum.release(); d.slice_buf.release(); d.out64.release(); d.counter.release(); d.cancel_word.release();
+        if (d.cancel_stream) cudaStreamDestroy(d.cancel_stream);
         d.pp_in.release(); d.pp_mapped.release(); d.pp_rgba.release();
         if (d.ev_traced) cudaEventDestroy(d.ev_traced);
         wavefront_release(d.wf);

@@ -377,7 +377,12 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     const int py = ty * RT_TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool valid = px < P.width && py < P.height;
     int s_first = P.s_begin, s_last = P.s_end;
-    if (P.slices > 1) {
+    if (P.slices > 1 && P.slice_halving) {
+        // halving lengths: n/2, n/4, ..., and the last two slices equal — boundaries n - (n >> j)
+        const int n = P.s_end - P.s_begin;
+        s_first = P.s_begin + (n - (n >> slice));
+        s_last = slice + 1 == P.slices ? P.s_end : P.s_begin + (n - (n >> (slice + 1)));
+    } else if (P.slices > 1) {
         const long long n = P.s_end - P.s_begin, S = P.slices, total = S * (S + 1) / 2;
         const long long c0 = (long long)slice * S - (long long)slice * (slice - 1) / 2;       // weights of the slices before this one
         const long long c1 = c0 + (S - slice);

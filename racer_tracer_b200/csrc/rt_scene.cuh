@@ -117,6 +117,7 @@ struct KParams {
     float final_scale;          // != 0: what is stored is sqrt(final_scale * sum), Vec3::scale_sqrt folded into the store
                                 // (rc_render_frame: the pixel goes straight into the finished image); needs overwrite
     int slices;                 // > 1: every tile's sample range is cut into this many CTAs (few tiles per GPU)
+    int slice_halving;          // slice lengths: 0 = linearly decreasing (S, S-1, .., 1), 1 = halving (n/2, n/4, .., last two equal)
     float* slice_buf;           // [slices][n_tiles * 128][3] partial sums, reduced in slice order afterwards
     int tiles_x, tile_w, tile_h;
     int n_prims, n_nodes;
@@ -137,7 +138,7 @@ struct KParams {
     cudaTextureObject_t images[RT_MAX_IMAGES];
     int image_w[RT_MAX_IMAGES], image_h[RT_MAX_IMAGES];
     unsigned long long* segment_counter;
-    const int* cancel_flag;     // NULL, or a word in mapped host memory: every CTA reads it once before it starts and leaves
+    const int* cancel_flag;     // NULL, or a word in this device's memory: every CTA reads it once before it starts and leaves
                                 // at once when it is set (the host's cancel flag relayed by rc_render, renderer.rs:25-30)
     DevPrim cprims[RT_MAX_CONST_PRIMS];   // type-sorted copy for the linear constant-bank path
     // rectangles of the constant-bank path once more, split by plane axis so that the

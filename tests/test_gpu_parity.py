@@ -488,6 +488,39 @@ def test_gpu_lbvh_build_and_parity(renderer, oracle, cfg, name):
     assert np.array_equal(renderer.primary_aov(p, 64)[0], ids)
 
 
+def test_library_resplits_a_median_tree_by_sah(renderer, oracle, cfg, monkeypatch):
+    """A host that passes the reference's own median-split tree (Node::build, src/bvh_node.rs:31-82) — what the Rust
+    shim does — gets the surface-area-heuristic tree anyway: rc_upload_scene re-splits the same leaves when that
+    lowers the expected number of box tests by 10 % or more (instance-free scenes, RC_KEEP_TREE=1 keeps the tree).
+    Same leaves, same primitives, another tree: the f64 primary hits are those of the oracle on the tree passed
+    (ties resolve by primitive order, which the re-split keeps consistent), the image is the same image."""
+    def tree_cost(nodes):
+        area = lambda n: 2.0 * sum((n.bmax[a] - n.bmin[a]) * (n.bmax[(a + 1) % 3] - n.bmin[(a + 1) % 3]) for a in range(3))
+        return sum(area(n) for n in nodes) / area(nodes[0])
+    monkeypatch.setattr(harness, "SAH_MIN_OBJECTS", 10 ** 9)      # the harness builds the median tree, like the reference
+    w, h = 320, 240
+    job = job_for("random", cfg, w, h)
+    p = harness.make_params(w, h, 1, 20, fixed_jitter=1)
+    q = harness.make_params(w, h, 8, 20, seed=4)
+    monkeypatch.setenv("RC_KEEP_TREE", "1")
+    renderer.upload(job)
+    kept, kept_order = renderer.get_bvh(job.scene.c.n_prims)
+    ids_kept = renderer.primary_aov(p, 64)[0]
+    img_kept = renderer.render(q)
+    assert np.array_equal(ids_kept, oracle.primary_aov(job, p)[0])
+    monkeypatch.delenv("RC_KEEP_TREE")
+    renderer.upload(job)
+    nodes, order = renderer.get_bvh(job.scene.c.n_prims)
+    assert len(nodes) == len(kept)
+    check_tree(nodes, order, job.scene.c.n_prims, job.scene.np["prim_aabb"])
+    assert tree_cost(nodes) < 0.9 * tree_cost(kept), (tree_cost(nodes), tree_cost(kept))
+    ids = renderer.primary_aov(p, 64)[0]
+    assert (ids != ids_kept).mean() < 1e-4                      # (exact ties between different objects only)
+    img = renderer.render(q)
+    err = np.abs(img - img_kept).max(axis=2)
+    assert float((err > 2e-3).mean()) < 1e-3 and np.median(err) == 0.0
+
+
 def test_processes_store_their_tiles_into_one_shared_frame(cfg):
     """One process per GPU (the bench contract): rc_render_tiles_into stores every rank's tiles into rank 0's
     frame buffer, mapped with CUDA IPC — the tile-split gather happens inside the render kernel.  The frame is

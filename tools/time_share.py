@@ -19,7 +19,9 @@ r.set_stream(torch.cuda.current_stream().cuda_stream)
 r.upload(job)
 acc = torch.zeros(w * h * 3, dtype=torch.float32, device="cuda")
 full = None
-for slices in ([None] if world == 1 else [None, 1, 3, 6, 12, 24, 48]):
+shapes = [(0, None)] if world == 1 else [(0, None), (0, 1), (0, 3), (0, 6), (0, 12), (0, 24), (1, 4), (1, 5), (1, 6), (1, 7), (1, 8)]
+for halving, slices in shapes:
+    os.environ["RC_SLICE_HALVING"] = str(halving)       # 0: slice lengths S, S-1, .., 1; 1: n/2, n/4, .., last two equal
     if slices is None:
         os.environ.pop("RC_SLICES", None)
     else:
@@ -34,5 +36,5 @@ for slices in ([None] if world == 1 else [None, 1, 3, 6, 12, 24, 48]):
         r.render_accumulate(p, acc.data_ptr())
     e1.record()
     torch.cuda.synchronize()
-    print(f"world {world} RC_SLICES={slices}: {e0.elapsed_time(e1) / 5:.3f} ms per share, {r.stats().kernel_launches} launches", flush=True)
+    print(f"world {world} halving={halving} RC_SLICES={slices}: {e0.elapsed_time(e1) / 5:.3f} ms per share, {r.stats().kernel_launches} launches", flush=True)
 r.close()
