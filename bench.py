@@ -326,7 +326,7 @@ def main():
         dist.all_reduce(segs, op=dist.ReduceOp.SUM)
 
     # ---- end to end through the public host call (rank-local share; N GPUs run concurrently) ----
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 10))
     # the host-side result buffer: page-locked, allocated once (the Rust host reuses its Vec likewise)
     host_out = torch.empty((h, w, 3), dtype=torch.float64, pin_memory=True).numpy()
     scene_bytes = (job.scene.c.n_prims * (4 + 40 + 4 + 4 + 4 + 48) + job.scene.c.n_materials * 16 +
