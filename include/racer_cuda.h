@@ -349,13 +349,16 @@ int rc_shared_close(rc_ctx* ctx, void* d_ptr);
  * with rc_frame_open (CUDA IPC: peer access over NVLink).  rc_frame_close unmaps / frees.
  *
  * rc_render_frame(params with rank / world, RC_SPLIT_TILES, megakernel), called by EVERY rank once per frame:
- *   - waits on the device until rank 0 has released the image this frame goes into,
+ *   - waits on the device until rank 0 has released the image this frame goes into (rank 0 releases the images of
+ *     frames n and n + 1 when its stream reaches its own call n: the other ranks may run one frame ahead of the
+ *     slowest rank instead of meeting it at every frame),
  *   - traces this rank's tiles and stores sqrt(sum / samples) — Vec3::scale_sqrt (src/vec3.rs:119-125) folded into
  *     the store — straight into rank 0's image as each tile finishes: the gather happens inside the render kernel,
  *   - publishes "frame f done" in its progress word; rank 0's stream then waits for every rank's word.
  * Nothing but kernels and stream-ordered waits is enqueued: no collective library, no host synchronisation.
  * On rank 0, *d_rgb (if not NULL) receives the device pointer of the finished float image (stream-ordered: valid for
- * work enqueued on the context's stream, until the next-but-one rc_render_frame); if out_rgb is not NULL the image is
+ * work enqueued on the context's stream BEFORE the next rc_render_frame — that call hands the image to the ranks for
+ * the frame after it); if out_rgb is not NULL the image is
  * widened to f64, copied into it (width*height*3 doubles, like rc_render) and the call returns when it is there.
  * On other ranks both must be NULL.  cancel: as for rc_render (every rank must pass a flag or none). */
 typedef struct rc_frame rc_frame;

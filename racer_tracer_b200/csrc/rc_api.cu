@@ -466,13 +466,18 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         // into slices so that the grid is still >= 8 full machine loads of CTAs
         kp.slices = 1;
         kp.slice_buf = nullptr;
-        kp.slice_halving = 1;   // (measured: one rank's share of an 8-way split 4.17 ms against 4.21 ms with linear lengths)
-        if (const char* e = std::getenv("RC_SLICE_HALVING")) kp.slice_halving = std::atoi(e);
+        kp.slice_halving = 0;
         {
             const long long want = 8LL * d.sm_count * 10;
             long long sl = (want + kp.n_tiles - 1) / kp.n_tiles;
             if (sl > (s1 - s0) / 16) sl = (s1 - s0) / 16;
             if (const char* e = std::getenv("RC_SLICES")) sl = std::atoll(e);
+            // Slice lengths: halving (n/2, n/4, .., the last two equal) from five slices on, linearly decreasing below —
+            // with two or three slices the halving scheme's last slice is too long a tail.  One rank's share of the
+            // bench frame alone on one GPU (tools/time_share.py): 8-way split, six slices: 4.17 ms halving / 4.21 linear
+            // (4.08 = an eighth of the frame); 2-way split, two slices: 16.54 halving / 16.39 linear (16.32 = half).
+            kp.slice_halving = sl >= 5 ? 1 : 0;
+            if (const char* e = std::getenv("RC_SLICE_HALVING")) kp.slice_halving = std::atoi(e);
             while (kp.slice_halving && sl > 1 && ((s1 - s0) >> (sl - 1)) < 8) --sl;   // the last two slices keep >= 8 samples
             if (sl > 1) {
                 CUDA_TRY(d.slice_buf.resize((size_t)sl * kp.n_tiles * RT_BLOCK * 3));
@@ -1365,10 +1370,14 @@ int rc_render_frame(rc_ctx* ctx, const rc_params* p, rc_frame* f, const float** 
     CUDA_TRY(cudaSetDevice(d.device));
     const int frame_no = ++f->frame_no;
     float* image = f->base + (size_t)(frame_no & 1) * f->image_floats;
-    // the image of frame n was last used by frame n - 2: rank 0 releases it when it gets here (whatever read it was
-    // enqueued on this stream before), the others wait for that release
+    // The image of frame n was last used by frame n - 2: the others wait for rank 0 to release it.  When rank 0's
+    // stream gets HERE, everything enqueued on it before this call has run: the wait for every rank's frame n - 1 and
+    // whatever read the images of frames n - 1 and n - 2.  So both images are free — this frame's and the NEXT one's
+    // (frame n + 1 goes into the image of n - 1) — and rank 0 releases up to n + 1: the other ranks may run one frame
+    // ahead of the slowest one instead of meeting it at every frame (a per-frame barrier in all but name, which is
+    // what releasing only n amounted to: rank 0 gets here only after every rank's n - 1).
     if (world > 1) {
-        if (f->rank == 0) frame_publish_kernel<<<1, 1, 0, d.stream>>>(f->words, frame_no);
+        if (f->rank == 0) frame_publish_kernel<<<1, 1, 0, d.stream>>>(f->words, frame_no + 1);
         else frame_wait_kernel<<<1, 32, 0, d.stream>>>(f->words, 0, 1, frame_no, f->timed_out);
         CUDA_TRY(cudaGetLastError());
     }

@@ -366,8 +366,8 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     // CTA -> (tile, slice of the sample range).  With one GPU there are thousands of tiles and
     // slices == 1; when the tiles are shared out over several GPUs each tile's samples are cut
     // into `slices` CTAs so the grid still fills the machine many times over.
-    // Slice-major order with DECREASING slice lengths — halving (n/2, n/4, .., the last two equal; the default) or
-    // linear (weights S, S-1, .., 1): the CTAs scheduled last — the ones that form the tail of the grid — are the
+    // Slice-major order with DECREASING slice lengths — halving (n/2, n/4, .., the last two equal: five slices and
+    // more) or linear (weights S, S-1, .., 1): the CTAs scheduled last — the ones that form the tail of the grid — are the
     // short ones, and most of the work sits in few long CTAs.
     const int slice = P.slices > 1 ? (int)blockIdx.x / P.n_tiles : 0;
     const int tile_k = P.slices > 1 ? (int)blockIdx.x - slice * P.n_tiles : (int)blockIdx.x;

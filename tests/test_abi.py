@@ -213,3 +213,38 @@ def test_opposite_walls_become_one_test_only_when_every_ray_starts_between_them(
     for other in ("sandbox_boxes", "emissive"):
         j = harness.prepare_job(scene_path(other), cfg, 64, 64)
         assert "// slab pair" not in _spec_source(cuda_lib, j, camera=j.camera.origin)
+
+
+def test_generated_kernel_variants_compile_and_agree_on_their_planes(cuda_lib, cfg, tmp_path, monkeypatch):
+    """The pieces of the generated Cornell kernel that can be switched off one at a time all
+    compile, and in every variant the plane constant the hit record snaps a point to (spec_snap_row: the staged
+    table's K) is the same literal as the plane the rectangle TEST uses — if the two differed by an ulp, a ray leaving
+    a wall would re-hit it at t != 0."""
+    import re
+    from conftest import scene_path
+    job = harness.prepare_job(scene_path("cornell_box"), cfg, 64, 64)
+    for env in ({}, {"RC_SPEC_NO_REG_CONSTS": "1"}, {"RC_SPEC_PACK_ALL": "1"}, {"RC_SPEC_NO_SHIFT": "1"}, {"RC_SPEC_NO_SLAB": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        src = _spec_source(cuda_lib, job, camera=job.camera.origin)
+        for k in env:
+            monkeypatch.delenv(k)
+        _compile_like_the_library(src, tmp_path)
+        tested = re.findall(r"\((-?[0-9.]+f) - r\.o\.[xyz]\) \* r\.inv_d", src)           # single rectangles
+        for a, b in re.findall(r"// planes (-?[0-9.]+f), (-?[0-9.]+f)", src):                 # slab pairs
+            tested += [a, b]
+        for a, b in re.findall(r"pair_t\((-?[0-9.]+f), (-?[0-9.]+f), r\.o", src):             # packed pairs with literal planes
+            if "// planes" not in src or (a, b) not in re.findall(r"// planes (-?[0-9.]+f), (-?[0-9.]+f)", src):
+                tested += [a, b]
+        rows = re.findall(r"case \d+: a = make_float4\(([^)]*)\); bx = (-?[0-9.]+f); cw = [0-9.]+f;", src)
+        if "RC_SPEC_NO_SHIFT" in env:
+            assert not rows and "RT_SPEC_SNAP_TABLE" not in src      # world coordinates: the table keeps the uploaded k
+            continue
+        assert len(rows) == 6 and "#define RT_SPEC_SNAP_TABLE 1" in src
+        snapped = []
+        for a, bx in rows:
+            mx, my, kx, ky = [t.strip() for t in a.split(",")]
+            ks = [v for v, m in ((kx, mx), (ky, my)) if m == "0.0f"] or [bx]
+            assert len(ks) == 1
+            snapped.append(ks[0])
+        assert sorted(snapped) == sorted(tested), (env, sorted(snapped), sorted(tested))

@@ -66,7 +66,7 @@ kept = []
 for seed in seeds:
     p = harness.make_params(w, h, spp, 20, seed=seed, rank=rank, world=world, specialize=2)
     dptr = r.render_frame(p, frame, want_device_ptr=(rank == 0))
-    if rank == 0:   # a stream-ordered copy of the finished image (the frame's own image is reused two frames later)
+    if rank == 0:   # a stream-ordered copy of the finished image (enqueued before the next call, which hands the image on to the ranks)
         keep = torch.empty(n, dtype=torch.float32, device="cuda")
         keep.copy_(harness.device_view(dptr, n), non_blocking=True)
         kept.append(keep)

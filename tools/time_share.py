@@ -19,7 +19,7 @@ r.set_stream(torch.cuda.current_stream().cuda_stream)
 r.upload(job)
 acc = torch.zeros(w * h * 3, dtype=torch.float32, device="cuda")
 full = None
-shapes = [(0, None)] if world == 1 else [(0, None), (0, 1), (0, 3), (0, 6), (0, 12), (0, 24), (1, 4), (1, 5), (1, 6), (1, 7), (1, 8)]
+shapes = [(0, None), (1, None)] + [(0, k) for k in (1, 2, 3, 6, 12)] + [(1, k) for k in (2, 3, 4, 5, 6, 7, 8)]
 for halving, slices in shapes:
     os.environ["RC_SLICE_HALVING"] = str(halving)       # 0: slice lengths S, S-1, .., 1; 1: n/2, n/4, .., last two equal
     if slices is None:
