@@ -430,7 +430,11 @@ def main():
                                          "x cost table) / time.  This path does not execute all of them: tiles whose frustum contains no "
                                          "primitive trace nothing, opposite walls share one test, and BVH scenes walk a SAH tree instead of the "
                                          "reference's median-split tree whose node tests the oracle counts — so the fraction can exceed what the "
-                                         "FP32 pipes issued (frac_executed) and, for scenes that are mostly culled, even 1."),
+                                         "FP32 pipes issued (frac_executed) and, for scenes that are mostly culled, even 1.  "
+                                         "traffic = DRAM bytes ncu counted for the one launch: the kernel's only global write is the "
+                                         "frame (width x height x 12 B, the algorithmic traffic), which is still in the 126 MB L2 when the "
+                                         "kernel ends, so the counter sees next to nothing; the bound is instruction issue, not HBM."),
+                                "algorithmic_bytes_per_launch": int(w * h * 12),
                                 "peak_source": "FFMA micro-benchmark in this run (rc_fp32_peak), per GPU",
                                 "flops_per_sample": A_used, "lane_ginstr_per_s_peak": lane_ginstr,
                                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_kind,

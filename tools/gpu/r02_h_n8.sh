@@ -22,6 +22,5 @@ except Exception as e:
 PY
 }
 run n8 8 RC_X=0 -- --steps 20 --warmup 5 --no-cpu-baseline
-run n2 2 RC_X=0 -- --steps 10 --warmup 3 --no-cpu-baseline
-run n4 4 RC_X=0 -- --steps 10 --warmup 3 --no-cpu-baseline
-run clown_n8 8 RC_X=0 -- --workload clown_4k_4096spp --steps 5 --warmup 3 --no-cpu-baseline
+run n2 2 RC_X=0 -- --steps 20 --warmup 3 --no-cpu-baseline
+run n4 4 RC_X=0 -- --steps 20 --warmup 3 --no-cpu-baseline
