@@ -106,7 +106,28 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
 
+    def run_nvml(self):
+        """In-process NVML: a sample every 10 ms (nvidia-smi as a subprocess manages one per ~0.3 s, and a timed region
+        of a few steps lasts 0.1 - 0.2 s).  Same fields as the nvidia-smi query."""
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not self.stop_flag.is_set():
+            r = get_reasons(h)
+            self.rows.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), str(N.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                             ["Active" if r & b else "Not Active" for _, b in bits])
+            self.stop_flag.wait(0.01)
+        N.nvmlShutdown()
+
     def run(self):
+        try:
+            self.run_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
