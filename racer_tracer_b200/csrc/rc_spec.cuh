@@ -11,6 +11,13 @@
 // has no link-time dependency on either; when rc_params.specialize == 1 and anything here fails
 // the render call fails loudly (rc_params.specialize == 2 falls back to the precompiled CUDA
 // kernel instead).
+//
+// Beyond immediates, the generator decides things only it can know: which opposite walls
+// are one rectangle test (slab pairs), the origin the kernel traces relative to (RT_SPEC_SHIFT: the most common
+// rectangle centre per axis), which literals are handed over as register constants (spec_reg_consts), the layout of
+// the staged table's rows for the hit record's plane snap (spec_snap_row), and where packed two-lane arithmetic pays
+// (operands already in register pairs).  Each of these has an environment switch that turns it off, so that the
+// equivalence tests and the measurements in DESIGN.md can be repeated (appendix there).
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
