@@ -186,6 +186,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     auto centre_b = [&](float c, int g) { return (float)((double)c - shift[g == 0 ? 1 : 2]); };
     if (const char* e = std::getenv("RC_STEAL")) o << "#define RT_STEAL " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_STEAL_MIN")) o << "#define RT_STEAL_MIN " << std::atoi(e) << "\n";
+    if (const char* e = std::getenv("RC_FIRST_TEST_RANGE")) o << "#define RT_FIRST_TEST_RANGE " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
     o << "#include \"rt_scene.cuh\"\n";
     // rectangle-only scenes keep the index of the best hit as a FLOAT, so that both conditional moves of the

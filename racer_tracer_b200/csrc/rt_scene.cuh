@@ -419,14 +419,23 @@ RT_D void rect_closest_fma(float t, float xa, float xb, float ha, float hb, floa
 
 // The FIRST test of a generated closest hit: nothing has been hit yet (best_t = RT_NO_HIT, index -1), so the two
 // results are selects between literals instead of updates of running values — two instructions fewer than the
-// general form, whose multiply-adds with the known start values ptxas does not fold.  `t <= RT_NO_HIT` stays: a
-// ray parallel to the plane has t = +-inf or NaN.
+// general form, whose multiply-adds with the known start values ptxas does not fold.  `t <= RT_NO_HIT` could go as
+// well: a ray parallel to the plane has t = +-inf or NaN, and then the in-plane coordinates t * d + o are +-inf or
+// NaN too, which the bounds tests at the head of the chain reject (RT_FIRST_TEST_RANGE, above).
+// (1: the first test also compares t <= RT_NO_HIT.  The compare is redundant — see below — but the kernel WITHOUT
+// it measured 2.1 % slower, 33.39 against 32.71 ms on the same GPU, profiles/r02_v26_sweeps.txt: one instruction
+// fewer, another ptxas schedule.  At 142 instructions the schedule's luck is worth more than an instruction.)
+#ifndef RT_FIRST_TEST_RANGE
+#define RT_FIRST_TEST_RANGE 1
+#endif
 RT_D void rect_closest_first(float t, float xa, float xb, float ha, float hb, float index, float& best_t, float& best_index) {
     asm("{\n\t.reg .pred p;\n\t"
         "setp.le.f32 p, %2, %4;\n\t"
         "setp.le.and.f32 p, %3, %5, p;\n\t"
         "setp.ge.and.f32 p, %6, 0f3A83126F, p;\n\t"   /* t >= 0.001f */
+#if RT_FIRST_TEST_RANGE
         "setp.le.and.f32 p, %6, 0f7F61B1E6, p;\n\t"   /* t <= RT_NO_HIT (3e38f) */
+#endif
         "selp.f32 %0, %6, 0f7F61B1E6, p;\n\t"
         "selp.f32 %1, %7, 0fBF800000, p;\n\t}"
         : "=f"(best_t), "=f"(best_index) : "f"(fabsf(xa)), "f"(fabsf(xb)), "f"(ha), "f"(hb), "f"(t), "f"(index));
@@ -882,8 +891,8 @@ RT_D Hit make_hit_local(const Scene& S, int prim, float4 a, float4 b, const RayT
         h.front_face = dn < 0.0f;   // dot(d, axis) < 0, geometry.rs:49-56
         // +1 if dn < 0 else -1, on the FMA pipe: sat(-dn * 3e38) is 1 or 0 (|dn| below 3e-39 — an fp32 subnormal —
         // would give a fraction; a ray that parallel to the plane has no hit to shade)
-        const float sgn = fmaf(k_two, __saturatef(dn * -3.0e38f), -1.0f);
         h.outward = N;
+        const float sgn = fmaf(k_two, __saturatef(dn * -3.0e38f), -1.0f);
         mul2_bcast(sgn, N.x, N.y, h.n.x, h.n.y);
         h.n.z = sgn * N.z;
     }
