@@ -187,6 +187,8 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     if (const char* e = std::getenv("RC_STEAL")) o << "#define RT_STEAL " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_STEAL_MIN")) o << "#define RT_STEAL_MIN " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_FIRST_TEST_RANGE")) o << "#define RT_FIRST_TEST_RANGE " << std::atoi(e) << "\n";
+    if (const char* e = std::getenv("RC_KCONST_MASK")) o << "#define RT_KCONST_MASK " << std::atoi(e) << "\n";
+    if (const char* e = std::getenv("RC_PHILOX_LATE")) o << "#define RT_PHILOX_LATE " << std::atoi(e) << "\n";
     if (const char* e = std::getenv("RC_MIN_BLOCKS")) o << "#define RT_MIN_BLOCKS " << std::atoi(e) << "\n";
     o << "#include \"rt_scene.cuh\"\n";
     // rectangle-only scenes keep the index of the best hit as a FLOAT, so that both conditional moves of the

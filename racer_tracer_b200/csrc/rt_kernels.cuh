@@ -338,6 +338,13 @@ RT_D bool shade_hit(const KParams& P, const TexCtx& X, const Scene& S, const Rng
 #endif
 
 
+#ifndef RT_KCONST_MASK
+#define RT_KCONST_MASK 7
+#endif
+#ifndef RT_PHILOX_LATE
+#define RT_PHILOX_LATE 0    // 1: the segment's block is drawn after the closest hit in the source (ptxas schedules it either way)
+#endif
+
 template <int MODE, int SAMPLER, int ROUNDS, bool TEX>
 RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned char* smem) {
     __shared__ float steal_parked[RT_STEAL ? 3 * RT_BLOCK : 1];   // per lane of the CTA: sums other lanes traced for its pixel
@@ -356,7 +363,10 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
     TexCtx X; X.perlin = L.perlin; X.perm = L.perm;
     {   // volatile: a plain load would be folded back into the literal (the only value ever stored there)
         const volatile float* rc = reg_consts;
-        X.k_two = rc[0]; X.k_phi = rc[1]; X.k_one = rc[2];   // held in registers across the path loop, see TexCtx
+        // held in registers across the path loop, see TexCtx (RT_KCONST_MASK: which of the three; experiments)
+        if (RT_KCONST_MASK & 1) X.k_two = rc[0];
+        if (RT_KCONST_MASK & 2) X.k_phi = rc[1];
+        if (RT_KCONST_MASK & 4) X.k_one = rc[2];
 #ifdef RT_SPECIALIZED
 #pragma unroll
         for (int j = 0; j < RT_SPEC_REG_CONSTS; ++j) X.k_spec[j] = rc[3 + j];
@@ -488,13 +498,19 @@ RT_D void megakernel_body(const KParams& P, float* __restrict__ accum, unsigned 
         // ---- the segment's random block: drawn here, by all lanes together.  Nothing before the hit record needs
         // it (the spare bytes of a sample's block 0 are the NEXT sample's v jitter), so its ten dependent
         // multiply-xor rounds are scheduled between the instructions of the closest hit instead of in front of them.
+#if !RT_PHILOX_LATE
         const uint2 rnd = philox2x32_from<ROUNDS>(ppre, ctr1, P.ks);   // == philox2x32_ks(pc.pixel, rt_ctr1(R.sample, seg, RT_TAG_PATH))
         if (fresh) vj_bits = __byte_perm(rnd.y, rnd.x, 0x0040);
+#endif
         RayT<float> r = make_ray(o, d, time);
         float t;
         int prim;
         if (MODE == RT_MODE_CONST_LINEAR) { ConstScene S(P, sh_prims); prim = closest_hit<MODE>(P, S, r, last_prim, t, X); }
         else { PtrScene S; S.prims = L.prims; S.nodes = L.nodes; S.inst = P.instances; S.ref_aabb = P.ref_aabb; prim = closest_hit<MODE>(P, S, r, last_prim, t, X); }
+#if RT_PHILOX_LATE
+        const uint2 rnd = philox2x32_from<ROUNDS>(ppre, ctr1, P.ks);
+        if (fresh) vj_bits = __byte_perm(rnd.y, rnd.x, 0x0040);
+#endif
         ++nseg;
         if (prim < 0) {  // renderer.rs:78-88
             if (!RT_SPEC_BG_BLACK) {
