@@ -471,6 +471,11 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
             const long long want = 8LL * d.sm_count * 10;
             long long sl = (want + kp.n_tiles - 1) / kp.n_tiles;
             if (sl > (s1 - s0) / 16) sl = (s1 - s0) / 16;
+            // A frame with plenty of tiles still ends in a tail: a CTA of the bench frame (128 pixels x 1024 samples)
+            // runs for 4 ms, and while the last ones finish the machine drains.  Two slices (2/3 and 1/3 of the samples)
+            // halve that: 32.37 against 32.63 ms for the whole frame on one GPU (tools/time_share.py 1); three or more
+            // cost more in per-CTA set-up than they save.
+            if (sl < 2 && s1 - s0 >= 512) sl = 2;
             if (const char* e = std::getenv("RC_SLICES")) sl = std::atoll(e);
             // Slice lengths: halving (n/2, n/4, .., the last two equal) from five slices on, linearly decreasing below —
             // with two or three slices the halving scheme's last slice is too long a tail.  One rank's share of the
@@ -998,6 +1003,18 @@ int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
         }
         d.sm_count = prop.multiProcessorCount;
         d.clock_khz = prop.clockRate;
+        // The small kernels every render path ends in are loaded now, not inside the first frame that needs them: with
+        // lazy module loading the first launch of reduce_slices_kernel cost 0.6 s in the middle of a render.
+        {
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, reduce_slices_kernel);
+            cudaFuncGetAttributes(&fa, finalize_kernel);
+            cudaFuncGetAttributes(&fa, finalize_to_f64_kernel);
+            cudaFuncGetAttributes(&fa, widen_kernel);
+            cudaFuncGetAttributes(&fa, frame_wait_kernel);
+            cudaFuncGetAttributes(&fa, frame_publish_kernel);
+            cudaGetLastError();
+        }
     }
     ctx->stats.n_devices = n;
     ctx->stats.sm_count = ctx->devs[0].sm_count;

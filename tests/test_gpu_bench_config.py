@@ -89,7 +89,7 @@ def test_cancel_flag_stops_a_running_render(renderer, cfg):
     renderer.upload(job)
     spp = 8192                                        # ~0.3 s of GPU time if left alone
     p = harness.make_params(w, h, spp, 20, seed=1, specialize=2)
-    renderer.render(harness.make_params(w, h, 8, 20, seed=1, specialize=2))   # compile + warm up
+    renderer.render(harness.make_params(w, h, 512, 20, seed=1, specialize=2))   # compile + warm up (512 spp: the sliced path, like the timed render)
     out = np.full((h, w, 3), -1.0)
     flag = C.c_int32(0)
     t = threading.Timer(0.03, lambda: setattr(flag, "value", 1))
