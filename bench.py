@@ -251,7 +251,7 @@ def main():
     job = harness.prepare_job(scene_file(scene), cfg, w, h)
     variant = capi.RC_VARIANT_MEGAKERNEL if args.variant == "megakernel" else capi.RC_VARIANT_WAVEFRONT
     sampler = capi.RC_SAMPLER_DIRECT if args.sampler == "direct" else capi.RC_SAMPLER_REJECTION
-    spec = args.specialize if (args.variant == "megakernel" and args.sampler == "direct" and args.rng_rounds == 10) else 0
+    spec = args.specialize if (args.variant == "megakernel" and args.sampler == "direct") else 0
 
     params = harness.make_params(w, h, spp, depth, seed=0, variant=variant, sampler=sampler, split=split,
                                  rank=rank, world=world, rng_rounds=args.rng_rounds, specialize=spec)

@@ -218,8 +218,8 @@ typedef struct rc_params {
                                  primitive / material / wrapper present for BVH
                                  scenes) and fail if that is impossible.  2: the
                                  same, but fall back to the precompiled kernel.
-                                 Needs the megakernel, the direct sampler, 10
-                                 Philox rounds and fixed_jitter = 0          */
+                                 Needs the megakernel, the direct sampler and
+                                 fixed_jitter = 0                            */
 } rc_params;
 
 typedef struct rc_tone_map {

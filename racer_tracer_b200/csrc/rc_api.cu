@@ -139,6 +139,7 @@ struct rc_ctx {
     int mats_mask = 0xF;         // material kinds the scene uses
     int prims_mask = 0xF;        // primitive kinds the scene uses (bit RT_PRIM_*; moving spheres count as spheres)
     std::string spec_source;     // generated source of the scene-specialised kernel ("" = not generated yet)
+    int spec_rounds = 10;        // Philox rounds spec_source was generated for
     std::vector<LbvhObject> objects, objects_next;   // top-level objects of the uploaded scene (rc_build_lbvh)
     std::vector<int> prim_order;       // device primitive i = uploaded primitive prim_order[i] (empty: identity)
     bool lbvh = false;
@@ -449,17 +450,19 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
         const bool spec_mode_ok = ctx->smem_bytes <= 48 * 1024 &&
                                   (ctx->mode == RT_MODE_CONST_LINEAR ||
                                    ((ctx->mode == RT_MODE_SMEM_BVH || ctx->mode == RT_MODE_GLOBAL_BVH) && std::getenv("RC_NO_BVH_SPEC") == nullptr));
-        if (p->specialize && spec_mode_ok && p->sampler == RC_SAMPLER_DIRECT && rounds == 10 && !p->fixed_jitter) {
+        if (p->specialize && spec_mode_ok && p->sampler == RC_SAMPLER_DIRECT && !p->fixed_jitter) {
             std::string err;
             if (!spec_load_api((const void*)&rc_abi_version)) err = spec_api().err;
             else {
-                if (ctx->spec_source.empty())
-                    ctx->spec_source = spec_generate(ctx->kp, ctx->has_textures, ctx->mats_mask, ctx->mode, ctx->prims_mask, ctx->instanced);
+                if (ctx->spec_source.empty() || ctx->spec_rounds != rounds) {
+                    ctx->spec_source = spec_generate(ctx->kp, ctx->has_textures, ctx->mats_mask, ctx->mode, ctx->prims_mask, ctx->instanced, rounds);
+                    ctx->spec_rounds = rounds;
+                }
                 spec = spec_build(d.spec_cache, ctx->spec_source, err, ++ctx->spec_clock);
             }
             if (!spec && p->specialize == 1) return fail(RC_ERR_STATE, "scene specialisation failed: " + err);
         } else if (p->specialize == 1) {
-            return fail(RC_ERR_INVALID, "specialize = 1 needs the megakernel, the direct sampler, 10 Philox rounds and no fixed jitter");
+            return fail(RC_ERR_INVALID, "specialize = 1 needs the megakernel, the direct sampler and no fixed jitter");
         }
         const int s0 = kp.s_begin, s1 = kp.s_end;
         // few tiles on this device (its share of a multi-GPU render): cut every tile's sample range

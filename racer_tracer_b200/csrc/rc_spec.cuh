@@ -116,7 +116,7 @@ inline std::string spec_float(float v) {
 // Source of the specialised translation unit for a scene already laid out in KParams
 // (type-sorted constant-bank table).
 inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int mode = RT_MODE_CONST_LINEAR, int prims_mask_all = 0xF,
-                                 bool instanced = false) {
+                                 bool instanced = false, int rounds = 10) {
     std::ostringstream o;
     if (mode != RT_MODE_CONST_LINEAR) {
         // BVH paths: the tables stay in memory; what is compiled in is which kinds of primitive, material, wrapper,
@@ -139,7 +139,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
         o << "extern \"C\" __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)\n"
              "spec_megakernel(const __grid_constant__ KParams P, float* __restrict__ accum) {\n"
              "    extern __shared__ __align__(16) unsigned char smem[];\n"
-             "    megakernel_body<" << (mode == RT_MODE_SMEM_BVH ? "RT_MODE_SMEM_BVH" : "RT_MODE_GLOBAL_BVH") << ", 0, 10, "
+             "    megakernel_body<" << (mode == RT_MODE_SMEM_BVH ? "RT_MODE_SMEM_BVH" : "RT_MODE_GLOBAL_BVH") << ", 0, " << rounds << ", "
           << (tex ? "true" : "false") << ">(P, accum, smem);\n}\n";
         return o.str();
     }
@@ -490,7 +490,7 @@ inline std::string spec_generate(const KParams& kp, bool tex, int mats_mask, int
     o << "extern \"C\" __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)\n"
          "spec_megakernel(const __grid_constant__ KParams P, float* __restrict__ accum) {\n"
          "    extern __shared__ __align__(16) unsigned char smem[];\n"
-         "    megakernel_body<RT_MODE_CONST_LINEAR, 0, 10, " << (tex ? "true" : "false") << ">(P, accum, smem);\n}\n";
+         "    megakernel_body<RT_MODE_CONST_LINEAR, 0, " << rounds << ", " << (tex ? "true" : "false") << ">(P, accum, smem);\n}\n";
     return o.str();
 }
 

@@ -65,6 +65,24 @@ def test_benched_kernel_matches_the_oracle_at_1080p(renderer, oracle, cfg):
     assert (np.abs(img0 - img).max(axis=2) > 2e-3).mean() < 0.01
 
 
+def test_seven_philox_rounds_in_the_specialised_kernel(renderer, oracle, cfg):
+    """rng_rounds = 7 (Philox2x32-7; the headline numbers use the default 10): the scene-specialised kernel is generated
+    for the requested number of rounds, traces the same streams as the oracle with 7 rounds, and going back to 10
+    regenerates the kernel for 10."""
+    w, h, spp = 320, 180, 8
+    job = job_for("cornell_box", cfg, w, h)
+    renderer.upload(job)
+    img7 = renderer.render(harness.make_params(w, h, spp, 20, seed=5, specialize=1, rng_rounds=7))
+    assert renderer.stats().specialized == 1
+    ref7 = oracle.render(job, harness.make_params(w, h, spp, 20, seed=5, rng_rounds=7))
+    err = np.abs(img7 - ref7).max(axis=2)
+    assert (err > 2e-3).mean() < 0.03 and np.median(err) < 1e-5
+    img10 = renderer.render(harness.make_params(w, h, spp, 20, seed=5, specialize=1))
+    ref10 = oracle.render(job, harness.make_params(w, h, spp, 20, seed=5))
+    assert (np.abs(img10 - ref10).max(axis=2) > 2e-3).mean() < 0.03
+    assert (np.abs(img10 - img7).max(axis=2) > 2e-3).mean() > 0.2       # other streams: another sample of the same image
+
+
 def test_converged_image_psnr_at_320x180(renderer, oracle, cfg):
     """north_star: the converged image within PSNR >= 40 dB of the reference's converged image.  Both sides are Monte
     Carlo estimates with independent streams (GPU: Philox, direct samplers; oracle: sequential generator, the
