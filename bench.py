@@ -269,12 +269,15 @@ def main():
 
     launches = [0]
 
-    # Tile split (every N, also 1): the whole exchange lives behind the ABI — rc_frame_create / rc_frame_open /
-    # rc_render_frame.  Rank 0 owns the frame (two images, alternating) and every rank maps it (CUDA IPC); the render
-    # kernel of every rank STORES sqrt(sum / spp) for its tiles into it over NVLink as they finish, then publishes a
-    # progress word that rank 0's stream waits for.  bench.py only carries the 64-byte handle to the other ranks.
+    # Every N (also 1), both splits: the whole exchange lives behind the ABI — rc_frame_create / rc_frame_open /
+    # rc_render_frame.  Rank 0 owns the frame (two images, alternating, one slot per rank each) and every rank maps it
+    # (CUDA IPC).  Tile split: the render kernel of every rank STORES sqrt(sum / spp) for its tiles into slot 0 over
+    # NVLink as they finish.  Sample split: it stores its partial sums into its own slot, and rank 0 adds the slots up.
+    # Either way a rank then publishes a progress word that rank 0's stream waits for; no collective library.
+    # bench.py only carries the 64-byte handle to the other ranks.  (RC_BENCH_NCCL_GATHER=1: the older form — local
+    # buffers summed with an NCCL reduce — for comparison.)
     frame = None
-    if split == capi.RC_SPLIT_TILES and variant == capi.RC_VARIANT_MEGAKERNEL and not os.environ.get("RC_BENCH_NCCL_GATHER"):
+    if variant == capi.RC_VARIANT_MEGAKERNEL and not os.environ.get("RC_BENCH_NCCL_GATHER"):
         if rank == 0:
             frame, handle = r.frame_create(w, h, world)
             hbuf = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
@@ -403,9 +406,12 @@ def main():
                        "tile_culling": "off" if os.environ.get("RC_NO_TILE_CULL") or job.camera.lens_radius != 0.0 else "on (bit-identical images)",
                        "l2": "256 MiB buffer written between timed iterations (flush)",
                        "parallelism": f"tiles{world}" if split_name == "tiles" else f"samples{world}",
-                       "exchange": ("none" if world == 1 else ("in-kernel peer stores into rank 0's frame (CUDA IPC, NVLink) + per-rank progress words "
-                                                               "(rc_render_frame; no collective)"
-                                                               if frame is not None else "NCCL reduce of the accumulation buffer to rank 0"))},
+                       "exchange": ("none" if world == 1 else (
+                           ("in-kernel peer stores into rank 0's frame (CUDA IPC, NVLink) + per-rank progress words (rc_render_frame; no collective)"
+                            if split_name == "tiles" else
+                            "in-kernel peer stores of every rank's partial sums into its slot of rank 0's frame (CUDA IPC, NVLink) + per-rank "
+                            "progress words, slots added in rank order on rank 0 (rc_render_frame; no collective)")
+                           if frame is not None else "NCCL reduce of the accumulation buffer to rank 0"))},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(scene_bytes),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "call": "rc_render_frame" if frame is not None else ("rc_render" if world == 1 else "rc_render_accumulate + torch reduce")},

@@ -348,13 +348,17 @@ int rc_shared_close(rc_ctx* ctx, void* d_ptr);
  * progress words per rank, and gets the 64-byte handle to pass to the other ranks (any byte channel); they map it
  * with rc_frame_open (CUDA IPC: peer access over NVLink).  rc_frame_close unmaps / frees.
  *
- * rc_render_frame(params with rank / world, RC_SPLIT_TILES, megakernel), called by EVERY rank once per frame:
+ * rc_render_frame(params with rank / world, megakernel), called by EVERY rank once per frame.  With RC_SPLIT_TILES:
  *   - waits on the device until rank 0 has released the image this frame goes into (rank 0 releases the images of
  *     frames n and n + 1 when its stream reaches its own call n: the other ranks may run one frame ahead of the
  *     slowest rank instead of meeting it at every frame),
  *   - traces this rank's tiles and stores sqrt(sum / samples) — Vec3::scale_sqrt (src/vec3.rs:119-125) folded into
  *     the store — straight into rank 0's image as each tile finishes: the gather happens inside the render kernel,
  *   - publishes "frame f done" in its progress word; rank 0's stream then waits for every rank's word.
+ * With RC_SPLIT_SAMPLES (every rank traces its samples of every pixel) the same protocol carries the REDUCE: a rank's
+ * kernel stores its partial sums into its own slot of the image (the frame holds one slot per rank and image:
+ * 2 * world * width * height * 12 bytes on rank 0), and rank 0, after the wait, adds the slots in rank order and takes
+ * sqrt(sum / samples) — deterministic, no ncclReduce.
  * Nothing but kernels and stream-ordered waits is enqueued: no collective library, no host synchronisation.
  * On rank 0, *d_rgb (if not NULL) receives the device pointer of the finished float image (stream-ordered: valid for
  * work enqueued on the context's stream BEFORE the next rc_render_frame — that call hands the image to the ranks for

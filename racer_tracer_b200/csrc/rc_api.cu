@@ -1016,6 +1016,7 @@ int rc_create(const int32_t* devices, int32_t n, rc_ctx** out) {
             cudaFuncGetAttributes(&fa, widen_kernel);
             cudaFuncGetAttributes(&fa, frame_wait_kernel);
             cudaFuncGetAttributes(&fa, frame_publish_kernel);
+            cudaFuncGetAttributes(&fa, sum_slots_kernel);
             cudaGetLastError();
         }
     }
@@ -1319,13 +1320,15 @@ static size_t frame_bytes(int width, int height, int world, size_t* image_floats
     size_t n = (size_t)width * height * 3;
     n = (n + 63) & ~(size_t)63;                       // images start on 256-byte boundaries
     *image_floats = n;
-    return 2 * n * sizeof(float) + (size_t)(world + 1) * 32 * sizeof(int);
+    // two images (they alternate), each with one slot per rank: the tile split stores finished pixels into slot 0;
+    // the sample split stores every rank's partial sums into its own slot, and rank 0 adds the slots up
+    return 2 * (size_t)world * n * sizeof(float) + (size_t)(world + 1) * 32 * sizeof(int);
 }
 
 static int frame_init(rc_ctx* ctx, rc_frame* f, void* base, int width, int height, int rank, int world, bool owner) {
     size_t nf = 0;
     frame_bytes(width, height, world, &nf);
-    f->base = (float*)base; f->image_floats = nf; f->words = (int*)(f->base + 2 * nf);
+    f->base = (float*)base; f->image_floats = nf; f->words = (int*)(f->base + 2 * (size_t)world * nf);
     f->width = width; f->height = height; f->rank = rank; f->world = world; f->owner = owner;
     if (cudaHostAlloc((void**)&f->timed_out, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return fail(RC_ERR_CUDA, "cudaHostAlloc failed");
     *f->timed_out = 0;
@@ -1377,7 +1380,8 @@ int rc_render_frame(rc_ctx* ctx, const rc_params* p, rc_frame* f, const float** 
     int rc = check_params(p);
     if (rc != RC_OK) return rc;
     if (std::find(ctx->frames.begin(), ctx->frames.end(), f) == ctx->frames.end()) return fail(RC_ERR_INVALID, "frame does not belong to this context");
-    if (p->split != RC_SPLIT_TILES || p->variant != RC_VARIANT_MEGAKERNEL) return fail(RC_ERR_INVALID, "rc_render_frame needs the tile split and the megakernel");
+    if (p->variant != RC_VARIANT_MEGAKERNEL) return fail(RC_ERR_INVALID, "rc_render_frame needs the megakernel");
+    const bool by_samples = p->split == RC_SPLIT_SAMPLES;
     if (p->width != f->width || p->height != f->height) return fail(RC_ERR_INVALID, "params and frame sizes differ");
     const int world = p->world > 0 ? p->world : 1;
     if (world != f->world || p->rank != f->rank) return fail(RC_ERR_INVALID, "params and frame rank / world differ");
@@ -1389,7 +1393,11 @@ int rc_render_frame(rc_ctx* ctx, const rc_params* p, rc_frame* f, const float** 
     DeviceState& d = ctx->devs[0];
     CUDA_TRY(cudaSetDevice(d.device));
     const int frame_no = ++f->frame_no;
-    float* image = f->base + (size_t)(frame_no & 1) * f->image_floats;
+    // slot 0 of this frame's image: where the finished pixels are (tile split: stored there by every rank's render
+    // kernel; sample split: summed there by rank 0 from the ranks' slots)
+    float* image = f->base + (size_t)(frame_no & 1) * f->world * f->image_floats;
+    // where THIS rank's kernel stores: finished pixels of its tiles into slot 0, or its partial sums into its own slot
+    float* target = by_samples ? image + (size_t)f->rank * f->image_floats : image;
     // The image of frame n was last used by frame n - 2: the others wait for rank 0 to release it.  When rank 0's
     // stream gets HERE, everything enqueued on it before this call has run: the wait for every rank's frame n - 1 and
     // whatever read the images of frames n - 1 and n - 2.  So both images are free — this frame's and the NEXT one's
@@ -1403,8 +1411,8 @@ int rc_render_frame(rc_ctx* ctx, const rc_params* p, rc_frame* f, const float** 
     }
     bool was_cancelled = false;
     ctx->overwrite = true;
-    ctx->final_scale = 1.0f / (float)p->samples;
-    rc = trace_share(ctx, p, image, cancel, was_cancelled);
+    ctx->final_scale = by_samples ? 0.0f : 1.0f / (float)p->samples;   // sample split: raw sums, the square root comes after the slots are added
+    rc = trace_share(ctx, p, target, cancel, was_cancelled);
     ctx->overwrite = false;
     ctx->final_scale = 0.0f;
     if (rc != RC_OK) return rc;
@@ -1413,6 +1421,14 @@ int rc_render_frame(rc_ctx* ctx, const rc_params* p, rc_frame* f, const float** 
         if (f->rank != 0) { frame_publish_kernel<<<1, 1, 0, d.stream>>>(f->words + 32 * f->rank, frame_no); extra = 2; }
         else { frame_wait_kernel<<<1, 32, 0, d.stream>>>(f->words, 1, world - 1, frame_no, f->timed_out); extra = 2; }
         CUDA_TRY(cudaGetLastError());
+    }
+    if (by_samples && f->rank == 0) {
+        // the reduce of the sample split: every rank's kernel has stored its partial sums into its slot of this image
+        // over NVLink; rank 0 adds the slots in rank order (deterministic) and takes sqrt(sum / samples) into slot 0
+        const size_t n = (size_t)p->width * p->height * 3;
+        sum_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(image, f->image_floats, world, n, 1.0f / (float)p->samples);
+        CUDA_TRY(cudaGetLastError());
+        extra += 1;
     }
     rc = finish_stats(ctx, p);
     if (rc != RC_OK) return rc;

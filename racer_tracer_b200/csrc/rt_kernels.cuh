@@ -919,6 +919,14 @@ __global__ void frame_wait_kernel(const int* words, int first, int n, int target
     }
     __threadfence_system();
 }
+// slot 0 <- sqrt(scale * (slot 0 + slot 1 + ... + slot world-1)), element by element, slots added in rank order
+__global__ void sum_slots_kernel(float* __restrict__ image, size_t slot_floats, int world, size_t n, float scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = image[i];
+    for (int r = 1; r < world; ++r) s += image[(size_t)r * slot_floats + i];
+    image[i] = sqrtf(scale * s);
+}
 __global__ void widen_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (double)in[i];

@@ -136,6 +136,10 @@ def test_frame_api_with_one_rank_equals_rc_render(renderer, cfg):
         out = np.empty((h, w, 3))
         renderer.render_frame(harness.make_params(w, h, spp, 20, seed=seed, specialize=2), frame, out=out)
         outs.append(out)
+    # the sample split through the frame (one rank: its slot holds all the samples, rank 0's slot sum is a square root)
+    by_samples = np.empty((h, w, 3))
+    renderer.render_frame(harness.make_params(w, h, spp, 20, seed=3, specialize=2, split=capi.RC_SPLIT_SAMPLES), frame, out=by_samples)
+    assert np.allclose(by_samples, outs[2], rtol=3e-7, atol=1e-7), np.abs(by_samples - outs[2]).max()
     renderer.frame_close(frame)
     for seed, out in zip((1, 2, 3), outs):
         want = renderer.render(harness.make_params(w, h, spp, 20, seed=seed, specialize=2))

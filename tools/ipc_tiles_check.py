@@ -87,6 +87,18 @@ dist.barrier()
 if rank == 0:
     want = r.render(harness.make_params(w, h, spp, 20, seed=11, specialize=2))
     assert np.allclose(out, want, rtol=3e-7, atol=1e-7), np.abs(out - want).max()
+# ---- the sample split through the same frame: every rank traces ITS samples of every pixel and stores the partial
+# sums into its slot of rank 0's frame; rank 0 adds the slots in rank order.  Equal to the single-GPU render up to the
+# order of the fp32 additions.
+for seed in (21, 22, 23):
+    out = np.empty((h, w, 3), dtype=np.float64) if rank == 0 else None
+    p = harness.make_params(w, h, spp, 20, seed=seed, rank=rank, world=world, specialize=2, split=capi.RC_SPLIT_SAMPLES)
+    r.render_frame(p, frame, out=out)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        want = r.render(harness.make_params(w, h, spp, 20, seed=seed, specialize=2))
+        assert np.allclose(out, want, rtol=2e-6, atol=1e-6), f"sample-split frame seed {seed}: {np.abs(out - want).max()}"
 r.frame_close(frame)
 r.close()
 if rank == 0:
