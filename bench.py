@@ -269,15 +269,19 @@ def main():
 
     launches = [0]
 
-    # Every N (also 1), both splits: the whole exchange lives behind the ABI — rc_frame_create / rc_frame_open /
+    # Tile split (every N, also 1): the whole exchange lives behind the ABI — rc_frame_create / rc_frame_open /
     # rc_render_frame.  Rank 0 owns the frame (two images, alternating, one slot per rank each) and every rank maps it
-    # (CUDA IPC).  Tile split: the render kernel of every rank STORES sqrt(sum / spp) for its tiles into slot 0 over
-    # NVLink as they finish.  Sample split: it stores its partial sums into its own slot, and rank 0 adds the slots up.
-    # Either way a rank then publishes a progress word that rank 0's stream waits for; no collective library.
-    # bench.py only carries the 64-byte handle to the other ranks.  (RC_BENCH_NCCL_GATHER=1: the older form — local
-    # buffers summed with an NCCL reduce — for comparison.)
+    # (CUDA IPC); the render kernel of every rank STORES sqrt(sum / spp) for its tiles into slot 0 over NVLink as they
+    # finish, then publishes a progress word that rank 0's stream waits for; no collective library.  bench.py only
+    # carries the 64-byte handle to the other ranks.  (RC_BENCH_NCCL_GATHER=1: local buffers + an NCCL reduce instead.)
+    # Sample split: the same frame can carry the reduce (every rank stores its partial sums into its own slot, rank 0
+    # adds the slots up: RC_BENCH_FRAME_SAMPLES=1); the default is local buffers summed with an NCCL reduce.
     frame = None
-    if variant == capi.RC_VARIANT_MEGAKERNEL and not os.environ.get("RC_BENCH_NCCL_GATHER"):
+    # (the sample split takes the frame with RC_BENCH_FRAME_SAMPLES=1; by default it sums local buffers with an NCCL
+    # reduce, which measured 3 % faster on eight GPUs: 56.6 against 58.3 ms per clown frame)
+    use_frame = (split == capi.RC_SPLIT_TILES and not os.environ.get("RC_BENCH_NCCL_GATHER")) or \
+                (split == capi.RC_SPLIT_SAMPLES and bool(os.environ.get("RC_BENCH_FRAME_SAMPLES")))
+    if variant == capi.RC_VARIANT_MEGAKERNEL and use_frame:
         if rank == 0:
             frame, handle = r.frame_create(w, h, world)
             hbuf = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")

@@ -140,6 +140,7 @@ struct rc_ctx {
     int prims_mask = 0xF;        // primitive kinds the scene uses (bit RT_PRIM_*; moving spheres count as spheres)
     std::string spec_source;     // generated source of the scene-specialised kernel ("" = not generated yet)
     int spec_rounds = 10;        // Philox rounds spec_source was generated for
+    bool spread_stores = false;  // set by rc_render_frame for a sample-split frame of several ranks (see trace_share)
     std::vector<LbvhObject> objects, objects_next;   // top-level objects of the uploaded scene (rc_build_lbvh)
     std::vector<int> prim_order;       // device primitive i = uploaded primitive prim_order[i] (empty: identity)
     bool lbvh = false;
@@ -478,7 +479,9 @@ int trace_share(rc_ctx* ctx, const rc_params* p, float* accum0, const volatile i
             // runs for 4 ms, and while the last ones finish the machine drains.  Two slices (2/3 and 1/3 of the samples)
             // halve that: 32.37 against 32.63 ms for the whole frame on one GPU (tools/time_share.py 1); three or more
             // cost more in per-CTA set-up than they save.
-            if (sl < 2 && s1 - s0 >= 512) sl = 2;
+            // (not for a sample-split frame of several ranks: there the kernel's own stores go to rank 0 over NVLink and
+            // should be spread over the frame, not issued by reduce_slices_kernel in one burst at its end)
+            if (sl < 2 && s1 - s0 >= 512 && !ctx->spread_stores) sl = 2;
             if (const char* e = std::getenv("RC_SLICES")) sl = std::atoll(e);
             // Slice lengths: halving (n/2, n/4, .., the last two equal) from five slices on, linearly decreasing below —
             // with two or three slices the halving scheme's last slice is too long a tail.  One rank's share of the
@@ -1412,7 +1415,9 @@ int rc_render_frame(rc_ctx* ctx, const rc_params* p, rc_frame* f, const float** 
     bool was_cancelled = false;
     ctx->overwrite = true;
     ctx->final_scale = by_samples ? 0.0f : 1.0f / (float)p->samples;   // sample split: raw sums, the square root comes after the slots are added
+    ctx->spread_stores = by_samples && world > 1;
     rc = trace_share(ctx, p, target, cancel, was_cancelled);
+    ctx->spread_stores = false;
     ctx->overwrite = false;
     ctx->final_scale = 0.0f;
     if (rc != RC_OK) return rc;
